@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config, one JSON line.
+
+Workload (configs[1]): synthetic 1 Mi-triangle soup (rtbvh_b200/workloads.soup, seed 0x50A90002), binned-SAH
+Bvh collapsed to an Mbvh, primary rays closest-hit: 1000x1000 pinhole frames from (0.5, 0.5, -1.5), 50 degree
+fov, hashed sub-pixel jitter per (frame, pixel).  One STEP = `--frames-per-step` frames (default 8 = 8 M rays,
+256 MB of rays: larger than the 126 MB L2, so no flush is needed between steps).  With the default
+--steps 125 the timed region traces exactly the config's 1 B rays.
+
+  value  : Mrays/s, rays already resident in HBM, one traversal kernel launch per step, CUDA events on the
+           launching stream, max over ranks.
+  e2e    : Mrays/s through the host-buffer C-ABI call (rtbvh_gpu_intersect): pinned host rays -> H2D ->
+           kernel -> D2H hits inside the timed region every step.
+  roofline.achieved : algorithmic bytes per ray (32 + 8 + 128*n_m + 40*n_p; n_m, n_p = node visits / triangle
+           tests per ray counted by the instrumented CPU oracle on a sample of the same rays, SURVEY.md
+           section 8d) x rays per launch / mean launch duration; peak = MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline : the CPU oracle (a C++ port of the reference's loop, OpenMP over chunks of 1000 rays like
+           examples/benchmark.rs:25) on all host cores, on a bounded sample of the same rays.
+
+`--impl reference` times that CPU port alone (the reference itself is Rust and cannot be built in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from rtbvh_b200 import workloads as W  # noqa: E402
+
+METRIC = "Mrays/s closest-hit (Mbvh, binned SAH, 1Mi-triangle soup, primary rays)"
+WIDTH = HEIGHT = 1000
+N_TRIS = 1 << 20
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene_host():
+    """Triangles + tree for config 2.  Returns (tris, bvh arrays, mbvh arrays, info)."""
+    tris = W.soup(N_TRIS)
+    return tris
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle): used as cpu_baseline on rank 0 and as the whole of --impl reference
+# ------------------------------------------------------------------------------------------------
+def oracle_tree(tris):
+    from oracle import oracle as O
+    aabbs, centers = O.prims_from_triangles(tris)
+    t0 = time.time()
+    rc, bvh = O.build(O.BINNED_SAH, aabbs, centers, 1)
+    assert rc == 0
+    build_s = time.time() - t0
+    m = bvh.collapse()
+    return O, bvh, m, build_s
+
+
+def cpu_sample_rate(O, m, tris, rays, target_s=12.0):
+    """Times the oracle on a bounded sample; returns (Mrays/s, n_sample, counters per ray)."""
+    threads = O.num_threads()
+    probe = rays[: min(len(rays), 200_000)]
+    _, ms, _ = O.trace(m, tris, probe, threads=threads)
+    rate = len(probe) / max(ms, 1e-3) * 1e3
+    n = int(min(len(rays), max(len(probe), rate * target_s)))
+    _, ms, _ = O.trace(m, tris, rays[:n], threads=threads)
+    _, _, cnt = O.trace(m, tris, rays[: min(n, 1_000_000)], threads=threads, counters=True)
+    nc = min(n, 1_000_000)
+    return n / ms / 1e3, n, {k: cnt[k] / nc for k in ("node_visits", "prim_tests")}, cnt["max_stack"], threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tris = build_scene_host()
+    O, bvh, m, build_s = oracle_tree(tris)
+    cam = W.soup_camera(WIDTH, HEIGHT)
+    rows = 250  # each step: a bounded sample of the frame (250 rows x 1000 px = 250 k rays)
+    threads = O.num_threads()
+
+    def step(k):
+        rays = W.camera_rays(cam, y0=(k * rows) % HEIGHT, y1=(k * rows) % HEIGHT + rows, jitter_seed=W.SEED_SOUP,
+                             frame=k * rows // HEIGHT)
+        _, ms, _ = O.trace(m, tris, rays, threads=threads)
+        return len(rays), ms
+
+    for k in range(args.warmup):
+        step(k)
+    n_tot, ms_tot = 0, 0.0
+    for k in range(args.steps):
+        n, ms = step(args.warmup + k)
+        n_tot += n
+        ms_tot += ms
+    v = n_tot / ms_tot / 1e3
+    sample = f"{rows}x{WIDTH} jittered camera rays per step ({n_tot} rays total), Mbvh single-ray closest hit"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "soup-1Mi-tris binned-SAH Mbvh primary rays closest-hit (BASELINE configs[1])",
+                   "note": "reference is Rust and cannot be built in this image (no rustc/cargo): this is the C++ "
+                           "oracle port of its loop, OpenMP dynamic chunks of 1000 rays like benchmark.rs:25"},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "oracle_build_ms_per_mtri": build_s * 1e3 / (N_TRIS / 1e6),
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from rtbvh_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if api.device_count() == 0:
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    api.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    tris = build_scene_host()
+    info = {}
+    bvh, mbvh, info = build_trees(api, tris, info, rank)
+    scene = api.Scene(tris, bvh=None, mbvh=mbvh)
+
+    fps = args.frames_per_step
+    rays_per_step = fps * WIDTH * HEIGHT
+    cam = W.soup_camera(WIDTH, HEIGHT)
+    free_b, _ = torch.cuda.mem_get_info()
+    ring = int(max(2, min(args.steps + args.warmup, (free_b * 0.6) // (rays_per_step * 40))))
+    stream = torch.cuda.current_stream().cuda_stream
+    d_rays = [torch.empty(rays_per_step * 8, dtype=torch.float32, device="cuda") for _ in range(ring)]
+    d_hits = [torch.empty(rays_per_step * 2, dtype=torch.float32, device="cuda") for _ in range(ring)]
+    # weak scaling: rank r traces its own frames (global step index = rank * steps + k)
+    for b in range(ring):
+        g = (rank * (args.steps + args.warmup) + b) * fps
+        for f in range(fps):
+            off = f * WIDTH * HEIGHT * 8
+            api.generate_camera_rays_device(cam, 0, HEIGHT, d_rays[b][off:], jitter_seed=W.SEED_SOUP, frame=g + f,
+                                            stream=stream)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k):
+        b = k % ring
+        scene.intersect_device(d_rays[b], rays_per_step, d_hits[b], api.TREE_MBVH, stream=stream)
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if scene.stack_overflowed():
+        raise RuntimeError("traversal stack overflow")
+
+    # ---- e2e: host buffers through rtbvh_gpu_intersect -------------------------------------------
+    n_host = min(3, ring)
+    h_rays = [torch.empty(rays_per_step * 8, dtype=torch.float32).pin_memory() for _ in range(n_host)]
+    h_hits = [torch.empty(rays_per_step * 2, dtype=torch.float32).pin_memory() for _ in range(n_host)]
+    for b in range(n_host):
+        h_rays[b].copy_(d_rays[b])
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for k in range(min(2, args.warmup)):
+        scene.intersect_ptr(h_rays[k % n_host].data_ptr(), rays_per_step, h_hits[k % n_host].data_ptr(), api.TREE_MBVH)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        scene.intersect_ptr(h_rays[k % n_host].data_ptr(), rays_per_step, h_hits[k % n_host].data_ptr(), api.TREE_MBVH)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    # the host-buffer path must agree with the resident path on the same rays
+    same = bool(torch.equal(h_hits[0].view(torch.int32), d_hits[0].cpu().view(torch.int32)))
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        total_rays = world * args.steps * rays_per_step
+        value = total_rays / ms / 1e3
+        e2e = world * e2e_steps * rays_per_step / e2e_ms / 1e3
+        # ---- CPU baseline + algorithmic bytes from the instrumented oracle on a sample of step 0's rays
+        cpu = None
+        bytes_per_ray, nm, npr = None, None, None
+        if not args.no_cpu:
+            from oracle import oracle as O
+            host_rays = d_rays[0][: WIDTH * HEIGHT * 8].cpu().numpy().view(api.RAY_DTYPE).reshape(-1)
+            otree = O.Mbvh(mbvh.nodes.copy(), mbvh.indices.copy())
+            rate, n_s, per_ray, max_stack, threads = cpu_sample_rate(O, otree, tris, host_rays)
+            nm, npr = per_ray["node_visits"], per_ray["prim_tests"]
+            bytes_per_ray = 32 + 8 + 128 * nm + 40 * npr
+            cpu = {"value": rate, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                   "sample": f"first {n_s} rays of frame 0 (same rays as the GPU step), Mbvh single-ray closest hit, "
+                             f"OpenMP dynamic chunks of 1000"}
+            # parity spot check inside the bench: oracle vs GPU on the sample
+            want, _, _ = O.trace(otree, tris, host_rays[:200_000], threads=threads)
+            got = d_hits[0][: 200_000 * 2].cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
+            info["parity_sample_bit_exact"] = bool(np.array_equal(want, got))
+            info["oracle_max_stack"] = int(max_stack)
+        peak, peak_src = measured_peak_gbs()
+        roof = None
+        if bytes_per_ray is not None:
+            launch_ms = ms / args.steps
+            achieved = bytes_per_ray * rays_per_step / (launch_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": info.get("ncu_dram_bytes_per_launch"), "peak_source": peak_src,
+                    "bytes_per_ray": bytes_per_ray, "node_visits_per_ray": nm, "tri_tests_per_ray": npr,
+                    "kernel": "trace_single_kernel<MBVH, closest>", "launch_ms": launch_ms}
+        out = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "soup-1Mi-tris binned-SAH Mbvh primary rays closest-hit (BASELINE configs[1])",
+                       "rays_per_step": rays_per_step, "frames_per_step": fps, "ray_ring_batches": ring,
+                       "l2": "inputs larger than L2 (256 MB rays per step, distinct buffers)", **info},
+            "clocks": clocks, "gpu_launches": args.steps,
+            "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": rays_per_step * 32,
+                    "d2h_bytes_per_step": rays_per_step * 8, "steps": e2e_steps, "host_equals_resident": same},
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    scene.free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def build_trees(api, tris, info, rank):
+    """Tree for the bench.  The GPU builder (create_bvh -> create_mbvh) is the product path; while it is not
+    available the reference-format tree built by the CPU oracle is uploaded unchanged (north_star check 1)."""
+    try:
+        from rtbvh_b200 import prims
+        aabbs, centers = prims.from_triangles(tris)
+        t0 = time.perf_counter()
+        bvh = api.Builder(aabbs, centers, 1).construct_binned_sah()
+        t1 = time.perf_counter()
+        mbvh = api.Mbvh.construct(bvh)
+        t2 = time.perf_counter()
+        info.update(tree="gpu-built: create_bvh(BinnedSAH) + create_mbvh",
+                    build_ms_per_mtri=(t1 - t0) * 1e3 / (len(tris) / 1e6), collapse_ms=(t2 - t1) * 1e3)
+        return bvh, mbvh, info
+    except (ImportError, api.RtbvhError) as e:
+        log(f"[bench] GPU builder unavailable ({e}); uploading the oracle-built reference-format tree")
+    O, obvh, om, build_s = oracle_tree(tris)
+    info.update(tree="reference-format tree built by the CPU oracle, uploaded unchanged",
+                oracle_build_ms_per_mtri=build_s * 1e3 / (len(tris) / 1e6))
+    return api.Bvh.from_arrays(obvh.nodes, obvh.indices), api.Mbvh.from_arrays(om.nodes, om.indices), info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=125)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / roofline sample (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,122 @@
+/* rtbvh_gpu.h — batch / device extension of the rtbvh C ABI (SURVEY.md §8b "required extension").
+ *
+ * The reference's traversal API is a host iterator that yields one candidate primitive at a time to
+ * user code (src/iter.rs, src/iter_indices.rs; FFI callback rtbvh_ffi/src/lib.rs:551-835).  A GPU
+ * cannot call back into host code per candidate, so the GPU path is a BATCH of the loop every caller
+ * of the reference writes (examples/benchmark.rs:25-31 / :55-61, rtbvh_ffi/src/lib.rs:572-576):
+ *
+ *     for (prim, ray) in tree.iter(ray) { SpatialTriangle::intersect(prim, ray) }       closest hit
+ *     ... with `break` on the first success                                              any hit
+ *
+ * with the canonical triangle tests of src/builders/spatial_sah.rs:131-244.  Visitation order,
+ * predicates and floating-point arithmetic are the reference's (no FMA contraction), so t is
+ * bit-identical to the host iterators and the primitive id is the lowest id among exactly equal t.
+ *
+ * Plain C: pointers and sizes only.  `*_device` variants take device pointers and a CUstream /
+ * cudaStream_t (as void*) and return without synchronising.
+ */
+#ifndef RTBVH_GPU_H
+#define RTBVH_GPU_H
+
+#include "rtbvh.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_NO_HIT 0xFFFFFFFFu
+
+/* First 32 bytes of rtbvh::Ray (src/ray.rs:9-16): origin, t_min, direction, t.  Ray::new's derived
+ * fields (inv_direction = 1/direction, signs) are recomputed on the device (src/ray.rs:166-182).
+ * Use t_min = 1e-4f and t = 1e34f for Ray::new's defaults. */
+typedef struct RTRay {
+  float origin[3];
+  float t_min;
+  float direction[3];
+  float t;
+} RTRay;
+
+/* Result of one ray: t as left in ray.t by the reference loop (unchanged input t on a miss) and the
+ * primitive that produced it (RT_NO_HIT on a miss). */
+typedef struct RTHit {
+  float t;
+  uint32_t prim;
+} RTHit;
+
+/* The seven SoA inputs of intersect_packet / intersect_mbvh_packet (rtbvh_ffi/src/lib.rs:599-608);
+ * == rtbvh::RayPacket4 (src/ray.rs:47-61) without the derived inv_direction_*. */
+typedef struct RTRayPacket4 {
+  float origin_x[4], origin_y[4], origin_z[4];
+  float direction_x[4], direction_y[4], direction_z[4];
+  float t[4];
+} RTRayPacket4;
+
+typedef struct RTHitPacket4 {
+  float t[4];
+  uint32_t prim[4];
+} RTHitPacket4;
+
+typedef enum RTTreeKind {
+  RT_TREE_BVH = 0,  /* rtbvh::Bvh: BvhIndexIterator / BvhPacketIndexIterator semantics  */
+  RT_TREE_MBVH = 1, /* rtbvh::Mbvh: MbvhIndexIterator / MbvhPacketIndexIterator semantics */
+} RTTreeKind;
+
+/* A scene resident on one GPU: the tree(s) uploaded UNCHANGED plus the triangles, pre-gathered into
+ * leaf order.  Opaque handle (0 is never valid). */
+typedef uint64_t RTGpuScene;
+
+/* ---- devices ---------------------------------------------------------------------------------- */
+int rtbvh_gpu_device_count(void);                 /* 0 when no CUDA device / driver */
+ResultCode rtbvh_gpu_set_device(int device);      /* device used by subsequent calls of this thread */
+const char *rtbvh_gpu_last_error(void);           /* message of the last Error on this thread */
+
+/* ---- scenes ----------------------------------------------------------------------------------- */
+/* Uploads host trees (either may be null, not both) and triangles.  The RTBvh / RTMbvh structs are
+ * trusted like the reference's intersect* trust them (no table lookup): any host arrays in the
+ * reference's node formats work, e.g. a reference-built tree.  `vertices`: 3 * triangle_count
+ * vertices, `vertex_stride` bytes apart (12 or 16), triangle i = vertices 3i, 3i+1, 3i+2 — the
+ * layout of rtbvh_ffi's RTTriangleWrapper (rtbvh_ffi/src/lib.rs:258-330) with triangle_stride =
+ * 3 * vertex_stride. */
+ResultCode rtbvh_gpu_scene_create(const RTBvh *bvh, const RTMbvh *mbvh, const float *vertices, size_t vertex_stride,
+                                  size_t triangle_count, RTGpuScene *scene);
+ResultCode rtbvh_gpu_scene_free(RTGpuScene scene);
+
+/* ---- closest hit / any hit, host buffers (H2D + kernels + D2H inside the call) ------------------ */
+ResultCode rtbvh_gpu_intersect(RTGpuScene scene, RTTreeKind tree, const RTRay *rays, size_t ray_count, RTHit *hits);
+ResultCode rtbvh_gpu_occluded(RTGpuScene scene, RTTreeKind tree, const RTRay *rays, size_t ray_count,
+                              uint8_t *occluded);
+/* Packets follow SpatialTriangle::intersect4 (eps 1e-6, t >= t_min): pass t_min = 1e-4f to match
+ * examples/benchmark.rs:58.  occluded: 4 bytes per packet. */
+ResultCode rtbvh_gpu_intersect_packets(RTGpuScene scene, RTTreeKind tree, const RTRayPacket4 *packets,
+                                       size_t packet_count, float t_min, RTHitPacket4 *hits);
+ResultCode rtbvh_gpu_occluded_packets(RTGpuScene scene, RTTreeKind tree, const RTRayPacket4 *packets,
+                                      size_t packet_count, float t_min, uint8_t *occluded);
+
+/* ---- same, device-resident buffers, asynchronous on `stream` ------------------------------------ */
+ResultCode rtbvh_gpu_intersect_device(RTGpuScene scene, RTTreeKind tree, const RTRay *d_rays, size_t ray_count,
+                                      RTHit *d_hits, void *stream);
+ResultCode rtbvh_gpu_occluded_device(RTGpuScene scene, RTTreeKind tree, const RTRay *d_rays, size_t ray_count,
+                                     uint8_t *d_occluded, void *stream);
+ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene scene, RTTreeKind tree, const RTRayPacket4 *d_packets,
+                                              size_t packet_count, float t_min, RTHitPacket4 *d_hits, void *stream);
+ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene scene, RTTreeKind tree, const RTRayPacket4 *d_packets,
+                                             size_t packet_count, float t_min, uint8_t *d_occluded, void *stream);
+/* Nonzero if any ray of a previous *_device call on this scene needed more than the 64-entry
+ * traversal stack (the reference's stack has 32 entries and panics / is UB beyond, src/iter.rs:25).
+ * Synchronises the device.  Host-buffer calls return Error in that case. */
+ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene scene, uint32_t *overflowed);
+
+/* ---- workload helper: CameraView3D::generate_ray on the device (shared/src/lib.rs:157-165) ----- */
+/* Writes width*rows rays for pixel rows [row0, row0+rows): u = (x + jx) / width, v = (y + jy) / height,
+ * direction = normalize(p1 + u*right + v*up - pos); (jx, jy) = 0 when jitter_seed == 0, else
+ * splitmix64-hashed sub-pixel offsets of (jitter_seed, frame, pixel).  t_min = 1e-4, t = 1e34. */
+ResultCode rtbvh_gpu_generate_camera_rays_device(const float pos[3], const float p1[3], const float right[3],
+                                                 const float up[3], uint32_t width, uint32_t height, uint32_t row0,
+                                                 uint32_t rows, uint64_t jitter_seed, uint64_t frame, RTRay *d_rays,
+                                                 void *stream);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* RTBVH_GPU_H */

@@ -1,0 +1,319 @@
+// capi.cu — the extern "C" boundary of librtbvh_rs.so: scenes and the batch traversal entry points of
+// include/rtbvh_gpu.h.  (The legacy rtbvh_ffi entry points of include/rtbvh.h live in legacy.cu.)
+//
+// Ownership model mirrors rtbvh_ffi's StructureManager (rtbvh_ffi/src/lib.rs:12-127): a process-global
+// table guarded by a reader/writer lock, ids never reused.
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "build.cuh"
+#include "traverse.cuh"
+
+using namespace rtb;
+
+namespace rtb {
+thread_local std::string g_last_error;
+
+ResultCode fail(const char* what, cudaError_t e) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return Error;
+}
+ResultCode fail(const char* what) {
+    g_last_error = what;
+    return Error;
+}
+}  // namespace rtb
+
+#define RTB_CUDA(call)                                  \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return fail(#call, e__); \
+    } while (0)
+
+namespace {
+
+constexpr int kPipeStreams = 3;                  // H2D / kernel / D2H of consecutive chunks overlap
+constexpr size_t kChunkRays = size_t(1) << 21;   // 2 Mi rays (64 MiB of RTRay) per pipeline stage
+
+struct Scene {
+    int device = 0;
+    DeviceTree bvh{nullptr, 0, nullptr, 0};
+    DeviceTree mbvh{nullptr, 0, nullptr, 0};
+    void* d_bvh_nodes = nullptr;
+    void* d_mbvh_nodes = nullptr;
+    TriRec* d_tris_bvh = nullptr;   // leaf order of the Bvh's indices
+    TriRec* d_tris_mbvh = nullptr;  // leaf order of the Mbvh's indices (may alias d_tris_bvh)
+    uint32_t* d_overflow = nullptr;
+    // host-buffer pipeline (lazily created)
+    cudaStream_t streams[kPipeStreams] = {nullptr, nullptr, nullptr};
+    void* d_in[kPipeStreams] = {nullptr, nullptr, nullptr};
+    void* d_out[kPipeStreams] = {nullptr, nullptr, nullptr};
+    std::mutex pipe_mutex;
+
+    ~Scene() {
+        cudaSetDevice(device);
+        for (int i = 0; i < kPipeStreams; i++) {
+            if (streams[i]) cudaStreamDestroy(streams[i]);
+            cudaFree(d_in[i]);
+            cudaFree(d_out[i]);
+        }
+        cudaFree(d_bvh_nodes);
+        cudaFree(d_mbvh_nodes);
+        if (d_tris_mbvh != d_tris_bvh) cudaFree(d_tris_mbvh);
+        cudaFree(d_tris_bvh);
+        cudaFree(d_overflow);
+    }
+};
+
+struct SceneTable {
+    std::shared_mutex mu;
+    std::vector<std::shared_ptr<Scene>> scenes;  // index = handle - 1; freed entries become null
+} g_scenes;
+
+std::shared_ptr<Scene> get_scene(RTGpuScene h) {
+    std::shared_lock<std::shared_mutex> lk(g_scenes.mu);
+    if (h == 0 || h > g_scenes.scenes.size()) return nullptr;
+    return g_scenes.scenes[h - 1];
+}
+
+const DeviceTree* pick_tree(const Scene& s, RTTreeKind kind) {
+    const DeviceTree* t = kind == RT_TREE_MBVH ? &s.mbvh : (kind == RT_TREE_BVH ? &s.bvh : nullptr);
+    if (!t || !t->nodes) return nullptr;
+    return t;
+}
+
+ResultCode ensure_pipeline(Scene& s) {
+    if (s.streams[0]) return Ok;
+    for (int i = 0; i < kPipeStreams; i++) {
+        RTB_CUDA(cudaStreamCreateWithFlags(&s.streams[i], cudaStreamNonBlocking));
+        RTB_CUDA(cudaMalloc(&s.d_in[i], kChunkRays * sizeof(RTRay)));  // a packet chunk is kChunkRays/4 * 112 B < this
+        RTB_CUDA(cudaMalloc(&s.d_out[i], kChunkRays * sizeof(RTHit)));
+    }
+    return Ok;
+}
+
+// One host-buffer batch: chunks flow through kPipeStreams streams, each doing H2D -> kernel -> D2H.
+// unit_in / unit_out are bytes per ray (single) or per packet; rays_per_unit is 1 or 4.
+template <class Launch>
+ResultCode run_host_batch(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit,
+                          void* out, Launch&& launch) {
+    if (units == 0) return Ok;
+    if (!in || !out) return fail("null host buffer");
+    std::lock_guard<std::mutex> lk(s.pipe_mutex);
+    RTB_CUDA(cudaSetDevice(s.device));
+    if (ensure_pipeline(s) != Ok) return Error;
+    RTB_CUDA(cudaMemsetAsync(s.d_overflow, 0, sizeof(uint32_t), s.streams[0]));
+    RTB_CUDA(cudaStreamSynchronize(s.streams[0]));
+    const size_t chunk_units = kChunkRays / rays_per_unit;
+    size_t done = 0;
+    for (int c = 0; done < units; c++) {
+        const int k = c % kPipeStreams;
+        const size_t m = units - done < chunk_units ? units - done : chunk_units;
+        cudaStream_t st = s.streams[k];
+        RTB_CUDA(cudaMemcpyAsync(s.d_in[k], (const char*)in + done * unit_in, m * unit_in, cudaMemcpyHostToDevice, st));
+        RTB_CUDA(launch(s.d_in[k], m, s.d_out[k], st));
+        RTB_CUDA(cudaMemcpyAsync((char*)out + done * unit_out, s.d_out[k], m * unit_out, cudaMemcpyDeviceToHost, st));
+        done += m;
+    }
+    for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s.streams[i]));
+    uint32_t ovf = 0;
+    RTB_CUDA(cudaMemcpy(&ovf, s.d_overflow, sizeof(ovf), cudaMemcpyDeviceToHost));
+    if (ovf) return fail("traversal stack overflow (> 64 entries)");
+    return Ok;
+}
+
+ResultCode upload(void** dst, const void* src, size_t bytes) {
+    RTB_CUDA(cudaMalloc(dst, bytes ? bytes : 16));
+    if (bytes) RTB_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return Ok;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtbvh_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+ResultCode rtbvh_gpu_set_device(int device) {
+    RTB_CUDA(cudaSetDevice(device));
+    return Ok;
+}
+
+const char* rtbvh_gpu_last_error(void) { return g_last_error.c_str(); }
+
+ResultCode rtbvh_gpu_scene_create(const RTBvh* bvh, const RTMbvh* mbvh, const float* vertices, size_t vertex_stride,
+                                  size_t triangle_count, RTGpuScene* scene) {
+    if (!scene || !vertices || (!bvh && !mbvh)) return fail("rtbvh_gpu_scene_create: null argument");
+    if (vertex_stride != 12 && vertex_stride != 16) return fail("vertex_stride must be 12 or 16 bytes");
+    if (bvh && (!bvh->nodes || !bvh->indices)) return fail("RTBvh with null pointers");
+    if (mbvh && (!mbvh->nodes || !mbvh->indices)) return fail("RTMbvh with null pointers");
+    if (rtbvh_gpu_device_count() == 0) return fail("no CUDA device: the traversal path has no CPU fallback");
+    auto s = std::make_shared<Scene>();
+    RTB_CUDA(cudaGetDevice(&s->device));
+    RTB_CUDA(cudaMalloc(&s->d_overflow, sizeof(uint32_t)));
+    RTB_CUDA(cudaMemset(s->d_overflow, 0, sizeof(uint32_t)));
+    float* d_verts = nullptr;
+    const size_t vbytes = triangle_count * 3 * vertex_stride;
+    if (upload((void**)&d_verts, vertices, vbytes) != Ok) return Error;
+    auto gather = [&](const uint32_t* indices, uint32_t index_count, TriRec** out) -> ResultCode {
+        uint32_t* d_idx = nullptr;
+        if (upload((void**)&d_idx, indices, (size_t)index_count * 4) != Ok) return Error;
+        RTB_CUDA(cudaMalloc((void**)out, (size_t)(index_count ? index_count : 1) * sizeof(TriRec)));
+        RTB_CUDA(launch_gather_tris(d_verts, (uint32_t)(vertex_stride / 4), d_idx, index_count, (uint32_t)triangle_count,
+                                    *out, 0));
+        RTB_CUDA(cudaDeviceSynchronize());
+        cudaFree(d_idx);
+        return Ok;
+    };
+    ResultCode rc = Ok;
+    if (bvh) {
+        rc = upload(&s->d_bvh_nodes, bvh->nodes, (size_t)bvh->node_count * sizeof(RTBvhNode));
+        if (rc == Ok) rc = gather(bvh->indices, bvh->index_count, &s->d_tris_bvh);
+        s->bvh = DeviceTree{(const float4*)s->d_bvh_nodes, bvh->node_count, s->d_tris_bvh, bvh->index_count};
+    }
+    if (rc == Ok && mbvh) {
+        rc = upload(&s->d_mbvh_nodes, mbvh->nodes, (size_t)mbvh->node_count * sizeof(RTMbvhNode));
+        const bool same = bvh && bvh->index_count == mbvh->index_count &&
+                          (bvh->indices == mbvh->indices ||
+                           std::memcmp(bvh->indices, mbvh->indices, (size_t)bvh->index_count * 4) == 0);
+        if (rc == Ok) {
+            if (same)
+                s->d_tris_mbvh = s->d_tris_bvh;  // Mbvh keeps a clone of the Bvh's prim_indices (src/bvh.rs:399-403)
+            else
+                rc = gather(mbvh->indices, mbvh->index_count, &s->d_tris_mbvh);
+        }
+        s->mbvh = DeviceTree{(const float4*)s->d_mbvh_nodes, mbvh->node_count, s->d_tris_mbvh, mbvh->index_count};
+    }
+    cudaFree(d_verts);
+    if (rc != Ok) return rc;
+    std::unique_lock<std::shared_mutex> lk(g_scenes.mu);
+    g_scenes.scenes.push_back(s);
+    *scene = (RTGpuScene)g_scenes.scenes.size();
+    return Ok;
+}
+
+ResultCode rtbvh_gpu_scene_free(RTGpuScene h) {
+    std::unique_lock<std::shared_mutex> lk(g_scenes.mu);
+    if (h == 0 || h > g_scenes.scenes.size() || !g_scenes.scenes[h - 1]) return fail("unknown scene");
+    g_scenes.scenes[h - 1].reset();
+    return Ok;
+}
+
+// ---- device-resident, asynchronous ---------------------------------------------------------------
+ResultCode rtbvh_gpu_intersect_device(RTGpuScene h, RTTreeKind tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
+                                      void* stream) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    RTB_CUDA(launch_trace_single(*t, tree, false, d_rays, n, d_hits, nullptr, s->d_overflow, (cudaStream_t)stream));
+    return Ok;
+}
+ResultCode rtbvh_gpu_occluded_device(RTGpuScene h, RTTreeKind tree, const RTRay* d_rays, size_t n, uint8_t* d_occ,
+                                     void* stream) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    RTB_CUDA(launch_trace_single(*t, tree, true, d_rays, n, nullptr, d_occ, s->d_overflow, (cudaStream_t)stream));
+    return Ok;
+}
+ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* d_packets, size_t n,
+                                              float t_min, RTHitPacket4* d_hits, void* stream) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    RTB_CUDA(launch_trace_packets(*t, tree, false, d_packets, n, t_min, d_hits, nullptr, s->d_overflow, (cudaStream_t)stream));
+    return Ok;
+}
+ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* d_packets, size_t n,
+                                             float t_min, uint8_t* d_occ, void* stream) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    RTB_CUDA(launch_trace_packets(*t, tree, true, d_packets, n, t_min, nullptr, d_occ, s->d_overflow, (cudaStream_t)stream));
+    return Ok;
+}
+ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene h, uint32_t* overflowed) {
+    auto s = get_scene(h);
+    if (!s || !overflowed) return fail("unknown scene");
+    RTB_CUDA(cudaSetDevice(s->device));
+    RTB_CUDA(cudaDeviceSynchronize());
+    RTB_CUDA(cudaMemcpy(overflowed, s->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    RTB_CUDA(cudaMemset(s->d_overflow, 0, sizeof(uint32_t)));
+    return Ok;
+}
+
+// ---- host buffers ------------------------------------------------------------------------------
+ResultCode rtbvh_gpu_intersect(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, RTHit* hits) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    return run_host_batch(*s, rays, n, sizeof(RTRay), sizeof(RTHit), 1, hits,
+                          [&](void* din, size_t m, void* dout, cudaStream_t st) {
+                              return launch_trace_single(*t, tree, false, (const RTRay*)din, m, (RTHit*)dout, nullptr,
+                                                         s->d_overflow, st);
+                          });
+}
+ResultCode rtbvh_gpu_occluded(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, uint8_t* occluded) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    return run_host_batch(*s, rays, n, sizeof(RTRay), 1, 1, occluded,
+                          [&](void* din, size_t m, void* dout, cudaStream_t st) {
+                              return launch_trace_single(*t, tree, true, (const RTRay*)din, m, nullptr, (uint8_t*)dout,
+                                                         s->d_overflow, st);
+                          });
+}
+ResultCode rtbvh_gpu_intersect_packets(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* packets, size_t n,
+                                       float t_min, RTHitPacket4* hits) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    return run_host_batch(*s, packets, n, sizeof(RTRayPacket4), sizeof(RTHitPacket4), 4, hits,
+                          [&](void* din, size_t m, void* dout, cudaStream_t st) {
+                              return launch_trace_packets(*t, tree, false, (const RTRayPacket4*)din, m, t_min,
+                                                          (RTHitPacket4*)dout, nullptr, s->d_overflow, st);
+                          });
+}
+ResultCode rtbvh_gpu_occluded_packets(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* packets, size_t n,
+                                      float t_min, uint8_t* occluded) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    return run_host_batch(*s, packets, n, sizeof(RTRayPacket4), 4, 4, occluded,
+                          [&](void* din, size_t m, void* dout, cudaStream_t st) {
+                              return launch_trace_packets(*t, tree, true, (const RTRayPacket4*)din, m, t_min, nullptr,
+                                                          (uint8_t*)dout, s->d_overflow, st);
+                          });
+}
+
+ResultCode rtbvh_gpu_generate_camera_rays_device(const float pos[3], const float p1[3], const float right[3],
+                                                 const float up[3], uint32_t width, uint32_t height, uint32_t row0,
+                                                 uint32_t rows, uint64_t jitter_seed, uint64_t frame, RTRay* d_rays,
+                                                 void* stream) {
+    if (!pos || !p1 || !right || !up || !d_rays) return fail("null argument");
+    RTB_CUDA(launch_camera_rays(pos, p1, right, up, width, height, row0, rows, jitter_seed, frame, d_rays,
+                                (cudaStream_t)stream));
+    return Ok;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// common.cuh — device-side types and exact-arithmetic helpers shared by the sm_100a kernels.
+//
+// All floating-point work on the hot path is written with the round-to-nearest intrinsics
+// (__fadd_rn / __fsub_rn / __fmul_rn / __fdiv_rn): nvcc never contracts those into FMA, which is
+// what keeps t bit-identical to the reference (Rust never fuses).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtbvh_gpu.h"
+
+namespace rtb {
+
+constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs
+constexpr uint32_t kNoHit = 0xFFFFFFFFu;
+
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// glam Vec4::min / max on x86-64 are _mm_min_ps / _mm_max_ps: `a < b ? a : b` (second operand when
+// either is NaN).  When no operand can be NaN this equals FMNMX (fminf/fmaxf) up to the sign of zero,
+// which no predicate on the path can observe.  EXACT = true is used only for rays whose slab
+// products can produce NaN (a zero / non-finite direction or origin component).
+template <bool EXACT>
+__device__ __forceinline__ float vmin(float a, float b) {
+    if (EXACT) return a < b ? a : b;
+    return fminf(a, b);
+}
+template <bool EXACT>
+__device__ __forceinline__ float vmax(float a, float b) {
+    if (EXACT) return a > b ? a : b;
+    return fmaxf(a, b);
+}
+
+// Triangle record in leaf order: 48 bytes = 3 x LDG.128.
+//   a = (v0.xyz, bitcast prim id), b = (v1 - v0, 0), c = (v2 - v0, 0)
+// edge1 / edge2 are the same single fp32 subtractions the reference performs per test
+// (src/builders/spatial_sah.rs:136-137), done once at upload.
+struct TriRec {
+    float4 a, b, c;
+};
+static_assert(sizeof(TriRec) == 48, "");
+
+struct DeviceTree {
+    const float4* nodes;      // Bvh: 2 float4 per node; Mbvh: 8 float4 per node
+    uint32_t node_count;
+    const TriRec* tris;       // index_count records (leaf order: tris[k] = triangle indices[k])
+    uint32_t index_count;
+};
+
+inline __host__ __device__ size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
+}  // namespace rtb

@@ -1,0 +1,568 @@
+// traverse.cu — closest-hit / any-hit traversal of Bvh and Mbvh for single rays and RayPacket4.
+//
+// Replaces, as ONE batched kernel per (tree, ray kind, query), the loop every caller of the reference
+// writes around its iterators:
+//     src/iter_indices.rs:69-106   BvhIndexIterator::next          + src/aabb.rs:146-181, src/bvh_node.rs:150-177
+//     src/iter_indices.rs:172-209  BvhPacketIndexIterator::next    + src/aabb.rs:218-244, src/bvh_node.rs:180-211
+//     src/iter_indices.rs:267-312  MbvhIndexIterator::next         + src/mbvh_node.rs:177-240
+//     src/iter_indices.rs:370-414  MbvhPacketIndexIterator::next   + src/mbvh_node.rs:243-295
+//     src/builders/spatial_sah.rs:131-163 / :165-244               SpatialTriangle::intersect / intersect4
+//     examples/benchmark.rs:25-31, :55-61; rtbvh_ffi/src/lib.rs:572-576 (callback `true` => break => any hit)
+//
+// Parity contract: identical visitation rules and predicates, fp32 with one
+// rounding per operation (the *_rn intrinsics never fuse).  Inside one node the reference's slot
+// results are frozen at node entry (`hit` is computed once, iter_indices.rs:281-285), so the leaf
+// slots of a node may be tested in any order without changing ray.t after the node; inner slots are
+// pushed in the reference's order (ids[3], ids[2], ids[1], ids[0] of its 5-comparator network).
+//
+// Layout / mapping (B200): one thread per ray (packets: 4 adjacent lanes = one RayPacket4, decisions
+// by quad vote).  Node = 8 x LDG.128 (Mbvh, 128 B = one L2 line) or a 64-byte adjacent child pair
+// (Bvh).  Triangles are 48-byte leaf-ordered records (3 x LDG.128, no index indirection).  The
+// traversal stack lives in shared memory, [entry][thread] so it is bank-conflict free.
+#include "traverse.cuh"
+
+namespace rtb {
+
+namespace {
+
+constexpr int kStackDepth = 64;  // reference: 32 (src/iter.rs:25); overflow is reported, never written
+constexpr int kBlock = 128;
+
+struct RayRegs {
+    float ox, oy, oz;
+    float dx, dy, dz;
+    float ix, iy, iz;
+    float t_min;   // single rays: ray.t_min; packets: the t_min argument of intersect4
+    float t;       // ray.t / packet.t[lane]
+    uint32_t prim;
+    bool exact;    // slab products may be NaN: use the SSE min/max operand rule
+    bool nan;      // origin or direction has a NaN component
+};
+
+__device__ __forceinline__ void finish_ray_setup(RayRegs& r) {
+    // Ray::new: inv_direction = Vec3::ONE / direction (src/ray.rs:179)
+    r.ix = fdiv(1.0f, r.dx);
+    r.iy = fdiv(1.0f, r.dy);
+    r.iz = fdiv(1.0f, r.dz);
+    r.prim = kNoHit;
+    const bool fin = isfinite(r.ox) && isfinite(r.oy) && isfinite(r.oz) && isfinite(r.dx) && isfinite(r.dy) &&
+                     isfinite(r.dz) && isfinite(r.ix) && isfinite(r.iy) && isfinite(r.iz);
+    r.exact = !fin;
+    r.nan = isnan(r.ox) || isnan(r.oy) || isnan(r.oz) || isnan(r.dx) || isnan(r.dy) || isnan(r.dz);
+}
+
+// ---- SpatialTriangle::intersect (single) / intersect4 lane (packet) -----------------------------
+// Returns true when the candidate was accepted with t < ray.t (ray.t shrunk).  Ties (t == ray.t from
+// an earlier accepted hit) only lower the reported id (north-star rule).
+template <bool PACKET>
+__device__ __forceinline__ bool tri_candidate(const TriRec* __restrict__ tris, int pos, RayRegs& r) {
+    const float4 A = __ldg(&tris[pos].a);
+    const float4 E1 = __ldg(&tris[pos].b);
+    const float4 E2 = __ldg(&tris[pos].c);
+    // h = direction x edge2
+    const float hx = fsub(fmul(r.dy, E2.z), fmul(E2.y, r.dz));
+    const float hy = fsub(fmul(r.dz, E2.x), fmul(E2.z, r.dx));
+    const float hz = fsub(fmul(r.dx, E2.y), fmul(E2.x, r.dy));
+    const float a = fadd(fadd(fmul(E1.x, hx), fmul(E1.y, hy)), fmul(E1.z, hz));
+    if (PACKET) {
+        if (!(a <= -1e-6f || a >= 1e-6f)) return false;  // spatial_sah.rs:191-196
+    } else {
+        if (a > -1e-5f && a < 1e-5f) return false;  // spatial_sah.rs:140-142
+    }
+    const float f = fdiv(1.0f, a);
+    const float sx = fsub(r.ox, A.x), sy = fsub(r.oy, A.y), sz = fsub(r.oz, A.z);
+    const float u = fmul(f, fadd(fadd(fmul(sx, hx), fmul(sy, hy)), fmul(sz, hz)));
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    // q = s x edge1
+    const float qx = fsub(fmul(sy, E1.z), fmul(E1.y, sz));
+    const float qy = fsub(fmul(sz, E1.x), fmul(E1.z, sx));
+    const float qz = fsub(fmul(sx, E1.y), fmul(E1.x, sy));
+    const float v = fmul(f, fadd(fadd(fmul(r.dx, qx), fmul(r.dy, qy)), fmul(r.dz, qz)));
+    if (PACKET) {
+        if (!(v >= 0.0f && fadd(u, v) <= 1.0f)) return false;  // spatial_sah.rs:218-222
+    } else {
+        if (v < 0.0f || fadd(u, v) > 1.0f) return false;  // spatial_sah.rs:150-152
+    }
+    const float t = fmul(f, fadd(fadd(fmul(E2.x, qx), fmul(E2.y, qy)), fmul(E2.z, qz)));
+    const bool above = PACKET ? (t >= r.t_min) : (t > r.t_min);
+    if (!above) return false;
+    const uint32_t id = __float_as_uint(A.w);
+    if (t < r.t) {
+        r.t = t;
+        r.prim = id;
+        return true;
+    }
+    if (r.prim != kNoHit && t == r.t && id < r.prim) r.prim = id;
+    return false;
+}
+
+// ---- Aabb::intersect (src/aabb.rs:146-181) -------------------------------------------------------
+__device__ __forceinline__ bool aabb_single(const float4 lo, const float4 hi, const RayRegs& r, float& key) {
+    const bool sx = r.dx < 0.0f, sy = r.dy < 0.0f, sz = r.dz < 0.0f;
+    float ray_min = fmul(fsub(sx ? hi.x : lo.x, r.ox), r.ix);
+    float ray_max = fmul(fsub(sx ? lo.x : hi.x, r.ox), r.ix);
+    const float y_min = fmul(fsub(sy ? hi.y : lo.y, r.oy), r.iy);
+    const float y_max = fmul(fsub(sy ? lo.y : hi.y, r.oy), r.iy);
+    if ((ray_min > y_max) || (y_min > ray_max)) return false;
+    if (y_min > ray_min) ray_min = y_min;
+    if (y_max < ray_max) ray_max = y_max;
+    const float z_min = fmul(fsub(sz ? hi.z : lo.z, r.oz), r.iz);
+    const float z_max = fmul(fsub(sz ? lo.z : hi.z, r.oz), r.iz);
+    if ((ray_min > z_max) || (z_min > ray_max)) return false;
+    if (z_max < ray_max) ray_max = z_max;
+    key = ray_max;
+    return ray_max > r.t_min;
+}
+
+// ---- Aabb::intersect4, one lane (src/aabb.rs:218-244) -------------------------------------------
+template <bool EXACT>
+__device__ __forceinline__ bool aabb_lane(const float4 lo, const float4 hi, const RayRegs& r, float& key) {
+    const float t1x = fmul(fsub(lo.x, r.ox), r.ix), t1y = fmul(fsub(lo.y, r.oy), r.iy), t1z = fmul(fsub(lo.z, r.oz), r.iz);
+    const float t2x = fmul(fsub(hi.x, r.ox), r.ix), t2y = fmul(fsub(hi.y, r.oy), r.iy), t2z = fmul(fsub(hi.z, r.oz), r.iz);
+    const float tmin = vmax<EXACT>(vmin<EXACT>(t1x, t2x), vmax<EXACT>(vmin<EXACT>(t1y, t2y), vmin<EXACT>(t1z, t2z)));
+    const float tmax = vmin<EXACT>(vmax<EXACT>(t1x, t2x), vmin<EXACT>(vmax<EXACT>(t1y, t2y), vmax<EXACT>(t1z, t2z)));
+    key = tmin;
+    return tmax > 0.0f && tmax > tmin && tmin < r.t;
+}
+
+// ---- MbvhNode::intersect slab part (src/mbvh_node.rs:177-206) ------------------------------------
+// key[s] = t_min of slot s; returns the 4-bit `result` mask (t_max >= t_min && t_min < ray.t).
+template <bool EXACT>
+__device__ __forceinline__ uint32_t mbvh_slabs(const float4 mnx, const float4 mxx, const float4 mny, const float4 mxy,
+                                               const float4 mnz, const float4 mxz, const RayRegs& r, float key[4]) {
+    const float a_mnx[4] = {mnx.x, mnx.y, mnx.z, mnx.w}, a_mxx[4] = {mxx.x, mxx.y, mxx.z, mxx.w};
+    const float a_mny[4] = {mny.x, mny.y, mny.z, mny.w}, a_mxy[4] = {mxy.x, mxy.y, mxy.z, mxy.w};
+    const float a_mnz[4] = {mnz.x, mnz.y, mnz.z, mnz.w}, a_mxz[4] = {mxz.x, mxz.y, mxz.z, mxz.w};
+    uint32_t mask = 0;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const float tx0 = fmul(fsub(a_mnx[s], r.ox), r.ix), tx1 = fmul(fsub(a_mxx[s], r.ox), r.ix);
+        const float ty0 = fmul(fsub(a_mny[s], r.oy), r.iy), ty1 = fmul(fsub(a_mxy[s], r.oy), r.iy);
+        const float tz0 = fmul(fsub(a_mnz[s], r.oz), r.iz), tz1 = fmul(fsub(a_mxz[s], r.oz), r.iz);
+        const float tmn = vmax<EXACT>(vmin<EXACT>(tx0, tx1), vmax<EXACT>(vmin<EXACT>(ty0, ty1), vmin<EXACT>(tz0, tz1)));
+        const float tmx = vmin<EXACT>(vmax<EXACT>(tx0, tx1), vmin<EXACT>(vmax<EXACT>(ty0, ty1), vmax<EXACT>(tz0, tz1)));
+        key[s] = tmn;
+        if (tmx >= tmn && tmn < r.t) mask |= 1u << s;
+    }
+    return mask;
+}
+
+// ---- MbvhNode::intersect4, one lane = one ray against the 4 slots (src/mbvh_node.rs:243-281) -----
+template <bool EXACT>
+__device__ __forceinline__ uint32_t mbvh_slabs_lane(const float4 mnx, const float4 mxx, const float4 mny,
+                                                    const float4 mxy, const float4 mnz, const float4 mxz,
+                                                    const RayRegs& r) {
+    const float a_mnx[4] = {mnx.x, mnx.y, mnx.z, mnx.w}, a_mxx[4] = {mxx.x, mxx.y, mxx.z, mxx.w};
+    const float a_mny[4] = {mny.x, mny.y, mny.z, mny.w}, a_mxy[4] = {mxy.x, mxy.y, mxy.z, mxy.w};
+    const float a_mnz[4] = {mnz.x, mnz.y, mnz.z, mnz.w}, a_mxz[4] = {mxz.x, mxz.y, mxz.z, mxz.w};
+    uint32_t mask = 0;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        float t1 = fmul(fsub(a_mnx[s], r.ox), r.ix), t2 = fmul(fsub(a_mxx[s], r.ox), r.ix);
+        float tmin = vmin<EXACT>(t1, t2), tmax = vmax<EXACT>(t1, t2);
+        t1 = fmul(fsub(a_mny[s], r.oy), r.iy);
+        t2 = fmul(fsub(a_mxy[s], r.oy), r.iy);
+        tmin = vmax<EXACT>(tmin, vmin<EXACT>(t1, t2));
+        tmax = vmin<EXACT>(tmax, vmax<EXACT>(t1, t2));
+        t1 = fmul(fsub(a_mnz[s], r.oz), r.iz);
+        t2 = fmul(fsub(a_mxz[s], r.oz), r.iz);
+        tmin = vmax<EXACT>(tmin, vmin<EXACT>(t1, t2));
+        tmax = vmin<EXACT>(tmax, vmax<EXACT>(t1, t2));
+        if (tmax > tmin && tmin < r.t) mask |= 1u << s;
+    }
+    return mask;
+}
+
+__device__ __forceinline__ int sel4(const int4 v, int s) { return s == 0 ? v.x : (s == 1 ? v.y : (s == 2 ? v.z : v.w)); }
+
+#define RTB_CSWAP(i, j)                 \
+    if (key[i] > key[j]) {              \
+        float tk = key[i];              \
+        key[i] = key[j];                \
+        key[j] = tk;                    \
+        int tp = pay[i];                \
+        pay[i] = pay[j];                \
+        pay[j] = tp;                    \
+    }
+
+struct Stack {
+    int* base;  // &smem[threadIdx.x]; entry e at base[e * kBlock]
+    int sp;
+    uint32_t* overflow;
+    __device__ __forceinline__ void push(int v) {
+        if (sp < kStackDepth) {
+            base[sp * kBlock] = v;
+            sp++;
+        } else {
+            *overflow = 1u;
+        }
+    }
+    __device__ __forceinline__ int pop() { return base[(--sp) * kBlock]; }
+};
+
+// ================================================================================================
+// Mbvh, single rays  (MbvhIndexIterator)
+// ================================================================================================
+template <bool ANY>
+__device__ __forceinline__ void trace_mbvh_single(const DeviceTree& tree, RayRegs& r, Stack& st) {
+    const float4* __restrict__ nodes = tree.nodes;
+    int cur = 0;
+    for (;;) {
+        const float4* n = nodes + (size_t)cur * 8;
+        const float4 mnx = __ldg(n + 0), mxx = __ldg(n + 1), mny = __ldg(n + 2), mxy = __ldg(n + 3);
+        const float4 mnz = __ldg(n + 4), mxz = __ldg(n + 5);
+        const float4 chf = __ldg(n + 6), cnf = __ldg(n + 7);
+        const int4 ch = make_int4(__float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w));
+        const int4 cn = make_int4(__float_as_int(cnf.x), __float_as_int(cnf.y), __float_as_int(cnf.z), __float_as_int(cnf.w));
+        float key[4];
+        const uint32_t mask = r.exact ? mbvh_slabs<true>(mnx, mxx, mny, mxy, mnz, mxz, r, key)
+                                      : mbvh_slabs<false>(mnx, mxx, mny, mxy, mnz, mxz, r, key);
+        const uint32_t leafbits = (cn.x > -1 ? 1u : 0u) | (cn.y > -1 ? 2u : 0u) | (cn.z > -1 ? 4u : 0u) | (cn.w > -1 ? 8u : 0u);
+        const uint32_t childbits = (ch.x > -1 ? 1u : 0u) | (ch.y > -1 ? 2u : 0u) | (ch.z > -1 ? 4u : 0u) | (ch.w > -1 ? 8u : 0u);
+        // leaf slots: yield every primitive (iter_indices.rs:292-303)
+        uint32_t leaves = mask & leafbits;
+        while (leaves) {
+            const int s = __ffs(leaves) - 1;
+            leaves &= leaves - 1;
+            const int first = sel4(ch, s), count = sel4(cn, s);
+            for (int j = 0; j < count; j++) {
+                const bool hit = tri_candidate<false>(tree.tris, first + j, r);
+                if (ANY && hit) return;
+            }
+        }
+        // inner slots: push in the order ids[3], ids[2], ids[1], ids[0] (iter_indices.rs:287, :304-309)
+        const uint32_t inner = mask & ~leafbits & childbits;
+        if (inner) {
+            int pay[4] = {(inner & 1u) ? ch.x : -1, (inner & 2u) ? ch.y : -1, (inner & 4u) ? ch.z : -1, (inner & 8u) ? ch.w : -1};
+            // the reference's 5-comparator network; the last comparator swaps ids only (mbvh_node.rs:219-237)
+            RTB_CSWAP(0, 1)
+            RTB_CSWAP(2, 3)
+            RTB_CSWAP(0, 2)
+            RTB_CSWAP(1, 3)
+            if (key[2] > key[3]) {
+                int tp = pay[2];
+                pay[2] = pay[3];
+                pay[3] = tp;
+            }
+            if (pay[3] >= 0) st.push(pay[3]);
+            if (pay[2] >= 0) st.push(pay[2]);
+            if (pay[1] >= 0) st.push(pay[1]);
+            if (pay[0] >= 0) st.push(pay[0]);
+        }
+        if (st.sp == 0) return;
+        cur = st.pop();
+    }
+}
+
+// ================================================================================================
+// Bvh, single rays  (BvhIndexIterator)
+// ================================================================================================
+template <bool ANY>
+__device__ __forceinline__ void trace_bvh_single(const DeviceTree& tree, RayRegs& r, Stack& st) {
+    const float4* __restrict__ nodes = tree.nodes;
+    st.push(0);  // the root is pushed without a box test (iter_indices.rs:32-46)
+    while (st.sp > 0) {
+        const int cur = st.pop();
+        const float4 n0 = __ldg(nodes + (size_t)cur * 2), n1 = __ldg(nodes + (size_t)cur * 2 + 1);
+        const int count = __float_as_int(n0.w), left_first = __float_as_int(n1.w);
+        if (count > -1) {
+            for (int i = 0; i < count; i++) {
+                const bool hit = tri_candidate<false>(tree.tris, left_first + i, r);
+                if (ANY && hit) return;
+            }
+        } else if (left_first > -1) {
+            const float4* c = nodes + (size_t)left_first * 2;
+            const float4 l0 = __ldg(c), l1 = __ldg(c + 1), r0 = __ldg(c + 2), r1 = __ldg(c + 3);
+            float kl = 0.f, kr = 0.f;
+            const bool hl = aabb_single(l0, l1, r, kl);
+            const bool hr = aabb_single(r0, r1, r, kr);
+            if (hl && hr) {  // BvhNode::sort_nodes (bvh_node.rs:150-177)
+                if (kl < kr) {
+                    st.push(left_first);
+                    st.push(left_first + 1);
+                } else {
+                    st.push(left_first + 1);
+                    st.push(left_first);
+                }
+            } else if (hl) {
+                st.push(left_first);
+            } else if (hr) {
+                st.push(left_first + 1);
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// Packets: 4 adjacent lanes = one RayPacket4; every traversal decision is a quad vote, so the four
+// lanes execute the same control flow, exactly like the SSE lanes of the reference.
+// ================================================================================================
+__device__ __forceinline__ uint32_t quad_mask() { return 0xFu << (threadIdx.x & 28u); }
+
+// any-hit retirement of a lane: the callback writes t = -1e34 (see rtbvh_gpu.h)
+template <bool ANY>
+__device__ __forceinline__ bool packet_candidate(const TriRec* __restrict__ tris, int pos, RayRegs& r, bool& retired,
+                                                 uint32_t qm) {
+    const bool hit = tri_candidate<true>(tris, pos, r);
+    if (ANY) {
+        if (hit) {
+            r.t = -1e34f;
+            retired = true;
+        }
+        return __all_sync(qm, retired) != 0;
+    }
+    return false;
+}
+
+template <bool ANY>
+__device__ __forceinline__ void trace_mbvh_packet(const DeviceTree& tree, RayRegs& r, Stack& st, bool& retired) {
+    const float4* __restrict__ nodes = tree.nodes;
+    const uint32_t qm = quad_mask();
+    int cur = 0;
+    for (;;) {
+        const float4* n = nodes + (size_t)cur * 8;
+        const float4 mnx = __ldg(n + 0), mxx = __ldg(n + 1), mny = __ldg(n + 2), mxy = __ldg(n + 3);
+        const float4 mnz = __ldg(n + 4), mxz = __ldg(n + 5);
+        const float4 chf = __ldg(n + 6), cnf = __ldg(n + 7);
+        const int4 ch = make_int4(__float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w));
+        const int4 cn = make_int4(__float_as_int(cnf.x), __float_as_int(cnf.y), __float_as_int(cnf.z), __float_as_int(cnf.w));
+        const uint32_t mine = r.exact ? mbvh_slabs_lane<true>(mnx, mxx, mny, mxy, mnz, mxz, r)
+                                      : mbvh_slabs_lane<false>(mnx, mxx, mny, mxy, mnz, mxz, r);
+        const uint32_t mask = __reduce_or_sync(qm, mine);  // result |= ... over the 4 rays (mbvh_node.rs:277-279)
+        // no ordering: ids = [0,1,2,3], slots visited 3, 2, 1, 0 (iter_indices.rs:390)
+#pragma unroll 1
+        for (int s = 3; s >= 0; s--) {
+            if (!((mask >> s) & 1u)) continue;
+            const int first = sel4(ch, s), count = sel4(cn, s);
+            if (count > -1) {
+                for (int j = 0; j < count; j++)
+                    if (packet_candidate<ANY>(tree.tris, first + j, r, retired, qm)) return;
+            } else if (first > -1) {
+                st.push(first);
+            }
+        }
+        if (st.sp == 0) return;
+        cur = st.pop();
+    }
+}
+
+template <bool ANY>
+__device__ __forceinline__ void trace_bvh_packet(const DeviceTree& tree, RayRegs& r, Stack& st, bool& retired) {
+    const float4* __restrict__ nodes = tree.nodes;
+    const uint32_t qm = quad_mask();
+    st.push(0);
+    while (st.sp > 0) {
+        const int cur = st.pop();
+        const float4 n0 = __ldg(nodes + (size_t)cur * 2), n1 = __ldg(nodes + (size_t)cur * 2 + 1);
+        const int count = __float_as_int(n0.w), left_first = __float_as_int(n1.w);
+        if (count > -1) {
+            for (int i = 0; i < count; i++)
+                if (packet_candidate<ANY>(tree.tris, left_first + i, r, retired, qm)) return;
+        } else if (left_first > -1) {
+            const float4* c = nodes + (size_t)left_first * 2;
+            const float4 l0 = __ldg(c), l1 = __ldg(c + 1), r0 = __ldg(c + 2), r1 = __ldg(c + 3);
+            float kl, kr;
+            const bool ml = r.exact ? aabb_lane<true>(l0, l1, r, kl) : aabb_lane<false>(l0, l1, r, kl);
+            const bool mr = r.exact ? aabb_lane<true>(r0, r1, r, kr) : aabb_lane<false>(r0, r1, r, kr);
+            const bool hl = __any_sync(qm, ml) != 0, hr = __any_sync(qm, mr) != 0;
+            if (hl && hr) {  // BvhNode::sort_nodes4: any lane with t_near_left < t_near_right (bvh_node.rs:180-211)
+                if (__any_sync(qm, kl < kr)) {
+                    st.push(left_first);
+                    st.push(left_first + 1);
+                } else {
+                    st.push(left_first + 1);
+                    st.push(left_first);
+                }
+            } else if (hl) {
+                st.push(left_first);
+            } else if (hr) {
+                st.push(left_first + 1);
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// kernels
+// ================================================================================================
+template <int TREE, bool ANY>
+__global__ void __launch_bounds__(kBlock) trace_single_kernel(const DeviceTree tree, const RTRay* __restrict__ rays,
+                                                              size_t n, RTHit* __restrict__ hits,
+                                                              uint8_t* __restrict__ occluded,
+                                                              uint32_t* __restrict__ overflow) {
+    __shared__ int smem[kStackDepth * kBlock];
+    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + i * 2);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rays) + i * 2 + 1);
+    RayRegs r;
+    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.t_min = a.w;
+    r.dx = b.x; r.dy = b.y; r.dz = b.z; r.t = b.w;
+    finish_ray_setup(r);
+    Stack st{smem + threadIdx.x, 0, overflow};
+    if (tree.node_count != 0 && !r.nan) {
+        if (TREE == RT_TREE_MBVH)
+            trace_mbvh_single<ANY>(tree, r, st);
+        else
+            trace_bvh_single<ANY>(tree, r, st);
+    }
+    if (ANY)
+        occluded[i] = r.prim != kNoHit ? 1 : 0;
+    else
+        reinterpret_cast<float2*>(hits)[i] = make_float2(r.t, __uint_as_float(r.prim));
+}
+
+template <int TREE, bool ANY>
+__global__ void __launch_bounds__(kBlock) trace_packet_kernel(const DeviceTree tree,
+                                                              const RTRayPacket4* __restrict__ packets, size_t n_packets,
+                                                              float t_min, RTHitPacket4* __restrict__ hits,
+                                                              uint8_t* __restrict__ occluded,
+                                                              uint32_t* __restrict__ overflow) {
+    __shared__ int smem[kStackDepth * kBlock];
+    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;  // ray index; packet = i / 4
+    const size_t p = i >> 2;
+    const int lane = (int)(i & 3);
+    if (p >= n_packets) return;  // whole quads leave together
+    const float* pk = reinterpret_cast<const float*>(packets + p);
+    RayRegs r;
+    r.ox = __ldg(pk + 0 + lane); r.oy = __ldg(pk + 4 + lane); r.oz = __ldg(pk + 8 + lane);
+    r.dx = __ldg(pk + 12 + lane); r.dy = __ldg(pk + 16 + lane); r.dz = __ldg(pk + 20 + lane);
+    r.t = __ldg(pk + 24 + lane);
+    r.t_min = t_min;
+    finish_ray_setup(r);
+    const uint32_t qm = quad_mask();
+    Stack st{smem + threadIdx.x, 0, overflow};
+    bool retired = false;
+    // BvhPacketIndexIterator rejects the packet when ANY lane has a NaN (iter_indices.rs:129-144);
+    // MbvhPacketIndexIterator has no such check (the NaN lane just never passes a comparison).
+    const bool reject = (TREE == RT_TREE_BVH) && (__any_sync(qm, r.nan) != 0);
+    if (tree.node_count != 0 && !reject) {
+        if (TREE == RT_TREE_MBVH)
+            trace_mbvh_packet<ANY>(tree, r, st, retired);
+        else
+            trace_bvh_packet<ANY>(tree, r, st, retired);
+    }
+    if (ANY) {
+        occluded[i] = retired ? 1 : 0;
+    } else {
+        hits[p].t[lane] = r.t;
+        hits[p].prim[lane] = r.prim;
+    }
+}
+
+// ---- scene upload helpers ---------------------------------------------------------------------
+__global__ void gather_tris_kernel(const float* __restrict__ verts, uint32_t stride_f, const uint32_t* __restrict__ indices,
+                                   uint32_t index_count, uint32_t tri_count, TriRec* __restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= index_count) return;
+    const uint32_t id = indices[k];
+    TriRec rec;
+    if (id < tri_count) {
+        const float* v = verts + (size_t)id * 3 * stride_f;
+        const float v0x = v[0], v0y = v[1], v0z = v[2];
+        const float v1x = v[stride_f], v1y = v[stride_f + 1], v1z = v[stride_f + 2];
+        const float v2x = v[2 * stride_f], v2y = v[2 * stride_f + 1], v2z = v[2 * stride_f + 2];
+        rec.a = make_float4(v0x, v0y, v0z, __uint_as_float(id));
+        rec.b = make_float4(fsub(v1x, v0x), fsub(v1y, v0y), fsub(v1z, v0z), 0.f);
+        rec.c = make_float4(fsub(v2x, v0x), fsub(v2y, v0y), fsub(v2z, v0z), 0.f);
+    } else {  // out-of-range id (never produced by the builders): degenerate triangle, never hit
+        rec.a = make_float4(0.f, 0.f, 0.f, __uint_as_float(id));
+        rec.b = make_float4(0.f, 0.f, 0.f, 0.f);
+        rec.c = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    out[k] = rec;
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float hash_unit(uint64_t seed, uint64_t index, uint32_t lane) {
+    return (float)(splitmix64(seed ^ (index * 16ull + lane)) >> 40) * (1.0f / 16777216.0f);
+}
+
+// CameraView3D::generate_ray (shared/src/lib.rs:157-165); normalize = v * (1 / sqrt(v.v))
+__global__ void camera_rays_kernel(float3 pos, float3 p1, float3 right, float3 up, uint32_t width, uint32_t height,
+                                   uint32_t row0, uint32_t rows, uint64_t seed, uint64_t frame, RTRay* __restrict__ out) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (size_t)width * rows) return;
+    const uint32_t x = (uint32_t)(k % width), y = row0 + (uint32_t)(k / width);
+    float fx = (float)x, fy = (float)y;
+    if (seed != 0) {
+        const uint64_t pix = frame * ((uint64_t)width * height) + (uint64_t)y * width + x;
+        fx = fadd(fx, hash_unit(seed, pix, 0));
+        fy = fadd(fy, hash_unit(seed, pix, 1));
+    }
+    const float u = fmul(fx, fdiv(1.0f, (float)width)), v = fmul(fy, fdiv(1.0f, (float)height));
+    const float px = fadd(fadd(p1.x, fmul(u, right.x)), fmul(v, up.x));
+    const float py = fadd(fadd(p1.y, fmul(u, right.y)), fmul(v, up.y));
+    const float pz = fadd(fadd(p1.z, fmul(u, right.z)), fmul(v, up.z));
+    const float dx = fsub(px, pos.x), dy = fsub(py, pos.y), dz = fsub(pz, pos.z);
+    const float inv = fdiv(1.0f, __fsqrt_rn(fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz))));
+    float4* o = reinterpret_cast<float4*>(out + k);
+    o[0] = make_float4(pos.x, pos.y, pos.z, 1e-4f);
+    o[1] = make_float4(fmul(dx, inv), fmul(dy, inv), fmul(dz, inv), 1e34f);
+}
+
+}  // namespace
+
+// ---- launchers ----------------------------------------------------------------------------------
+cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any, const RTRay* d_rays, size_t n,
+                                RTHit* d_hits, uint8_t* d_occluded, uint32_t* d_overflow, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)ceil_div(n, kBlock);
+    if (tree_kind == RT_TREE_MBVH) {
+        if (any)
+            trace_single_kernel<RT_TREE_MBVH, true><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_overflow);
+        else
+            trace_single_kernel<RT_TREE_MBVH, false><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_overflow);
+    } else {
+        if (any)
+            trace_single_kernel<RT_TREE_BVH, true><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_overflow);
+        else
+            trace_single_kernel<RT_TREE_BVH, false><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_overflow);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,
+                                 size_t n_packets, float t_min, RTHitPacket4* d_hits, uint8_t* d_occluded,
+                                 uint32_t* d_overflow, cudaStream_t stream) {
+    if (n_packets == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)ceil_div(n_packets * 4, kBlock);
+    if (tree_kind == RT_TREE_MBVH) {
+        if (any)
+            trace_packet_kernel<RT_TREE_MBVH, true><<<grid, kBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_overflow);
+        else
+            trace_packet_kernel<RT_TREE_MBVH, false><<<grid, kBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_overflow);
+    } else {
+        if (any)
+            trace_packet_kernel<RT_TREE_BVH, true><<<grid, kBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_overflow);
+        else
+            trace_packet_kernel<RT_TREE_BVH, false><<<grid, kBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_overflow);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_tris(const float* d_verts, uint32_t stride_floats, const uint32_t* d_indices,
+                               uint32_t index_count, uint32_t tri_count, TriRec* d_out, cudaStream_t stream) {
+    if (index_count == 0) return cudaSuccess;
+    gather_tris_kernel<<<(unsigned)ceil_div(index_count, 256), 256, 0, stream>>>(d_verts, stride_floats, d_indices,
+                                                                                  index_count, tri_count, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_camera_rays(const float pos[3], const float p1[3], const float right[3], const float up[3],
+                               uint32_t width, uint32_t height, uint32_t row0, uint32_t rows, uint64_t seed,
+                               uint64_t frame, RTRay* d_rays, cudaStream_t stream) {
+    const size_t n = (size_t)width * rows;
+    if (n == 0) return cudaSuccess;
+    camera_rays_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(
+        make_float3(pos[0], pos[1], pos[2]), make_float3(p1[0], p1[1], p1[2]), make_float3(right[0], right[1], right[2]),
+        make_float3(up[0], up[1], up[2]), width, height, row0, rows, seed, frame, d_rays);
+    return cudaGetLastError();
+}
+
+}  // namespace rtb

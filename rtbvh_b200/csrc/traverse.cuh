@@ -1,0 +1,18 @@
+// traverse.cuh — launchers of the traversal kernels (traverse.cu).
+#pragma once
+#include "common.cuh"
+
+namespace rtb {
+
+cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any, const RTRay* d_rays, size_t n,
+                                RTHit* d_hits, uint8_t* d_occluded, uint32_t* d_overflow, cudaStream_t stream);
+cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,
+                                 size_t n_packets, float t_min, RTHitPacket4* d_hits, uint8_t* d_occluded,
+                                 uint32_t* d_overflow, cudaStream_t stream);
+cudaError_t launch_gather_tris(const float* d_verts, uint32_t stride_floats, const uint32_t* d_indices,
+                               uint32_t index_count, uint32_t tri_count, TriRec* d_out, cudaStream_t stream);
+cudaError_t launch_camera_rays(const float pos[3], const float p1[3], const float right[3], const float up[3],
+                               uint32_t width, uint32_t height, uint32_t row0, uint32_t rows, uint64_t seed,
+                               uint64_t frame, RTRay* d_rays, cudaStream_t stream);
+
+}  // namespace rtb

@@ -1,0 +1,191 @@
+"""Parity of the CUDA traversal path against the CPU oracle, through the C ABI (include/rtbvh_gpu.h).
+
+Bar (BASELINE.json north_star): traversing a reference-format tree uploaded unchanged returns bit-exact hit
+primitive ids (lowest id on equal t) and t within 1e-5 relative.  The kernels reproduce the reference's
+arithmetic, so these tests demand BIT-EXACT t as well; TOL_REL documents the contractual tolerance.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL_REL = 1e-5  # contractual; the assertions below are exact (stricter)
+
+
+@pytest.fixture(scope="module")
+def A():
+    from rtbvh_b200 import api
+    if api.device_count() == 0:
+        pytest.fail("no CUDA device visible: -m gpu tests must run on the B200 box")
+    return api
+
+
+def _scene(A, tris, bvh, m):
+    return A.Scene(tris, bvh=A.Bvh.from_arrays(bvh.nodes, bvh.indices), mbvh=A.Mbvh.from_arrays(m.nodes, m.indices))
+
+
+def _check_all_paths(A, O, W, tris, bvh, m, rays, label):
+    sc = _scene(A, tris, bvh, m)
+    packets = W.pack4(rays[: len(rays) // 4 * 4])
+    try:
+        for kind, otree in ((A.TREE_BVH, bvh), (A.TREE_MBVH, m)):
+            want, _, _ = O.trace(otree, tris, rays)
+            got = sc.intersect(rays, kind)
+            assert np.array_equal(got["prim"], want["prim"]), f"{label}: ids differ (tree {kind})"
+            assert np.array_equal(got["t"], want["t"]), f"{label}: t differs (tree {kind})"
+            occ_w, _, _ = O.trace(otree, tris, rays, mode="any")
+            assert np.array_equal(sc.occluded(rays, kind), occ_w), f"{label}: any-hit differs (tree {kind})"
+            want4, _, _ = O.trace_packets(otree, tris, packets)
+            got4 = sc.intersect_packets(packets, kind)
+            assert np.array_equal(got4["prim"], want4["prim"]), f"{label}: packet ids differ (tree {kind})"
+            assert np.array_equal(got4["t"], want4["t"]), f"{label}: packet t differs (tree {kind})"
+            occ4_w, _, _ = O.trace_packets(otree, tris, packets, mode="any")
+            assert np.array_equal(sc.occluded_packets(packets, kind), occ4_w), f"{label}: packet any-hit (tree {kind})"
+        assert not sc.stack_overflowed()
+    finally:
+        sc.free()
+
+
+def test_ffi_kat_quad(A, O, W):
+    # rtbvh_ffi/src/lib.rs:946-1019: quad at z = 1, ray from the origin along +Z, t = 1e26 in -> t == 1.0
+    tris = W.quad()
+    aabbs, _ = O.prims_from_triangles(tris, pad=1e-4)
+    rc, bvh = O.build(O.BINNED_SAH, aabbs, O.aabb_centers(aabbs), 1)
+    m = bvh.collapse()
+    sc = _scene(A, tris, bvh, m)
+    rays = W.make_rays(np.zeros((1, 3), np.float32), np.array([[0, 0, 1]], np.float32), t_max=np.float32(1e26))
+    for kind in (A.TREE_BVH, A.TREE_MBVH):
+        h = sc.intersect(rays, kind)
+        assert abs(h["t"][0] - 1.0) < np.finfo(np.float32).eps and h["prim"][0] == 0
+    sc.free()
+
+
+@pytest.mark.parametrize("name", ["sah", "locb"])
+def test_teapot_benchmark_camera(A, O, W, teapot, teapot_trees, name):
+    bvh, m = teapot_trees[name]
+    rays = W.camera_rays(W.benchmark_camera(400, 400))
+    _check_all_paths(A, O, W, teapot["tris"], bvh, m, rays, f"teapot/{name}/camera")
+
+
+@pytest.mark.parametrize("name", ["sah", "locb"])
+def test_teapot_incoherent(A, O, W, teapot, teapot_trees, name):
+    bvh, m = teapot_trees[name]
+    rays = W.random_rays(100_000, *W.bounds(teapot["tris"]))
+    _check_all_paths(A, O, W, teapot["tris"], bvh, m, rays, f"teapot/{name}/random")
+
+
+def test_edge_rays(A, O, W, teapot, teapot_trees):
+    """Axis-parallel directions (inv_direction = +-inf, NaN slabs -> the SSE operand rule), rays starting on
+    box planes, NaN rays, zero-length windows, rays that start inside the model."""
+    tris = teapot["tris"]
+    lo, hi = W.bounds(tris)
+    rng = np.random.default_rng(7)
+    n = 4096
+    o = (lo + (hi - lo) * rng.random((n, 3))).astype(np.float32)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    axis = rng.integers(0, 3, n)
+    d[np.arange(n) % 2 == 0] = 0.0
+    d[np.arange(n), axis] = np.where(rng.random(n) < 0.5, -1.0, 1.0)
+    # snap some origins exactly onto vertex coordinates (planes of leaf boxes up to the 1e-4 padding)
+    v = tris.reshape(-1, 3)
+    pick = rng.integers(0, len(v), n)
+    snap = np.arange(n) % 3 == 0
+    o[snap] = v[pick[snap]]
+    rays = W.make_rays(o, d)
+    rays["t"][::7] = np.float32(0.5)
+    rays["t"][::11] = np.float32(1e-4)
+    rays["origin"][5] = np.nan
+    rays["direction"][9, 1] = np.nan
+    rays["direction"][13] = 0.0
+    bvh, m = teapot_trees["sah"]
+    _check_all_paths(A, O, W, tris, bvh, m, rays, "teapot/edge")
+    bvh, m = teapot_trees["locb"]
+    _check_all_paths(A, O, W, tris, bvh, m, rays, "teapot/edge-locb")
+
+
+def test_empty_and_ragged_batches(A, O, W, teapot, teapot_trees):
+    bvh, m = teapot_trees["sah"]
+    sc = _scene(A, teapot["tris"], bvh, m)
+    assert len(sc.intersect(np.zeros(0, A.RAY_DTYPE))) == 0
+    assert len(sc.intersect_packets(np.zeros(0, A.PACKET_DTYPE))) == 0
+    rays = W.random_rays(1001, *W.bounds(teapot["tris"]))  # not a multiple of the block size
+    want, _, _ = O.trace(m, teapot["tris"], rays)
+    assert np.array_equal(sc.intersect(rays), want)
+    pk = W.pack4(rays[:1000])[:33]  # 33 packets: a partially filled last warp
+    want4, _, _ = O.trace_packets(m, teapot["tris"], pk)
+    assert np.array_equal(sc.intersect_packets(pk), want4)
+    sc.free()
+
+
+def test_leaf_sizes_and_single_leaf_root(A, O, W, teapot):
+    tris = teapot["tris"][:300]
+    aabbs, centers = O.prims_from_triangles(tris)
+    rays = W.random_rays(20_000, *W.bounds(tris))
+    for leaf in (1, 2, 4, 8, 1000):  # 1000 -> the root is a single leaf holding every primitive
+        rc, bvh = O.build(O.BINNED_SAH, aabbs, centers, leaf)
+        assert rc == 0
+        _check_all_paths(A, O, W, tris, bvh, bvh.collapse(), rays, f"leaf{leaf}")
+    rc, bvh = O.build(O.LOCB, aabbs[:2], centers[:2], 1)  # LOCB with <= 2 prims: one root leaf (locb.rs:258-269)
+    _check_all_paths(A, O, W, tris[:2], bvh, bvh.collapse(), rays[:4096], "locb2")
+
+
+def test_soup_100k(A, O, W):
+    tris = W.soup(100_000)
+    aabbs, centers = O.prims_from_triangles(tris)
+    rc, bvh = O.build(O.BINNED_SAH, aabbs, centers, 1)
+    m = bvh.collapse()
+    rays = np.concatenate([W.camera_rays(W.soup_camera(256, 256), jitter_seed=5, frame=3),
+                           W.random_rays(50_000, *W.bounds(tris))])
+    _check_all_paths(A, O, W, tris, bvh, m, rays, "soup100k")
+    sh = W.shadow_rays(tris, 50_000)
+    sc = _scene(A, tris, bvh, m)
+    for kind, otree in ((A.TREE_BVH, bvh), (A.TREE_MBVH, m)):
+        occ, _, _ = O.trace(otree, tris, sh, mode="any")
+        assert np.array_equal(sc.occluded(sh, kind), occ)
+    sc.free()
+
+
+def test_device_resident_api_and_camera_rays(A, O, W, teapot, teapot_trees):
+    import torch
+    bvh, m = teapot_trees["sah"]
+    tris = teapot["tris"]
+    sc = _scene(A, tris, bvh, m)
+    cam = W.benchmark_camera(512, 512)
+    n = 512 * 512
+    d_rays = torch.empty(n * 8, dtype=torch.float32, device="cuda")
+    d_hits = torch.empty(n * 2, dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    A.generate_camera_rays_device(cam, 0, 512, d_rays, stream=stream)
+    sc.intersect_device(d_rays, n, d_hits, A.TREE_MBVH, stream=stream)
+    torch.cuda.synchronize()
+    rays = d_rays.cpu().numpy().view(A.RAY_DTYPE).reshape(-1)
+    ref_rays = W.camera_rays(cam)
+    assert np.allclose(rays["direction"], ref_rays["direction"], rtol=0, atol=1e-6)
+    hits = d_hits.cpu().numpy().view(A.HIT_DTYPE).reshape(-1)
+    want, _, _ = O.trace(m, tris, rays)  # the oracle runs on the very rays the device generated
+    assert np.array_equal(hits, want)
+    assert not sc.stack_overflowed()
+    sc.free()
+
+
+def test_full_size_properties_soup_1m(A, O, W):
+    """BASELINE config 2 at full geometry size: oracle parity on a sample plus size-independent properties
+    (any-hit == closest-hit predicate; a closest hit re-traced with t = t_hit*(1+1e-3) finds the same t)."""
+    tris = W.soup(1 << 20)
+    aabbs, centers = O.prims_from_triangles(tris)
+    rc, bvh = O.build(O.BINNED_SAH, aabbs, centers, 1)
+    m = bvh.collapse()
+    sc = _scene(A, tris, bvh, m)
+    rays = W.camera_rays(W.soup_camera(1000, 1000), jitter_seed=W.SEED_SOUP, frame=0)
+    got = sc.intersect(rays, A.TREE_MBVH)
+    sample = np.arange(0, len(rays), 16)
+    want, _, _ = O.trace(m, tris, rays[sample])
+    assert np.array_equal(got[sample], want)
+    occ = sc.occluded(rays, A.TREE_MBVH)
+    assert np.array_equal(occ.astype(bool), got["prim"] != A.NO_HIT)
+    hit = got["prim"] != A.NO_HIT
+    again = rays[hit].copy()
+    again["t"] = got["t"][hit] * np.float32(1.001)
+    got2 = sc.intersect(again, A.TREE_MBVH)
+    assert np.array_equal(got2["t"], got["t"][hit]) and np.array_equal(got2["prim"], got["prim"][hit])
+    assert not sc.stack_overflowed()
+    sc.free()
