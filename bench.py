@@ -296,7 +296,8 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "soup-1Mi-tris binned-SAH Mbvh primary rays closest-hit (BASELINE configs[1])",
                        "rays_per_step": rays_per_step, "frames_per_step": fps, "ray_ring_batches": ring,
-                       "l2": "inputs larger than L2 (256 MB rays per step, distinct buffers)", **info},
+                       "l2": "inputs larger than L2 (256 MB rays per step, distinct buffers)",
+                       "trace_mode": os.environ.get("RTBVH_TRACE_MODE", "persistent"), **info},
             "clocks": clocks, "gpu_launches": args.steps,
             "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": rays_per_step * 32,
                     "d2h_bytes_per_step": rays_per_step * 8, "steps": e2e_steps, "host_equals_resident": same},
@@ -311,19 +312,21 @@ def run_gpu(args):
 def build_trees(api, tris, info, rank):
     """Tree for the bench.  The GPU builder (create_bvh -> create_mbvh) is the product path; while it is not
     available the reference-format tree built by the CPU oracle is uploaded unchanged (north_star check 1)."""
-    try:
-        from rtbvh_b200 import prims
-        aabbs, centers = prims.from_triangles(tris)
+    if os.environ.get("RTBVH_BENCH_TREE", "gpu") == "gpu":
         t0 = time.perf_counter()
-        bvh = api.Builder(aabbs, centers, 1).construct_binned_sah()
+        bvh = api.build_triangles(tris, api.BINNED_SAH, 1)
+        st = api.last_build_stats()
         t1 = time.perf_counter()
         mbvh = api.Mbvh.construct(bvh)
-        t2 = time.perf_counter()
-        info.update(tree="gpu-built: create_bvh(BinnedSAH) + create_mbvh",
-                    build_ms_per_mtri=(t1 - t0) * 1e3 / (len(tris) / 1e6), collapse_ms=(t2 - t1) * 1e3)
+        cst = api.last_build_stats()
+        mtri = len(tris) / 1e6
+        info.update(tree="gpu-built: rtbvh_gpu_create_bvh_triangles(BinnedSAH) + create_mbvh",
+                    build={"binned_sah_device_ms_per_mtri": st["device_ms"] / mtri,
+                           "binned_sah_total_ms_per_mtri": st["total_ms"] / mtri,
+                           "collapse_device_ms": cst["device_ms"], "collapse_total_ms": cst["total_ms"],
+                           "bvh_nodes": int(bvh.rt.node_count), "mbvh_nodes": int(mbvh.rt.node_count),
+                           "wall_ms_build_call": (t1 - t0) * 1e3})
         return bvh, mbvh, info
-    except (ImportError, api.RtbvhError) as e:
-        log(f"[bench] GPU builder unavailable ({e}); uploading the oracle-built reference-format tree")
     O, obvh, om, build_s = oracle_tree(tris)
     info.update(tree="reference-format tree built by the CPU oracle, uploaded unchanged",
                 oracle_build_ms_per_mtri=build_s * 1e3 / (len(tris) / 1e6))

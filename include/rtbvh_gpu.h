@@ -106,6 +106,19 @@ ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene scene, RTTreeKind tree, 
  * Synchronises the device.  Host-buffer calls return Error in that case. */
 ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene scene, uint32_t *overflowed);
 
+/* ---- builders ---------------------------------------------------------------------------------- */
+/* create_bvh (rtbvh.h) is the drop-in builder entry: it takes what rtbvh_ffi takes (aabbs + centers).
+ * This variant is Builder{aabbs: None, primitives: &[Triangle]}.construct_* (src/bvh.rs:87-137) for
+ * triangle primitives: Primitive::aabb (un-padded grow of the three vertices) and Primitive::center
+ * ((v0+v1+v2) * (1/3)) of the bench Triangle (shared/src/lib.rs:27-39) are computed on the device.
+ * The result is stored like create_bvh's (free with free_bvh, collapse with create_mbvh). */
+ResultCode rtbvh_gpu_create_bvh_triangles(const float *vertices, size_t vertex_stride, size_t triangle_count,
+                                          size_t prims_per_leaf, BvhType bvh_type, RTBvh *result);
+/* Timing of the last create_bvh / create_mbvh / refit / rtbvh_gpu_create_bvh_triangles on this thread:
+ * device_ms = kernels only (CUDA events, inputs resident -> tree resident), total_ms = incl. the H2D of the
+ * inputs and the D2H of the host mirror; iterations = LOCB clustering iterations. */
+ResultCode rtbvh_gpu_last_build_stats(double *device_ms, double *total_ms, uint32_t *iterations);
+
 /* ---- workload helper: CameraView3D::generate_ray on the device (shared/src/lib.rs:157-165) ----- */
 /* Writes width*rows rays for pixel rows [row0, row0+rows): u = (x + jx) / width, v = (y + jy) / height,
  * direction = normalize(p1 + u*right + v*up - pos); (jx, jy) = 0 when jitter_seed == 0, else

@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtbvh_rs.so")
+LIB_PATH = os.environ.get("RTBVH_LIB") or os.path.join(_HERE, "librtbvh_rs.so")  # RTBVH_LIB: A/B builds only
 
 NODE_DTYPE = np.dtype([("min", "<f4", 3), ("count", "<i4"), ("max", "<f4", 3), ("left_first", "<i4")])
 MNODE_DTYPE = np.dtype(
@@ -45,7 +45,8 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_scene_free", "rtbvh_gpu_intersect", "rtbvh_gpu_occluded", "rtbvh_gpu_intersect_packets",
                "rtbvh_gpu_occluded_packets", "rtbvh_gpu_intersect_device", "rtbvh_gpu_occluded_device",
                "rtbvh_gpu_intersect_packets_device", "rtbvh_gpu_occluded_packets_device",
-               "rtbvh_gpu_scene_stack_overflowed", "rtbvh_gpu_generate_camera_rays_device")
+               "rtbvh_gpu_scene_stack_overflowed", "rtbvh_gpu_generate_camera_rays_device",
+               "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats")
 
 
 class RTBvh(C.Structure):  # rtbvh_ffi/src/lib.rs:210-220
@@ -129,6 +130,10 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_occluded_packets_device.argtypes = [u64, C.c_int, vp, sz, f32, vp, vp]
     L.rtbvh_gpu_scene_stack_overflowed.restype = rc
     L.rtbvh_gpu_scene_stack_overflowed.argtypes = [u64, C.POINTER(u32)]
+    L.rtbvh_gpu_create_bvh_triangles.restype = rc
+    L.rtbvh_gpu_create_bvh_triangles.argtypes = [vp, sz, sz, sz, u32, C.POINTER(RTBvh)]
+    L.rtbvh_gpu_last_build_stats.restype = rc
+    L.rtbvh_gpu_last_build_stats.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u32)]
     L.rtbvh_gpu_generate_camera_rays_device.restype = rc
     L.rtbvh_gpu_generate_camera_rays_device.argtypes = [vp, vp, vp, vp, u32, u32, u32, u32, u64, u64, vp, vp]
     _lib = L
@@ -276,6 +281,23 @@ class Builder:
 
     def construct_locally_ordered_clustered(self) -> Bvh:
         return self._construct(LOCALLY_ORDERED_CLUSTERED)
+
+
+def build_triangles(vertices: np.ndarray, bvh_type: int = BINNED_SAH, primitives_per_leaf: int | None = None) -> Bvh:
+    """Builder{aabbs: None, primitives: triangles}.construct_*: aabbs and centers computed on the device."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32)
+    stride = 16 if v.shape[-1] == 4 else 12
+    v = v.reshape(-1, stride // 4)
+    out = RTBvh(0xFFFFFFFF, 0, None, 0, None)
+    _check(lib().rtbvh_gpu_create_bvh_triangles(_p(v), stride, v.shape[0] // 3, primitives_per_leaf or 0, bvh_type,
+                                                C.byref(out)))
+    return Bvh(out, owned=True)
+
+
+def last_build_stats() -> dict:
+    d, t, it = C.c_double(), C.c_double(), C.c_uint32()
+    lib().rtbvh_gpu_last_build_stats(C.byref(d), C.byref(t), C.byref(it))
+    return {"device_ms": d.value, "total_ms": t.value, "iterations": it.value}
 
 
 def _dev_ptr(x):

@@ -1,5 +1,6 @@
 // build.cuh — GPU builders behind create_bvh / create_mbvh / refit (build.cu).
 #pragma once
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -17,6 +18,13 @@ struct HostMbvh {  // rtbvh::Mbvh, src/bvh.rs:320-324
     std::vector<uint32_t> indices;
 };
 
+struct BuildStats {   // of the last build / collapse / refit on this thread
+    double device_ms = 0;   // kernels only (inputs resident -> tree resident), CUDA events
+    double total_ms = 0;    // incl. H2D of the inputs and D2H of the host mirror
+    uint32_t iterations = 0;  // LOCB clustering iterations
+    uint32_t node_count = 0;
+};
+extern thread_local BuildStats g_build_stats;
 extern thread_local std::string g_last_error;
 ResultCode fail(const char* what, cudaError_t e);
 ResultCode fail(const char* what);
@@ -24,6 +32,10 @@ ResultCode fail(const char* what);
 // Builder::construct_binned_sah / construct_locally_ordered_clustered (src/bvh.rs:87-137) on the GPU.
 ResultCode gpu_build_bvh(const RTAabb* aabbs, size_t prim_count, const float* centers, size_t center_stride,
                          size_t prims_per_leaf, uint32_t bvh_type, HostBvh* out);
+// Same, with Primitive::aabb / Primitive::center of the bench Triangle computed on the device from the
+// vertices (shared/src/lib.rs:27-39): the "AABB/centroid reduction" stage of the GPU builder.
+ResultCode gpu_build_bvh_triangles(const float* vertices, size_t vertex_stride, size_t tri_count, size_t prims_per_leaf,
+                                   uint32_t bvh_type, HostBvh* out);
 // Mbvh::construct (src/bvh.rs:381-404) on the GPU.
 ResultCode gpu_collapse(const HostBvh& bvh, HostMbvh* out);
 // Bvh::refit (src/bvh.rs:176-205) on the GPU.

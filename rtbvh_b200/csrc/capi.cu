@@ -3,7 +3,9 @@
 //
 // Ownership model mirrors rtbvh_ffi's StructureManager (rtbvh_ffi/src/lib.rs:12-127): a process-global
 // table guarded by a reader/writer lock, ids never reused.
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -39,6 +41,16 @@ namespace {
 
 constexpr int kPipeStreams = 3;                  // H2D / kernel / D2H of consecutive chunks overlap
 constexpr size_t kChunkRays = size_t(1) << 21;   // 2 Mi rays (64 MiB of RTRay) per pipeline stage
+constexpr uint32_t kCounterSlots = 1024;
+
+// RTBVH_TRACE_MODE=static selects the one-thread-per-ray kernel without refill (A/B measurements only)
+bool persistent_mode() {
+    static const bool v = [] {
+        const char* e = std::getenv("RTBVH_TRACE_MODE");
+        return !(e && std::string(e) == "static");
+    }();
+    return v;
+}
 
 struct Scene {
     int device = 0;
@@ -49,6 +61,11 @@ struct Scene {
     TriRec* d_tris_bvh = nullptr;   // leaf order of the Bvh's indices
     TriRec* d_tris_mbvh = nullptr;  // leaf order of the Mbvh's indices (may alias d_tris_bvh)
     uint32_t* d_overflow = nullptr;
+    // work counters of the persistent kernels: every launch takes the next slot and zeroes it on its
+    // own stream, so launches on different streams never share a counter
+    unsigned long long* d_counters = nullptr;
+    std::atomic<uint32_t> next_counter{0};
+    unsigned long long* counter_slot() { return d_counters + (next_counter.fetch_add(1) % kCounterSlots); }
     // host-buffer pipeline (lazily created)
     cudaStream_t streams[kPipeStreams] = {nullptr, nullptr, nullptr};
     void* d_in[kPipeStreams] = {nullptr, nullptr, nullptr};
@@ -67,6 +84,7 @@ struct Scene {
         if (d_tris_mbvh != d_tris_bvh) cudaFree(d_tris_mbvh);
         cudaFree(d_tris_bvh);
         cudaFree(d_overflow);
+        cudaFree(d_counters);
     }
 };
 
@@ -164,6 +182,7 @@ ResultCode rtbvh_gpu_scene_create(const RTBvh* bvh, const RTMbvh* mbvh, const fl
     RTB_CUDA(cudaGetDevice(&s->device));
     RTB_CUDA(cudaMalloc(&s->d_overflow, sizeof(uint32_t)));
     RTB_CUDA(cudaMemset(s->d_overflow, 0, sizeof(uint32_t)));
+    RTB_CUDA(cudaMalloc(&s->d_counters, kCounterSlots * sizeof(unsigned long long)));
     float* d_verts = nullptr;
     const size_t vbytes = triangle_count * 3 * vertex_stride;
     if (upload((void**)&d_verts, vertices, vbytes) != Ok) return Error;
@@ -218,7 +237,8 @@ ResultCode rtbvh_gpu_intersect_device(RTGpuScene h, RTTreeKind tree, const RTRay
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
-    RTB_CUDA(launch_trace_single(*t, tree, false, d_rays, n, d_hits, nullptr, s->d_overflow, (cudaStream_t)stream));
+    RTB_CUDA(launch_trace_single(*t, tree, false, d_rays, n, d_hits, nullptr, s->counter_slot(), s->d_overflow,
+                                 persistent_mode(), (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_occluded_device(RTGpuScene h, RTTreeKind tree, const RTRay* d_rays, size_t n, uint8_t* d_occ,
@@ -227,7 +247,8 @@ ResultCode rtbvh_gpu_occluded_device(RTGpuScene h, RTTreeKind tree, const RTRay*
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
-    RTB_CUDA(launch_trace_single(*t, tree, true, d_rays, n, nullptr, d_occ, s->d_overflow, (cudaStream_t)stream));
+    RTB_CUDA(launch_trace_single(*t, tree, true, d_rays, n, nullptr, d_occ, s->counter_slot(), s->d_overflow,
+                                 persistent_mode(), (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* d_packets, size_t n,
@@ -267,7 +288,7 @@ ResultCode rtbvh_gpu_intersect(RTGpuScene h, RTTreeKind tree, const RTRay* rays,
     return run_host_batch(*s, rays, n, sizeof(RTRay), sizeof(RTHit), 1, hits,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_single(*t, tree, false, (const RTRay*)din, m, (RTHit*)dout, nullptr,
-                                                         s->d_overflow, st);
+                                                         s->counter_slot(), s->d_overflow, persistent_mode(), st);
                           });
 }
 ResultCode rtbvh_gpu_occluded(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, uint8_t* occluded) {
@@ -278,7 +299,7 @@ ResultCode rtbvh_gpu_occluded(RTGpuScene h, RTTreeKind tree, const RTRay* rays, 
     return run_host_batch(*s, rays, n, sizeof(RTRay), 1, 1, occluded,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_single(*t, tree, true, (const RTRay*)din, m, nullptr, (uint8_t*)dout,
-                                                         s->d_overflow, st);
+                                                         s->counter_slot(), s->d_overflow, persistent_mode(), st);
                           });
 }
 ResultCode rtbvh_gpu_intersect_packets(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* packets, size_t n,

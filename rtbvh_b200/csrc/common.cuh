@@ -34,14 +34,36 @@ __device__ __forceinline__ float vmax(float a, float b) {
     return fmaxf(a, b);
 }
 
-// Triangle record in leaf order: 48 bytes = 3 x LDG.128.
-//   a = (v0.xyz, bitcast prim id), b = (v1 - v0, 0), c = (v2 - v0, 0)
+// Triangle record in leaf order: 64 bytes = 2 x LDG.256 (sm_100 has 256-bit global loads).
+//   a = (v0.xyz, bitcast prim id), b = (v1 - v0, 0), c = (v2 - v0, 0), d = unused padding
 // edge1 / edge2 are the same single fp32 subtractions the reference performs per test
 // (src/builders/spatial_sah.rs:136-137), done once at upload.
-struct TriRec {
-    float4 a, b, c;
+struct alignas(32) TriRec {
+    float4 a, b, c, d;
 };
-static_assert(sizeof(TriRec) == 48, "");
+static_assert(sizeof(TriRec) == 64, "");
+
+// 256-bit read-only global load (PTX ISA 8.8, sm_100+: SASS LDG.E.ENL2.256.CONSTANT).  A lane that
+// fetches its own node pays one L1 wavefront per load instruction, so halving the instruction count
+// halves the L1 data-pipe work of a node visit.  RTB_LD256=0 builds the 2 x LDG.128 variant for A/B.
+#ifndef RTB_LD256
+#define RTB_LD256 1
+#endif
+struct alignas(32) F8 {
+    float4 lo, hi;
+};
+__device__ __forceinline__ F8 ld256(const void* p) {
+    F8 r;
+#if RTB_LD256
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p));
+#else
+    r.lo = __ldg(reinterpret_cast<const float4*>(p));
+    r.hi = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#endif
+    return r;
+}
 
 struct DeviceTree {
     const float4* nodes;      // Bvh: 2 float4 per node; Mbvh: 8 float4 per node

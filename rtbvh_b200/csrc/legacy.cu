@@ -14,6 +14,7 @@
 
 #include "build.cuh"
 #include "host_iter.hpp"
+#include "../../include/rtbvh_gpu.h"
 
 using namespace rtb;
 namespace hi = rtbvh_host;
@@ -73,6 +74,26 @@ ResultCode create_bvh(const RTAabb* aabbs, size_t prim_count, const float* cente
     const ResultCode rc = gpu_build_bvh(aabbs, prim_count, centers, center_stride, prims_per_leaf, (uint32_t)bvh_type, b.get());
     if (rc != Ok) return rc;
     *result = g_manager.store(std::move(b));
+    return Ok;
+}
+
+// rtbvh_gpu.h: Builder::construct_* for triangle primitives whose aabb()/center() are computed on the device
+ResultCode rtbvh_gpu_create_bvh_triangles(const float* vertices, size_t vertex_stride, size_t triangle_count,
+                                          size_t prims_per_leaf, BvhType bvh_type, RTBvh* result) {
+    if (!vertices || !result) return Error;
+    if (vertex_stride != 12 && vertex_stride != 16) return fail("vertex_stride must be 12 or 16 bytes");
+    if (triangle_count == 0) return NoPrimitives;
+    auto b = std::make_unique<HostBvh>();
+    const ResultCode rc = gpu_build_bvh_triangles(vertices, vertex_stride, triangle_count, prims_per_leaf, (uint32_t)bvh_type, b.get());
+    if (rc != Ok) return rc;
+    *result = g_manager.store(std::move(b));
+    return Ok;
+}
+
+ResultCode rtbvh_gpu_last_build_stats(double* device_ms, double* total_ms, uint32_t* iterations) {
+    if (device_ms) *device_ms = g_build_stats.device_ms;
+    if (total_ms) *total_ms = g_build_stats.total_ms;
+    if (iterations) *iterations = g_build_stats.iterations;
     return Ok;
 }
 

@@ -17,7 +17,8 @@
 //
 // Layout / mapping (B200): one thread per ray (packets: 4 adjacent lanes = one RayPacket4, decisions
 // by quad vote).  Node = 8 x LDG.128 (Mbvh, 128 B = one L2 line) or a 64-byte adjacent child pair
-// (Bvh).  Triangles are 48-byte leaf-ordered records (3 x LDG.128, no index indirection).  The
+// (Bvh), fetched with 256-bit loads (4 resp. 2 LDG.256 per visit: one L1 wavefront per instruction
+// and lane).  Triangles are 64-byte leaf-ordered records (LDG.256 + LDG.128, no index indirection).  The
 // traversal stack lives in shared memory, [entry][thread] so it is bank-conflict free.
 #include "traverse.cuh"
 
@@ -25,8 +26,11 @@ namespace rtb {
 
 namespace {
 
-constexpr int kStackDepth = 64;  // reference: 32 (src/iter.rs:25); overflow is reported, never written
+constexpr int kSmemStack = 32;    // entries kept in shared memory (the reference's whole stack, src/iter.rs:25)
+constexpr int kSpillStack = 96;   // further entries spill to thread-local memory (only touched by deep rays); beyond 128 -> overflow flag
 constexpr int kBlock = 128;
+constexpr int kRefillIdle = 8;    // persistent kernels: refill a warp once this many lanes are idle
+constexpr unsigned kRayChunk = 256;  // rays a warp reserves per global atomic
 
 struct RayRegs {
     float ox, oy, oz;
@@ -56,8 +60,8 @@ __device__ __forceinline__ void finish_ray_setup(RayRegs& r) {
 // an earlier accepted hit) only lower the reported id (north-star rule).
 template <bool PACKET>
 __device__ __forceinline__ bool tri_candidate(const TriRec* __restrict__ tris, int pos, RayRegs& r) {
-    const float4 A = __ldg(&tris[pos].a);
-    const float4 E1 = __ldg(&tris[pos].b);
+    const F8 ab = ld256(&tris[pos].a);
+    const float4 A = ab.lo, E1 = ab.hi;
     const float4 E2 = __ldg(&tris[pos].c);
     // h = direction x edge2
     const float hx = fsub(fmul(r.dy, E2.z), fmul(E2.y, r.dz));
@@ -186,111 +190,123 @@ __device__ __forceinline__ int sel4(const int4 v, int s) { return s == 0 ? v.x :
     }
 
 struct Stack {
-    int* base;  // &smem[threadIdx.x]; entry e at base[e * kBlock]
+    int* base;     // &smem[threadIdx.x]; entry e < kSmemStack at base[e * kBlock]
+    int* spill;    // thread-local array; entry e >= kSmemStack at spill[e - kSmemStack]
     int sp;
     uint32_t* overflow;
     __device__ __forceinline__ void push(int v) {
-        if (sp < kStackDepth) {
+        if (sp < kSmemStack) {
             base[sp * kBlock] = v;
+            sp++;
+        } else if (sp < kSmemStack + kSpillStack) {
+            spill[sp - kSmemStack] = v;
             sp++;
         } else {
             *overflow = 1u;
         }
     }
-    __device__ __forceinline__ int pop() { return base[(--sp) * kBlock]; }
+    __device__ __forceinline__ int pop() {
+        --sp;
+        return sp < kSmemStack ? base[sp * kBlock] : spill[sp - kSmemStack];
+    }
+    __device__ __forceinline__ void reset() { sp = 0; }
 };
 
 // ================================================================================================
-// Mbvh, single rays  (MbvhIndexIterator)
+// Mbvh, single rays  (MbvhIndexIterator).  One call = one node visit; returns true when the ray is done.
 // ================================================================================================
 template <bool ANY>
-__device__ __forceinline__ void trace_mbvh_single(const DeviceTree& tree, RayRegs& r, Stack& st) {
-    const float4* __restrict__ nodes = tree.nodes;
-    int cur = 0;
-    for (;;) {
-        const float4* n = nodes + (size_t)cur * 8;
-        const float4 mnx = __ldg(n + 0), mxx = __ldg(n + 1), mny = __ldg(n + 2), mxy = __ldg(n + 3);
-        const float4 mnz = __ldg(n + 4), mxz = __ldg(n + 5);
-        const float4 chf = __ldg(n + 6), cnf = __ldg(n + 7);
-        const int4 ch = make_int4(__float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w));
-        const int4 cn = make_int4(__float_as_int(cnf.x), __float_as_int(cnf.y), __float_as_int(cnf.z), __float_as_int(cnf.w));
-        float key[4];
-        const uint32_t mask = r.exact ? mbvh_slabs<true>(mnx, mxx, mny, mxy, mnz, mxz, r, key)
-                                      : mbvh_slabs<false>(mnx, mxx, mny, mxy, mnz, mxz, r, key);
-        const uint32_t leafbits = (cn.x > -1 ? 1u : 0u) | (cn.y > -1 ? 2u : 0u) | (cn.z > -1 ? 4u : 0u) | (cn.w > -1 ? 8u : 0u);
-        const uint32_t childbits = (ch.x > -1 ? 1u : 0u) | (ch.y > -1 ? 2u : 0u) | (ch.z > -1 ? 4u : 0u) | (ch.w > -1 ? 8u : 0u);
-        // leaf slots: yield every primitive (iter_indices.rs:292-303)
-        uint32_t leaves = mask & leafbits;
-        while (leaves) {
-            const int s = __ffs(leaves) - 1;
-            leaves &= leaves - 1;
-            const int first = sel4(ch, s), count = sel4(cn, s);
-            for (int j = 0; j < count; j++) {
-                const bool hit = tri_candidate<false>(tree.tris, first + j, r);
-                if (ANY && hit) return;
-            }
+__device__ __forceinline__ bool mbvh_single_step(const DeviceTree& tree, RayRegs& r, Stack& st, int& cur) {
+    const float4* n = tree.nodes + (size_t)cur * 8;
+    const F8 q0 = ld256(n), q1 = ld256(n + 2), q2 = ld256(n + 4), q3 = ld256(n + 6);
+    const float4 mnx = q0.lo, mxx = q0.hi, mny = q1.lo, mxy = q1.hi, mnz = q2.lo, mxz = q2.hi;
+    const float4 chf = q3.lo, cnf = q3.hi;
+    const int4 ch = make_int4(__float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w));
+    const int4 cn = make_int4(__float_as_int(cnf.x), __float_as_int(cnf.y), __float_as_int(cnf.z), __float_as_int(cnf.w));
+    float key[4];
+    const uint32_t mask = r.exact ? mbvh_slabs<true>(mnx, mxx, mny, mxy, mnz, mxz, r, key)
+                                  : mbvh_slabs<false>(mnx, mxx, mny, mxy, mnz, mxz, r, key);
+    const uint32_t leafbits = (cn.x > -1 ? 1u : 0u) | (cn.y > -1 ? 2u : 0u) | (cn.z > -1 ? 4u : 0u) | (cn.w > -1 ? 8u : 0u);
+    const uint32_t childbits = (ch.x > -1 ? 1u : 0u) | (ch.y > -1 ? 2u : 0u) | (ch.z > -1 ? 4u : 0u) | (ch.w > -1 ? 8u : 0u);
+    // leaf slots: yield every primitive (iter_indices.rs:292-303)
+    uint32_t leaves = mask & leafbits;
+    while (leaves) {
+        const int s = __ffs(leaves) - 1;
+        leaves &= leaves - 1;
+        const int first = sel4(ch, s), count = sel4(cn, s);
+        for (int j = 0; j < count; j++) {
+            const bool hit = tri_candidate<false>(tree.tris, first + j, r);
+            if (ANY && hit) return true;
         }
-        // inner slots: push in the order ids[3], ids[2], ids[1], ids[0] (iter_indices.rs:287, :304-309)
-        const uint32_t inner = mask & ~leafbits & childbits;
-        if (inner) {
-            int pay[4] = {(inner & 1u) ? ch.x : -1, (inner & 2u) ? ch.y : -1, (inner & 4u) ? ch.z : -1, (inner & 8u) ? ch.w : -1};
-            // the reference's 5-comparator network; the last comparator swaps ids only (mbvh_node.rs:219-237)
-            RTB_CSWAP(0, 1)
-            RTB_CSWAP(2, 3)
-            RTB_CSWAP(0, 2)
-            RTB_CSWAP(1, 3)
-            if (key[2] > key[3]) {
-                int tp = pay[2];
-                pay[2] = pay[3];
-                pay[3] = tp;
-            }
-            if (pay[3] >= 0) st.push(pay[3]);
-            if (pay[2] >= 0) st.push(pay[2]);
-            if (pay[1] >= 0) st.push(pay[1]);
-            if (pay[0] >= 0) st.push(pay[0]);
-        }
-        if (st.sp == 0) return;
-        cur = st.pop();
     }
+    // inner slots: push in the order ids[3], ids[2], ids[1], ids[0] (iter_indices.rs:287, :304-309)
+    const uint32_t inner = mask & ~leafbits & childbits;
+    if (inner) {
+        int pay[4] = {(inner & 1u) ? ch.x : -1, (inner & 2u) ? ch.y : -1, (inner & 4u) ? ch.z : -1, (inner & 8u) ? ch.w : -1};
+        // the reference's 5-comparator network; the last comparator swaps ids only (mbvh_node.rs:219-237)
+        RTB_CSWAP(0, 1)
+        RTB_CSWAP(2, 3)
+        RTB_CSWAP(0, 2)
+        RTB_CSWAP(1, 3)
+        if (key[2] > key[3]) {
+            int tp = pay[2];
+            pay[2] = pay[3];
+            pay[3] = tp;
+        }
+        if (pay[3] >= 0) st.push(pay[3]);
+        if (pay[2] >= 0) st.push(pay[2]);
+        if (pay[1] >= 0) st.push(pay[1]);
+        if (pay[0] >= 0) st.push(pay[0]);
+    }
+    if (st.sp == 0) return true;
+    cur = st.pop();
+    return false;
 }
 
 // ================================================================================================
-// Bvh, single rays  (BvhIndexIterator)
+// Bvh, single rays  (BvhIndexIterator).  One call = one popped node (the root is popped without a box
+// test, iter_indices.rs:32-46); returns true when the stack is empty.
 // ================================================================================================
 template <bool ANY>
-__device__ __forceinline__ void trace_bvh_single(const DeviceTree& tree, RayRegs& r, Stack& st) {
+__device__ __forceinline__ bool bvh_single_step(const DeviceTree& tree, RayRegs& r, Stack& st, int& cur) {
     const float4* __restrict__ nodes = tree.nodes;
-    st.push(0);  // the root is pushed without a box test (iter_indices.rs:32-46)
-    while (st.sp > 0) {
-        const int cur = st.pop();
-        const float4 n0 = __ldg(nodes + (size_t)cur * 2), n1 = __ldg(nodes + (size_t)cur * 2 + 1);
-        const int count = __float_as_int(n0.w), left_first = __float_as_int(n1.w);
-        if (count > -1) {
-            for (int i = 0; i < count; i++) {
-                const bool hit = tri_candidate<false>(tree.tris, left_first + i, r);
-                if (ANY && hit) return;
-            }
-        } else if (left_first > -1) {
-            const float4* c = nodes + (size_t)left_first * 2;
-            const float4 l0 = __ldg(c), l1 = __ldg(c + 1), r0 = __ldg(c + 2), r1 = __ldg(c + 3);
-            float kl = 0.f, kr = 0.f;
-            const bool hl = aabb_single(l0, l1, r, kl);
-            const bool hr = aabb_single(r0, r1, r, kr);
-            if (hl && hr) {  // BvhNode::sort_nodes (bvh_node.rs:150-177)
-                if (kl < kr) {
-                    st.push(left_first);
-                    st.push(left_first + 1);
-                } else {
-                    st.push(left_first + 1);
-                    st.push(left_first);
-                }
-            } else if (hl) {
+    const F8 nd = ld256(nodes + (size_t)cur * 2);
+    const int count = __float_as_int(nd.lo.w), left_first = __float_as_int(nd.hi.w);
+    if (count > -1) {
+        for (int i = 0; i < count; i++) {
+            const bool hit = tri_candidate<false>(tree.tris, left_first + i, r);
+            if (ANY && hit) return true;
+        }
+    } else if (left_first > -1) {
+        const float4* c = nodes + (size_t)left_first * 2;
+        const F8 lc = ld256(c), rc = ld256(c + 2);
+        const float4 l0 = lc.lo, l1 = lc.hi, r0 = rc.lo, r1 = rc.hi;
+        float kl = 0.f, kr = 0.f;
+        const bool hl = aabb_single(l0, l1, r, kl);
+        const bool hr = aabb_single(r0, r1, r, kr);
+        if (hl && hr) {  // BvhNode::sort_nodes (bvh_node.rs:150-177)
+            if (kl < kr) {
                 st.push(left_first);
-            } else if (hr) {
                 st.push(left_first + 1);
+            } else {
+                st.push(left_first + 1);
+                st.push(left_first);
             }
+        } else if (hl) {
+            st.push(left_first);
+        } else if (hr) {
+            st.push(left_first + 1);
         }
     }
+    if (st.sp == 0) return true;
+    cur = st.pop();
+    return false;
+}
+
+template <int TREE, bool ANY>
+__device__ __forceinline__ bool single_step(const DeviceTree& tree, RayRegs& r, Stack& st, int& cur) {
+    if (TREE == RT_TREE_MBVH) return mbvh_single_step<ANY>(tree, r, st, cur);
+    return bvh_single_step<ANY>(tree, r, st, cur);
 }
 
 // ================================================================================================
@@ -321,9 +337,9 @@ __device__ __forceinline__ void trace_mbvh_packet(const DeviceTree& tree, RayReg
     int cur = 0;
     for (;;) {
         const float4* n = nodes + (size_t)cur * 8;
-        const float4 mnx = __ldg(n + 0), mxx = __ldg(n + 1), mny = __ldg(n + 2), mxy = __ldg(n + 3);
-        const float4 mnz = __ldg(n + 4), mxz = __ldg(n + 5);
-        const float4 chf = __ldg(n + 6), cnf = __ldg(n + 7);
+        const F8 q0 = ld256(n), q1 = ld256(n + 2), q2 = ld256(n + 4), q3 = ld256(n + 6);
+        const float4 mnx = q0.lo, mxx = q0.hi, mny = q1.lo, mxy = q1.hi, mnz = q2.lo, mxz = q2.hi;
+        const float4 chf = q3.lo, cnf = q3.hi;
         const int4 ch = make_int4(__float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w));
         const int4 cn = make_int4(__float_as_int(cnf.x), __float_as_int(cnf.y), __float_as_int(cnf.z), __float_as_int(cnf.w));
         const uint32_t mine = r.exact ? mbvh_slabs_lane<true>(mnx, mxx, mny, mxy, mnz, mxz, r)
@@ -353,14 +369,15 @@ __device__ __forceinline__ void trace_bvh_packet(const DeviceTree& tree, RayRegs
     st.push(0);
     while (st.sp > 0) {
         const int cur = st.pop();
-        const float4 n0 = __ldg(nodes + (size_t)cur * 2), n1 = __ldg(nodes + (size_t)cur * 2 + 1);
-        const int count = __float_as_int(n0.w), left_first = __float_as_int(n1.w);
+        const F8 nd = ld256(nodes + (size_t)cur * 2);
+        const int count = __float_as_int(nd.lo.w), left_first = __float_as_int(nd.hi.w);
         if (count > -1) {
             for (int i = 0; i < count; i++)
                 if (packet_candidate<ANY>(tree.tris, left_first + i, r, retired, qm)) return;
         } else if (left_first > -1) {
             const float4* c = nodes + (size_t)left_first * 2;
-            const float4 l0 = __ldg(c), l1 = __ldg(c + 1), r0 = __ldg(c + 2), r1 = __ldg(c + 3);
+            const F8 lc = ld256(c), rc = ld256(c + 2);
+            const float4 l0 = lc.lo, l1 = lc.hi, r0 = rc.lo, r1 = rc.hi;
             float kl, kr;
             const bool ml = r.exact ? aabb_lane<true>(l0, l1, r, kl) : aabb_lane<false>(l0, l1, r, kl);
             const bool mr = r.exact ? aabb_lane<true>(r0, r1, r, kr) : aabb_lane<false>(r0, r1, r, kr);
@@ -385,31 +402,109 @@ __device__ __forceinline__ void trace_bvh_packet(const DeviceTree& tree, RayRegs
 // ================================================================================================
 // kernels
 // ================================================================================================
+__device__ __forceinline__ void load_ray(const RTRay* __restrict__ rays, size_t i, RayRegs& r) {
+    const F8 ab = ld256(reinterpret_cast<const float4*>(rays) + i * 2);
+    const float4 a = ab.lo, b = ab.hi;
+    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.t_min = a.w;
+    r.dx = b.x; r.dy = b.y; r.dz = b.z; r.t = b.w;
+    finish_ray_setup(r);
+}
+template <bool ANY>
+__device__ __forceinline__ void store_result(const RayRegs& r, size_t i, RTHit* __restrict__ hits,
+                                             uint8_t* __restrict__ occluded) {
+    if (ANY)
+        occluded[i] = r.prim != kNoHit ? 1 : 0;
+    else
+        reinterpret_cast<float2*>(hits)[i] = make_float2(r.t, __uint_as_float(r.prim));
+}
+
+// Static assignment: thread i traces ray i.  Kept for A/B runs (RTBVH_TRACE_MODE=static) and for
+// small batches; a warp lives as long as its slowest ray.
 template <int TREE, bool ANY>
 __global__ void __launch_bounds__(kBlock) trace_single_kernel(const DeviceTree tree, const RTRay* __restrict__ rays,
                                                               size_t n, RTHit* __restrict__ hits,
                                                               uint8_t* __restrict__ occluded,
                                                               uint32_t* __restrict__ overflow) {
-    __shared__ int smem[kStackDepth * kBlock];
+    __shared__ int smem[kSmemStack * kBlock];
+    int deep[kSpillStack];
     const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + i * 2);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(rays) + i * 2 + 1);
     RayRegs r;
-    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.t_min = a.w;
-    r.dx = b.x; r.dy = b.y; r.dz = b.z; r.t = b.w;
-    finish_ray_setup(r);
-    Stack st{smem + threadIdx.x, 0, overflow};
+    load_ray(rays, i, r);
+    Stack st{smem + threadIdx.x, deep, 0, overflow};
     if (tree.node_count != 0 && !r.nan) {
-        if (TREE == RT_TREE_MBVH)
-            trace_mbvh_single<ANY>(tree, r, st);
-        else
-            trace_bvh_single<ANY>(tree, r, st);
+        int cur = 0;
+        while (!single_step<TREE, ANY>(tree, r, st, cur)) {
+        }
     }
-    if (ANY)
-        occluded[i] = r.prim != kNoHit ? 1 : 0;
-    else
-        reinterpret_cast<float2*>(hits)[i] = make_float2(r.t, __uint_as_float(r.prim));
+    store_result<ANY>(r, i, hits, occluded);
+}
+
+// Persistent warps with dynamic ray refill (the "persistent-thread, warp-cooperative" kernel of the
+// north star): the grid is sized to the machine (SMs x resident blocks), every warp reserves rays in
+// chunks of kRayChunk from a global counter and, whenever kRefillIdle or more lanes have finished,
+// hands the idle lanes the next rays (ballot + prefix popcount).  Lanes therefore sit at different
+// depths of different rays, but all execute the same node-visit step, which keeps the SIMD lanes
+// busy when ray lengths differ (one missing ray no longer pins 31 idle lanes).
+template <int TREE, bool ANY>
+__global__ void __launch_bounds__(kBlock) trace_single_persistent_kernel(const DeviceTree tree,
+                                                                         const RTRay* __restrict__ rays, size_t n,
+                                                                         RTHit* __restrict__ hits,
+                                                                         uint8_t* __restrict__ occluded,
+                                                                         unsigned long long* __restrict__ counter,
+                                                                         uint32_t* __restrict__ overflow) {
+    __shared__ int smem[kSmemStack * kBlock];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int deep[kSpillStack];
+    Stack st{smem + threadIdx.x, deep, 0, overflow};
+    RayRegs r;
+    int cur = 0;
+    size_t my = 0;
+    bool active = false;
+    unsigned long long res_next = 0, res_end = 0;  // this warp's reserved index range (warp-uniform)
+    bool exhausted = false;                        // the global counter ran past n (warp-uniform)
+    for (;;) {
+        unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (idle == 0xFFFFFFFFu || (!exhausted && __popc(idle) >= kRefillIdle)) {
+            while (idle != 0 && !exhausted) {
+                if (res_next >= res_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(counter, (unsigned long long)kRayChunk);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (base >= n) {
+                        exhausted = true;
+                        break;
+                    }
+                    res_next = base;
+                    res_end = base + kRayChunk < n ? base + kRayChunk : n;
+                }
+                const unsigned long long avail = res_end - res_next;
+                const unsigned want = __popc(idle);
+                const unsigned take = avail < want ? (unsigned)avail : want;
+                const unsigned rank = __popc(idle & lt_mask);
+                if (!active && rank < take) {
+                    my = (size_t)(res_next + rank);
+                    load_ray(rays, my, r);
+                    st.reset();
+                    cur = 0;
+                    if (tree.node_count != 0 && !r.nan)
+                        active = true;
+                    else
+                        store_result<ANY>(r, my, hits, occluded);
+                }
+                res_next += take;
+                idle = __ballot_sync(0xFFFFFFFFu, !active);
+            }
+            if (idle == 0xFFFFFFFFu) break;  // nothing left to trace for this warp
+        }
+        if (active) {
+            if (single_step<TREE, ANY>(tree, r, st, cur)) {
+                store_result<ANY>(r, my, hits, occluded);
+                active = false;
+            }
+        }
+    }
 }
 
 template <int TREE, bool ANY>
@@ -418,7 +513,7 @@ __global__ void __launch_bounds__(kBlock) trace_packet_kernel(const DeviceTree t
                                                               float t_min, RTHitPacket4* __restrict__ hits,
                                                               uint8_t* __restrict__ occluded,
                                                               uint32_t* __restrict__ overflow) {
-    __shared__ int smem[kStackDepth * kBlock];
+    __shared__ int smem[kSmemStack * kBlock];
     const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;  // ray index; packet = i / 4
     const size_t p = i >> 2;
     const int lane = (int)(i & 3);
@@ -431,7 +526,8 @@ __global__ void __launch_bounds__(kBlock) trace_packet_kernel(const DeviceTree t
     r.t_min = t_min;
     finish_ray_setup(r);
     const uint32_t qm = quad_mask();
-    Stack st{smem + threadIdx.x, 0, overflow};
+    int deep[kSpillStack];
+    Stack st{smem + threadIdx.x, deep, 0, overflow};
     bool retired = false;
     // BvhPacketIndexIterator rejects the packet when ANY lane has a NaN (iter_indices.rs:129-144);
     // MbvhPacketIndexIterator has no such check (the NaN lane just never passes a comparison).
@@ -465,10 +561,12 @@ __global__ void gather_tris_kernel(const float* __restrict__ verts, uint32_t str
         rec.a = make_float4(v0x, v0y, v0z, __uint_as_float(id));
         rec.b = make_float4(fsub(v1x, v0x), fsub(v1y, v0y), fsub(v1z, v0z), 0.f);
         rec.c = make_float4(fsub(v2x, v0x), fsub(v2y, v0y), fsub(v2z, v0z), 0.f);
+        rec.d = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {  // out-of-range id (never produced by the builders): degenerate triangle, never hit
         rec.a = make_float4(0.f, 0.f, 0.f, __uint_as_float(id));
         rec.b = make_float4(0.f, 0.f, 0.f, 0.f);
         rec.c = make_float4(0.f, 0.f, 0.f, 0.f);
+        rec.d = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     out[k] = rec;
 }
@@ -509,22 +607,44 @@ __global__ void camera_rays_kernel(float3 pos, float3 p1, float3 right, float3 u
 }  // namespace
 
 // ---- launchers ----------------------------------------------------------------------------------
-cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any, const RTRay* d_rays, size_t n,
-                                RTHit* d_hits, uint8_t* d_occluded, uint32_t* d_overflow, cudaStream_t stream) {
-    if (n == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)ceil_div(n, kBlock);
-    if (tree_kind == RT_TREE_MBVH) {
-        if (any)
-            trace_single_kernel<RT_TREE_MBVH, true><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_overflow);
-        else
-            trace_single_kernel<RT_TREE_MBVH, false><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_overflow);
+// grid of a persistent kernel: resident blocks per SM x number of SMs (queried once per kernel)
+template <class K>
+static unsigned persistent_grid(K kernel) {
+    int dev = 0, sms = kSmCount, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0);
+    return (unsigned)(sms * (per_sm > 0 ? per_sm : 1));
+}
+
+template <int TREE, bool ANY>
+static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
+                                   uint8_t* d_occluded, unsigned long long* d_counter, uint32_t* d_overflow,
+                                   bool persistent, cudaStream_t stream) {
+    const size_t blocks_needed = ceil_div(n, kBlock);
+    if (persistent) {
+        static const unsigned machine = persistent_grid(trace_single_persistent_kernel<TREE, ANY>);
+        const unsigned grid = (unsigned)(blocks_needed < machine ? blocks_needed : machine);
+        cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+        trace_single_persistent_kernel<TREE, ANY><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded,
+                                                                              d_counter, d_overflow);
     } else {
-        if (any)
-            trace_single_kernel<RT_TREE_BVH, true><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_overflow);
-        else
-            trace_single_kernel<RT_TREE_BVH, false><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_overflow);
+        trace_single_kernel<TREE, ANY><<<(unsigned)blocks_needed, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded,
+                                                                                     d_overflow);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any, const RTRay* d_rays, size_t n,
+                                RTHit* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
+                                uint32_t* d_overflow, bool persistent, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    if (tree_kind == RT_TREE_MBVH)
+        return any ? launch_single_t<RT_TREE_MBVH, true>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, persistent, stream)
+                   : launch_single_t<RT_TREE_MBVH, false>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, persistent, stream);
+    return any ? launch_single_t<RT_TREE_BVH, true>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, persistent, stream)
+               : launch_single_t<RT_TREE_BVH, false>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, persistent, stream);
 }
 
 cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,
