@@ -527,6 +527,13 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A, cons
     }
 }
 
+// {pairs, next task count} of the level = last exclusive rank + last value
+__global__ void sah_totals_kernel(const uint32_t* pair_rank, const uint32_t* splitf, const uint32_t* task_rank,
+                                  const uint32_t* ntask, uint32_t A, uint32_t* out) {
+    out[0] = pair_rank[A - 1] + splitf[A - 1];
+    out[1] = task_rank[A - 1] + ntask[A - 1];
+}
+
 // partition predicate (binned_sah.rs:213-219) for every index position
 __global__ void sah_flag_kernel(const uint32_t* __restrict__ idx, const int32_t* __restrict__ pos_task, uint32_t n,
                                 const TaskAux* __restrict__ aux, const Decision* __restrict__ dec,
@@ -677,20 +684,34 @@ __global__ void parents_kernel(const float4* __restrict__ nodes, uint32_t n_node
         parent[l + 1] = (int32_t)i;
     }
 }
-// depth by walking up; m-roots = inner nodes at even depth (every second level of merge_nodes' recursion).
-// Each m-root adds 1 to the subtree counter of itself and of every ancestor.
-__global__ void mroot_count_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const int32_t* __restrict__ parent,
-                                   uint8_t* __restrict__ is_mroot, uint32_t* __restrict__ sub) {
+// depth by walking up (reads only); m-roots = inner nodes at even depth (every second level of
+// merge_nodes' recursion).
+__global__ void mroot_flag_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const int32_t* __restrict__ parent,
+                                  uint8_t* __restrict__ is_mroot) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     const bool inner = node_count_of(nodes, i) < 0 && node_left_of(nodes, i) >= 0;
     uint32_t depth = 0;
     for (int p = parent[i]; p >= 0; p = parent[p]) depth++;
-    const bool m = inner && (depth & 1u) == 0u;
-    is_mroot[i] = m ? 1 : 0;
-    if (m) {
-        atomicAdd(&sub[i], 1u);
-        for (int p = parent[i]; p >= 0; p = parent[p]) atomicAdd(&sub[p], 1u);
+    is_mroot[i] = (inner && (depth & 1u) == 0u) ? 1 : 0;
+}
+// sub[i] = number of m-roots in the subtree of i, bottom-up: every leaf climbs, the second child to
+// arrive at a node finishes it (one arrival counter per node, no contended counters).
+__global__ void mroot_sub_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const int32_t* __restrict__ parent,
+                                 const uint8_t* __restrict__ is_mroot, uint32_t* sub, uint32_t* __restrict__ arrived) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    if (!(node_count_of(nodes, i) >= 0 || node_left_of(nodes, i) < 0)) return;  // start from leaves (and invalid nodes)
+    sub[i] = 0;
+    int cur = (int)i;
+    for (;;) {
+        const int p = parent[cur];
+        if (p < 0) break;
+        __threadfence();
+        if (atomicAdd(&arrived[p], 1u) == 0u) break;
+        const int l = node_left_of(nodes, p);
+        sub[p] = __ldcg(&sub[l]) + __ldcg(&sub[l + 1]) + (uint32_t)is_mroot[p];
+        cur = p;
     }
 }
 // pre-order (depth-first, slot order) index of every m-root == the pool_ptr numbering of merge_nodes
@@ -796,16 +817,36 @@ __global__ void refit_kernel(float4* nodes, uint32_t n_nodes, const int32_t* __r
 }
 
 // ---- small RAII helpers ----------------------------------------------------------------------------
+// Stream-ordered allocations from the device's default memory pool (release threshold raised once):
+// after the first build the builders' scratch buffers come out of the pool without touching the driver.
+static void tune_pool_once() {
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done = true;
+}
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
-    ~DevBuf() { cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, 0);
+    }
     cudaError_t alloc(size_t b) {
         if (b <= bytes) return cudaSuccess;
-        cudaFree(p);
+        tune_pool_once();
+        if (p) cudaFreeAsync(p, 0);
         p = nullptr;
         bytes = 0;
-        cudaError_t e = cudaMalloc(&p, b ? b : 16);
+        cudaError_t e = cudaMallocAsync(&p, b ? b : 16, 0);
         if (e == cudaSuccess) bytes = b;
         return e;
     }
@@ -927,13 +968,12 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         RTB_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tbytes, splitf.as<uint32_t>(), pair_rank.as<uint32_t>(), (int)A));
         tbytes = temp.bytes;
         RTB_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tbytes, ntask.as<uint32_t>(), task_rank.as<uint32_t>(), (int)A));
-        // totals: pairs and next tasks = last rank + last value
-        uint32_t h[4];
-        RTB_CUDA(cudaMemcpy(&h[0], pair_rank.as<uint32_t>() + (A - 1), 4, cudaMemcpyDeviceToHost));
-        RTB_CUDA(cudaMemcpy(&h[1], splitf.as<uint32_t>() + (A - 1), 4, cudaMemcpyDeviceToHost));
-        RTB_CUDA(cudaMemcpy(&h[2], task_rank.as<uint32_t>() + (A - 1), 4, cudaMemcpyDeviceToHost));
-        RTB_CUDA(cudaMemcpy(&h[3], ntask.as<uint32_t>() + (A - 1), 4, cudaMemcpyDeviceToHost));
-        const uint32_t pairs = h[0] + h[1], next_A = h[2] + h[3];
+        // one small D2H per level: the host needs the next level's task count to size its launches
+        sah_totals_kernel<<<1, 1>>>(pair_rank.as<uint32_t>(), splitf.as<uint32_t>(), task_rank.as<uint32_t>(),
+                                    ntask.as<uint32_t>(), A, totals.as<uint32_t>());
+        uint32_t h[2];
+        RTB_CUDA(cudaMemcpy(h, totals.p, 8, cudaMemcpyDeviceToHost));
+        const uint32_t pairs = h[0], next_A = h[1];
         if ((size_t)next_A * 2 * sizeof(Task) > tasksB.bytes) {
             RTB_CUDA(tasksB.alloc((size_t)next_A * 2 * sizeof(Task)));
             t_nxt = tasksB.as<Task>();
@@ -1069,15 +1109,19 @@ static ResultCode collapse_device(const float4* d_nodes, uint32_t n_nodes, DevBu
         *m_count = 1;
         return Ok;
     }
-    DevBuf parent, is_m, sub, mindex;
+    DevBuf parent, is_m, sub, mindex, arrived;
     RTB_CUDA(parent.alloc((size_t)n_nodes * 4));
     RTB_CUDA(is_m.alloc(n_nodes));
     RTB_CUDA(sub.alloc((size_t)n_nodes * 4));
     RTB_CUDA(mindex.alloc((size_t)n_nodes * 4));
-    RTB_CUDA(cudaMemset(sub.p, 0, (size_t)n_nodes * 4));
-    RTB_CUDA(cudaMemset(parent.p, 0xFF, (size_t)n_nodes * 4));
+    RTB_CUDA(arrived.alloc((size_t)n_nodes * 4));
+    RTB_CUDA(cudaMemsetAsync(sub.p, 0, (size_t)n_nodes * 4, 0));
+    RTB_CUDA(cudaMemsetAsync(arrived.p, 0, (size_t)n_nodes * 4, 0));
+    RTB_CUDA(cudaMemsetAsync(parent.p, 0xFF, (size_t)n_nodes * 4, 0));
     parents_kernel<<<blocks(n_nodes, 256), 256>>>(d_nodes, n_nodes, parent.as<int32_t>());
-    mroot_count_kernel<<<blocks(n_nodes, 256), 256>>>(d_nodes, n_nodes, parent.as<int32_t>(), is_m.as<uint8_t>(), sub.as<uint32_t>());
+    mroot_flag_kernel<<<blocks(n_nodes, 256), 256>>>(d_nodes, n_nodes, parent.as<int32_t>(), is_m.as<uint8_t>());
+    mroot_sub_kernel<<<blocks(n_nodes, 256), 256>>>(d_nodes, n_nodes, parent.as<int32_t>(), is_m.as<uint8_t>(),
+                                                    sub.as<uint32_t>(), arrived.as<uint32_t>());
     uint32_t total = 0;
     RTB_CUDA(cudaMemcpy(&total, sub.p, 4, cudaMemcpyDeviceToHost));
     RTB_CUDA(mnodes->alloc((size_t)total * 128));
