@@ -190,7 +190,19 @@ def run_gpu(args):
 
     tris = build_scene_host()
     info = {}
-    bvh, mbvh, info = build_trees(api, tris, info, rank)
+    if world == 1:
+        bvh, mbvh, info = build_trees(api, tris, info, rank)
+    else:
+        # the tree is built once (rank 0) and replicated: one broadcast per scene over NCCL
+        from rtbvh_b200 import multigpu as MG
+        arrays = None
+        if rank == 0:
+            bvh, mbvh, info = build_trees(api, tris, info, rank)
+            arrays = {"mnodes": mbvh.nodes, "indices": mbvh.indices}
+        arrays = MG.broadcast_arrays(arrays, src=0, device="cuda")
+        if rank != 0:
+            mbvh = api.Mbvh.from_arrays(arrays["mnodes"], arrays["indices"])
+        info["replication"] = "tree built on rank 0, broadcast over NCCL, one replica per GPU"
     scene = api.Scene(tris, bvh=None, mbvh=mbvh)
 
     fps = args.frames_per_step
@@ -215,9 +227,19 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # hit records of every rank are gathered over NVLink (all_gather, 8 B per ray), asynchronously so that the
+    # transfer of step k overlaps the traversal of step k+1
+    gather = world > 1 and not args.no_gather
+    g_out = [torch.empty(world * rays_per_step * 2, dtype=torch.float32, device="cuda") for _ in range(2)] if gather else None
+    works = []
+
     def step(k):
         b = k % ring
         scene.intersect_device(d_rays[b], rays_per_step, d_hits[b], api.TREE_MBVH, stream=stream)
+        if gather:
+            if len(works) >= 2:
+                works[-2].wait()  # the output buffer about to be reused
+            works.append(dist.all_gather_into_tensor(g_out[k % 2], d_hits[b], async_op=True))
 
     for k in range(args.warmup):
         step(k)
@@ -229,6 +251,8 @@ def run_gpu(args):
     ev0.record()
     for k in range(args.steps):
         step(args.warmup + k)
+    for w in works[-2:]:
+        w.wait()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -297,7 +321,10 @@ def run_gpu(args):
             "config": {"workload": "soup-1Mi-tris binned-SAH Mbvh primary rays closest-hit (BASELINE configs[1])",
                        "rays_per_step": rays_per_step, "frames_per_step": fps, "ray_ring_batches": ring,
                        "l2": "inputs larger than L2 (256 MB rays per step, distinct buffers)",
-                       "trace_mode": os.environ.get("RTBVH_TRACE_MODE", "persistent"), **info},
+                       "trace_mode": os.environ.get("RTBVH_TRACE_MODE", "persistent"),
+                       "sharding": ("rays sharded by frame range, tree replicated; hit records all_gathered over NVLink "
+                                    f"({world * rays_per_step * 8} B per step per GPU, overlapped)" if gather else
+                                    "single GPU" if world == 1 else "rays sharded, tree replicated, no gather"), **info},
             "clocks": clocks, "gpu_launches": args.steps,
             "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": rays_per_step * 32,
                     "d2h_bytes_per_step": rays_per_step * 8, "steps": e2e_steps, "host_equals_resident": same},
@@ -348,7 +375,18 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / roofline sample (profiling runs)")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: do not all_gather the hit records")
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: `python bench.py --gpus N` re-launches itself one rank per GPU (the driver uses torchrun directly)
+        import socket
+        sock = socket.socket()
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+        sock.close()
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", str(port),
+                                   os.path.abspath(__file__)] + sys.argv[1:])
     if args.impl == "reference":
         run_reference(args)
     else:

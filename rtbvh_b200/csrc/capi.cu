@@ -43,11 +43,17 @@ constexpr int kPipeStreams = 3;                  // H2D / kernel / D2H of consec
 constexpr size_t kChunkRays = size_t(1) << 21;   // 2 Mi rays (64 MiB of RTRay) per pipeline stage
 constexpr uint32_t kCounterSlots = 1024;
 
-// RTBVH_TRACE_MODE=static selects the one-thread-per-ray kernel without refill (A/B measurements only)
-bool persistent_mode() {
-    static const bool v = [] {
+// RTBVH_TRACE_MODE selects the single-ray kernel variant (A/B measurements); default: see kDefaultTraceMode
+constexpr int kDefaultTraceMode = kTracePersistent;
+int persistent_mode() {
+    static const int v = [] {
         const char* e = std::getenv("RTBVH_TRACE_MODE");
-        return !(e && std::string(e) == "static");
+        if (!e) return kDefaultTraceMode;
+        const std::string m(e);
+        if (m == "static") return (int)kTraceStatic;
+        if (m == "persistent") return (int)kTracePersistent;
+        if (m == "coop") return (int)kTraceCoop;
+        return kDefaultTraceMode;
     }();
     return v;
 }

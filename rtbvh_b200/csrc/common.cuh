@@ -46,6 +46,9 @@ static_assert(sizeof(TriRec) == 64, "");
 // 256-bit read-only global load (PTX ISA 8.8, sm_100+: SASS LDG.E.ENL2.256.CONSTANT).  A lane that
 // fetches its own node pays one L1 wavefront per load instruction, so halving the instruction count
 // halves the L1 data-pipe work of a node visit.  RTB_LD256=0 builds the 2 x LDG.128 variant for A/B.
+#ifndef RTB_PREFETCH
+#define RTB_PREFETCH 1
+#endif
 #ifndef RTB_LD256
 #define RTB_LD256 1
 #endif

@@ -29,7 +29,13 @@ namespace {
 constexpr int kSmemStack = 32;    // entries kept in shared memory (the reference's whole stack, src/iter.rs:25)
 constexpr int kSpillStack = 96;   // further entries spill to thread-local memory (only touched by deep rays); beyond 128 -> overflow flag
 constexpr int kBlock = 128;
-constexpr int kRefillIdle = 8;    // persistent kernels: refill a warp once this many lanes are idle
+#ifndef RTB_REFILL
+#define RTB_REFILL 8
+#endif
+#ifndef RTB_MINBLOCKS
+#define RTB_MINBLOCKS 1
+#endif
+constexpr int kRefillIdle = RTB_REFILL;  // persistent kernels: refill a warp once this many lanes are idle
 constexpr unsigned kRayChunk = 256;  // rays a warp reserves per global atomic
 
 struct RayRegs {
@@ -177,6 +183,13 @@ __device__ __forceinline__ uint32_t mbvh_slabs_lane(const float4 mnx, const floa
     return mask;
 }
 
+// L1 prefetch of the 128-byte line at p (no destination register)
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#if RTB_PREFETCH
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+
 __device__ __forceinline__ int sel4(const int4 v, int s) { return s == 0 ? v.x : (s == 1 ? v.y : (s == 2 ? v.z : v.w)); }
 
 #define RTB_CSWAP(i, j)                 \
@@ -213,33 +226,34 @@ struct Stack {
 };
 
 // ================================================================================================
-// Mbvh, single rays  (MbvhIndexIterator).  One call = one node visit; returns true when the ray is done.
+// Mbvh, single rays  (MbvhIndexIterator).
 // ================================================================================================
-template <bool ANY>
-__device__ __forceinline__ bool mbvh_single_step(const DeviceTree& tree, RayRegs& r, Stack& st, int& cur) {
-    const float4* n = tree.nodes + (size_t)cur * 8;
+struct MNode {  // one 128-byte MbvhNode in registers
+    float4 mnx, mxx, mny, mxy, mnz, mxz;
+    int4 ch, cn;
+};
+__device__ __forceinline__ int4 as_int4(const float4 f) {
+    return make_int4(__float_as_int(f.x), __float_as_int(f.y), __float_as_int(f.z), __float_as_int(f.w));
+}
+__device__ __forceinline__ MNode mnode_load_global(const float4* __restrict__ nodes, int cur) {
+    const float4* n = nodes + (size_t)cur * 8;
     const F8 q0 = ld256(n), q1 = ld256(n + 2), q2 = ld256(n + 4), q3 = ld256(n + 6);
-    const float4 mnx = q0.lo, mxx = q0.hi, mny = q1.lo, mxy = q1.hi, mnz = q2.lo, mxz = q2.hi;
-    const float4 chf = q3.lo, cnf = q3.hi;
-    const int4 ch = make_int4(__float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w));
-    const int4 cn = make_int4(__float_as_int(cnf.x), __float_as_int(cnf.y), __float_as_int(cnf.z), __float_as_int(cnf.w));
+    return MNode{q0.lo, q0.hi, q1.lo, q1.hi, q2.lo, q2.hi, as_int4(q3.lo), as_int4(q3.hi)};
+}
+
+// Node entry: MbvhNode::intersect with the ray.t of this moment, then the inner slots are pushed in the
+// order ids[3], ids[2], ids[1], ids[0] (iter_indices.rs:287, :304-309).  The pushes do not depend on what
+// the leaf slots of this node do to ray.t (the slot results are frozen at node entry), so they are done
+// BEFORE the leaf slots: the next node is then known early and can be fetched while triangles are tested.
+// Returns the next node (-1: stack empty); `leaves` = hit leaf slots still to be tested.
+__device__ __forceinline__ int mbvh_visit_push(const MNode& nd, const RayRegs& r, Stack& st, uint32_t& leaves) {
     float key[4];
-    const uint32_t mask = r.exact ? mbvh_slabs<true>(mnx, mxx, mny, mxy, mnz, mxz, r, key)
-                                  : mbvh_slabs<false>(mnx, mxx, mny, mxy, mnz, mxz, r, key);
+    const uint32_t mask = r.exact ? mbvh_slabs<true>(nd.mnx, nd.mxx, nd.mny, nd.mxy, nd.mnz, nd.mxz, r, key)
+                                  : mbvh_slabs<false>(nd.mnx, nd.mxx, nd.mny, nd.mxy, nd.mnz, nd.mxz, r, key);
+    const int4 ch = nd.ch, cn = nd.cn;
     const uint32_t leafbits = (cn.x > -1 ? 1u : 0u) | (cn.y > -1 ? 2u : 0u) | (cn.z > -1 ? 4u : 0u) | (cn.w > -1 ? 8u : 0u);
     const uint32_t childbits = (ch.x > -1 ? 1u : 0u) | (ch.y > -1 ? 2u : 0u) | (ch.z > -1 ? 4u : 0u) | (ch.w > -1 ? 8u : 0u);
-    // leaf slots: yield every primitive (iter_indices.rs:292-303)
-    uint32_t leaves = mask & leafbits;
-    while (leaves) {
-        const int s = __ffs(leaves) - 1;
-        leaves &= leaves - 1;
-        const int first = sel4(ch, s), count = sel4(cn, s);
-        for (int j = 0; j < count; j++) {
-            const bool hit = tri_candidate<false>(tree.tris, first + j, r);
-            if (ANY && hit) return true;
-        }
-    }
-    // inner slots: push in the order ids[3], ids[2], ids[1], ids[0] (iter_indices.rs:287, :304-309)
+    leaves = mask & leafbits;
     const uint32_t inner = mask & ~leafbits & childbits;
     if (inner) {
         int pay[4] = {(inner & 1u) ? ch.x : -1, (inner & 2u) ? ch.y : -1, (inner & 4u) ? ch.z : -1, (inner & 8u) ? ch.w : -1};
@@ -258,8 +272,33 @@ __device__ __forceinline__ bool mbvh_single_step(const DeviceTree& tree, RayRegs
         if (pay[1] >= 0) st.push(pay[1]);
         if (pay[0] >= 0) st.push(pay[0]);
     }
-    if (st.sp == 0) return true;
-    cur = st.pop();
+    return st.sp > 0 ? st.pop() : -1;
+}
+// leaf slots: yield every primitive (iter_indices.rs:292-303).  Returns true when an any-hit query is done.
+template <bool ANY>
+__device__ __forceinline__ bool mbvh_visit_leaves(const int4 ch, const int4 cn, uint32_t leaves, const DeviceTree& tree,
+                                                  RayRegs& r) {
+    while (leaves) {
+        const int s = __ffs(leaves) - 1;
+        leaves &= leaves - 1;
+        const int first = sel4(ch, s), count = sel4(cn, s);
+        for (int j = 0; j < count; j++) {
+            const bool hit = tri_candidate<false>(tree.tris, first + j, r);
+            if (ANY && hit) return true;
+        }
+    }
+    return false;
+}
+// One call = one node visit; returns true when the ray is done.
+template <bool ANY>
+__device__ __forceinline__ bool mbvh_single_step(const DeviceTree& tree, RayRegs& r, Stack& st, int& cur) {
+    const MNode nd = mnode_load_global(tree.nodes, cur);
+    uint32_t leaves;
+    const int next = mbvh_visit_push(nd, r, st, leaves);
+    if (next >= 0) prefetch_l1(tree.nodes + (size_t)next * 8);
+    if (mbvh_visit_leaves<ANY>(nd.ch, nd.cn, leaves, tree, r)) return true;
+    if (next < 0) return true;
+    cur = next;
     return false;
 }
 
@@ -447,7 +486,7 @@ __global__ void __launch_bounds__(kBlock) trace_single_kernel(const DeviceTree t
 // depths of different rays, but all execute the same node-visit step, which keeps the SIMD lanes
 // busy when ray lengths differ (one missing ray no longer pins 31 idle lanes).
 template <int TREE, bool ANY>
-__global__ void __launch_bounds__(kBlock) trace_single_persistent_kernel(const DeviceTree tree,
+__global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent_kernel(const DeviceTree tree,
                                                                          const RTRay* __restrict__ rays, size_t n,
                                                                          RTHit* __restrict__ hits,
                                                                          uint8_t* __restrict__ occluded,
@@ -505,6 +544,124 @@ __global__ void __launch_bounds__(kBlock) trace_single_persistent_kernel(const D
             }
         }
     }
+}
+
+// ---- lane-cooperative node fetch -------------------------------------------------------------------
+// When every lane fetches its own 128-byte node, the L1 data pipe moves 16 bytes per wavefront (one
+// wavefront per lane and 16-byte chunk: 256 per warp and visit) and becomes the limiter (ncu:
+// l1tex__data_pipe_lsu_wavefronts ~70 % with long-scoreboard stalls).  Here the 8 lanes of a group
+// fetch ONE node together — lane j copies chunk j with cp.async (LDGSTS), a full 128-byte line per
+// wavefront — into a per-warp shared-memory tile, and every lane then reads its own node back with
+// conflict-free LDS.128 (144-byte row stride).  ~3x fewer data-pipe wavefronts per visit, and the copy
+// of the NEXT node is issued before the triangles of the current node are tested.
+constexpr int kNodeRowWords = 36;  // 128-byte node + 16 bytes of padding: LDS.128 of 8 lanes hits 32 distinct banks
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Collective over the warp: lane L wants node `want` (or -1).  Group g = L / 8 serves its 8 owners in turn.
+__device__ __forceinline__ void coop_fetch(const float4* __restrict__ nodes, int want, float* warp_tile, unsigned lane) {
+    const unsigned sub = lane & 7u, base = lane & 24u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int c = __shfl_sync(0xFFFFFFFFu, want, (int)(base + i));
+        if (c >= 0) cp_async16(warp_tile + (base + i) * kNodeRowWords + sub * 4, nodes + (size_t)c * 8 + sub);
+    }
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock, 6) trace_mbvh_coop_kernel(const DeviceTree tree,
+                                                                                const RTRay* __restrict__ rays, size_t n,
+                                                                                RTHit* __restrict__ hits,
+                                                                                uint8_t* __restrict__ occluded,
+                                                                                unsigned long long* __restrict__ counter,
+                                                                                uint32_t* __restrict__ overflow) {
+    __shared__ int smem[kSmemStack * kBlock];
+    __shared__ __align__(16) float tiles[(kBlock / 32) * 32 * kNodeRowWords];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float* warp_tile = tiles + (threadIdx.x >> 5) * 32 * kNodeRowWords;
+    const float4* my_row = reinterpret_cast<const float4*>(warp_tile + lane * kNodeRowWords);
+    int deep[kSpillStack];
+    Stack st{smem + threadIdx.x, deep, 0, overflow};
+    RayRegs r;
+    int cur = 0, fetched = -1;  // fetched: the node whose copy is in (or on its way to) this lane's row
+    size_t my = 0;
+    bool active = false;
+    unsigned long long res_next = 0, res_end = 0;
+    bool exhausted = false;
+    for (;;) {
+        unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (idle == 0xFFFFFFFFu || (!exhausted && __popc(idle) >= kRefillIdle)) {
+            while (idle != 0 && !exhausted) {
+                if (res_next >= res_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(counter, (unsigned long long)kRayChunk);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (base >= n) {
+                        exhausted = true;
+                        break;
+                    }
+                    res_next = base;
+                    res_end = base + kRayChunk < n ? base + kRayChunk : n;
+                }
+                const unsigned long long avail = res_end - res_next;
+                const unsigned want = __popc(idle);
+                const unsigned take = avail < want ? (unsigned)avail : want;
+                const unsigned rank = __popc(idle & lt_mask);
+                if (!active && rank < take) {
+                    my = (size_t)(res_next + rank);
+                    load_ray(rays, my, r);
+                    st.reset();
+                    cur = 0;
+                    fetched = -1;
+                    if (tree.node_count != 0 && !r.nan)
+                        active = true;
+                    else
+                        store_result<ANY>(r, my, hits, occluded);
+                }
+                res_next += take;
+                idle = __ballot_sync(0xFFFFFFFFu, !active);
+            }
+            if (idle == 0xFFFFFFFFu) break;
+        }
+        // rows that do not hold the node their lane is about to visit (fresh rays): fetch now
+        const int want = (active && fetched != cur) ? cur : -1;
+        if (__any_sync(0xFFFFFFFFu, want >= 0)) coop_fetch(tree.nodes, want, warp_tile, lane);
+        cp_async_wait_all();
+        __syncwarp();
+        MNode nd;
+        if (active) {
+            nd.mnx = my_row[0]; nd.mxx = my_row[1]; nd.mny = my_row[2]; nd.mxy = my_row[3];
+            nd.mnz = my_row[4]; nd.mxz = my_row[5];
+            nd.ch = as_int4(my_row[6]);
+            nd.cn = as_int4(my_row[7]);
+        }
+        __syncwarp();  // every lane has its node in registers: the tile may be overwritten
+        int next = -1;
+        uint32_t leaves = 0;
+        int4 ch = make_int4(-1, -1, -1, -1), cn = ch;
+        if (active) {
+            next = mbvh_visit_push(nd, r, st, leaves);
+            ch = nd.ch;
+            cn = nd.cn;
+        }
+        fetched = (active && next >= 0) ? next : -1;
+        coop_fetch(tree.nodes, fetched, warp_tile, lane);  // in flight while the triangles below are tested
+        if (active) {
+            const bool done = mbvh_visit_leaves<ANY>(ch, cn, leaves, tree, r);
+            if (done || next < 0) {
+                store_result<ANY>(r, my, hits, occluded);
+                active = false;
+            } else {
+                cur = next;
+            }
+        }
+    }
+    cp_async_wait_all();
 }
 
 template <int TREE, bool ANY>
@@ -620,8 +777,17 @@ static unsigned persistent_grid(K kernel) {
 template <int TREE, bool ANY>
 static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
                                    uint8_t* d_occluded, unsigned long long* d_counter, uint32_t* d_overflow,
-                                   bool persistent, cudaStream_t stream) {
+                                   int mode, cudaStream_t stream) {
     const size_t blocks_needed = ceil_div(n, kBlock);
+    const bool persistent = mode != kTraceStatic;
+    if (TREE == RT_TREE_MBVH && mode == kTraceCoop) {
+        static const unsigned machine = persistent_grid(trace_mbvh_coop_kernel<ANY>);
+        const unsigned grid = (unsigned)(blocks_needed < machine ? blocks_needed : machine);
+        cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+        trace_mbvh_coop_kernel<ANY><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow);
+        return cudaGetLastError();
+    }
     if (persistent) {
         static const unsigned machine = persistent_grid(trace_single_persistent_kernel<TREE, ANY>);
         const unsigned grid = (unsigned)(blocks_needed < machine ? blocks_needed : machine);
@@ -638,13 +804,13 @@ static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, 
 
 cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any, const RTRay* d_rays, size_t n,
                                 RTHit* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
-                                uint32_t* d_overflow, bool persistent, cudaStream_t stream) {
+                                uint32_t* d_overflow, int mode, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     if (tree_kind == RT_TREE_MBVH)
-        return any ? launch_single_t<RT_TREE_MBVH, true>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, persistent, stream)
-                   : launch_single_t<RT_TREE_MBVH, false>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, persistent, stream);
-    return any ? launch_single_t<RT_TREE_BVH, true>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, persistent, stream)
-               : launch_single_t<RT_TREE_BVH, false>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, persistent, stream);
+        return any ? launch_single_t<RT_TREE_MBVH, true>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, mode, stream)
+                   : launch_single_t<RT_TREE_MBVH, false>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, mode, stream);
+    return any ? launch_single_t<RT_TREE_BVH, true>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, mode, stream)
+               : launch_single_t<RT_TREE_BVH, false>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, mode, stream);
 }
 
 cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,

@@ -4,11 +4,16 @@
 
 namespace rtb {
 
+// Kernel variants of the single-ray path (RTBVH_TRACE_MODE = static | persistent | coop):
+enum TraceMode {
+    kTraceStatic = 0,      // one thread per ray, no refill (A/B only)
+    kTracePersistent = 1,  // persistent warps + ray refill, every lane fetches its own node
+    kTraceCoop = 2,        // same + lane-cooperative node fetch through shared memory (Mbvh; Bvh falls back to 1)
+};
 // d_counter: one 64-bit work counter owned by this launch (zeroed on `stream` by the launcher).
-// persistent = false selects the static one-thread-per-ray kernel (A/B runs).
 cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any, const RTRay* d_rays, size_t n,
                                 RTHit* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
-                                uint32_t* d_overflow, bool persistent, cudaStream_t stream);
+                                uint32_t* d_overflow, int mode, cudaStream_t stream);
 cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,
                                  size_t n_packets, float t_min, RTHitPacket4* d_hits, uint8_t* d_occluded,
                                  uint32_t* d_overflow, cudaStream_t stream);
