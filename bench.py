@@ -119,9 +119,17 @@ def oracle_tree(tris):
     return O, bvh, m, build_s
 
 
+def host_threads():
+    """All host cores this process may use (torchrun sets OMP_NUM_THREADS=1, which must not shrink the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample_rate(O, m, tris, rays, target_s=12.0):
     """Times the oracle on a bounded sample; returns (Mrays/s, n_sample, counters per ray)."""
-    threads = O.num_threads()
+    threads = host_threads()
     probe = rays[: min(len(rays), 200_000)]
     _, ms, _ = O.trace(m, tris, probe, threads=threads)
     rate = len(probe) / max(ms, 1e-3) * 1e3
@@ -140,7 +148,7 @@ def run_reference(args):
     O, bvh, m, build_s = oracle_tree(tris)
     cam = W.soup_camera(WIDTH, HEIGHT)
     rows = 250  # each step: a bounded sample of the frame (250 rows x 1000 px = 250 k rays)
-    threads = O.num_threads()
+    threads = host_threads()
 
     def step(k):
         rays = W.camera_rays(cam, y0=(k * rows) % HEIGHT, y1=(k * rows) % HEIGHT + rows, jitter_seed=W.SEED_SOUP,
@@ -181,6 +189,10 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if api.device_count() == 0:
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -330,9 +342,13 @@ def run_gpu(args):
                     "d2h_bytes_per_step": rays_per_step * 8, "steps": e2e_steps, "host_equals_resident": same},
             "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     scene.free()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
