@@ -53,6 +53,7 @@ constexpr int kBinWords = 7;         // min xyz, max xyz (ordered keys), count
 constexpr int kTaskBinWords = 3 * kBins * kBinWords;  // 336 words = 1344 B per active node
 constexpr float kPad = 0.0001f;
 constexpr int kRadius = 14;          // locb.rs:27
+constexpr uint32_t kSmall = 32;      // subtrees with <= kSmall primitives are finished by one warp (sah_small_kernel)
 
 // ---- order-preserving float <-> uint keys (so min/max can be integer atomics) --------------------
 __host__ __device__ inline uint32_t fkey(float f) {
@@ -343,7 +344,7 @@ __device__ __forceinline__ Box warp_union(Box b) {
 __global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__ tasks, uint32_t A,
                                                         const uint32_t* __restrict__ bins, const float4* __restrict__ nodes,
                                                         uint32_t max_leaf, uint32_t depth, Decision* __restrict__ dec,
-                                                        uint32_t* __restrict__ split_flag, uint32_t* __restrict__ ntask) {
+                                                        uint4* __restrict__ counts) {
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= A) return;
@@ -460,13 +461,22 @@ __global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__
             d.rmx[k] = rb.mx[k];
         }
         dec[t] = d;
-        split_flag[t] = d.split;
-        uint32_t nt = 0;
-        if (do_split) {  // children that are leaves on entry (n <= 1 or depth cap) never become tasks
+        // children: leaf on entry (n <= 1 or depth cap) / small subtree (one warp finishes it) / next-level task
+        uint4 c = make_uint4(d.split, 0u, 0u, 0u);
+        if (do_split) {
             const bool cap = depth + 1 >= (uint32_t)kMaxDepth;
-            nt = ((nleft > 1 && !cap) ? 1u : 0u) + (((n - nleft) > 1 && !cap) ? 1u : 0u);
+            const uint32_t nc[2] = {nleft, n - nleft};
+            for (int k = 0; k < 2; k++) {
+                if (nc[k] <= 1 || cap) continue;
+                if (nc[k] <= kSmall) {
+                    c.z += 1u;
+                    c.w += 2u * nc[k] - 2u;  // node slots reserved for the subtree below this child
+                } else {
+                    c.y += 1u;
+                }
+            }
         }
-        ntask[t] = nt;
+        counts[t] = c;
     }
 }
 
@@ -482,10 +492,16 @@ __global__ void root_leaf_kernel(float4* nodes, uint32_t n) {
     make_leaf(nodes, 0, b, 0, n);
 }
 
-// Allocate the child pairs (level order), write inner nodes / leaves, emit next-level tasks.
+struct SmallTask {
+    uint32_t node, begin, end, depth, node_base;
+};
+
+// Allocate the child pairs (level order), write inner nodes / leaves, emit next-level tasks and small subtrees.
+// rank[t] = exclusive scan of counts: x pairs, y next-level tasks, z small subtrees, w node slots of small subtrees.
 __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A, const Decision* __restrict__ dec,
-                                const uint32_t* __restrict__ pair_rank, const uint32_t* __restrict__ task_rank,
-                                uint32_t node_base, uint32_t depth, float4* nodes, Task* __restrict__ next_tasks,
+                                const uint4* __restrict__ rank, uint32_t node_base, uint32_t small_base,
+                                uint32_t small_node_base, uint32_t depth, float4* nodes, Task* __restrict__ next_tasks,
+                                SmallTask* __restrict__ small_tasks,
                                 int32_t* __restrict__ child_task /* 2 per task: next-level task index or -1 */) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= A) return;
@@ -499,39 +515,251 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A, cons
         child_task[2 * t + 1] = -1;
         return;
     }
-    const uint32_t left = node_base + 2u * pair_rank[t];
+    const uint4 r = rank[t];
+    const uint32_t left = node_base + 2u * r.x;
     store_node(nodes, task.node, nb, -1, (int)left);
     const bool cap = depth + 1 >= (uint32_t)kMaxDepth;
-    uint32_t next = task_rank[t];
+    uint32_t next = r.y, small = small_base + r.z, small_nodes = small_node_base + r.w;
     const uint32_t mid = task.begin + d.nleft;
-    Box lb{{d.lmn[0], d.lmn[1], d.lmn[2]}, {d.lmx[0], d.lmx[1], d.lmx[2]}};
-    Box rb{{d.rmn[0], d.rmn[1], d.rmn[2]}, {d.rmx[0], d.rmx[1], d.rmx[2]}};
-    // left child
-    if (d.nleft > 1 && !cap) {
-        store_node(nodes, left, lb, 0, 0);
-        next_tasks[next] = Task{left, task.begin, mid};
-        child_task[2 * t] = (int32_t)next++;
-    } else {  // leaf on entry: pad (run) + pad (make_leaf), binned_sah.rs:133-143
-        box_pad(lb, kPad);
-        make_leaf(nodes, left, lb, task.begin, d.nleft);
-        child_task[2 * t] = -1;
-    }
-    if ((n - d.nleft) > 1 && !cap) {
-        store_node(nodes, left + 1, rb, 0, 0);
-        next_tasks[next] = Task{left + 1, mid, task.end};
-        child_task[2 * t + 1] = (int32_t)next;
-    } else {
-        box_pad(rb, kPad);
-        make_leaf(nodes, left + 1, rb, mid, n - d.nleft);
-        child_task[2 * t + 1] = -1;
+    Box cb[2] = {Box{{d.lmn[0], d.lmn[1], d.lmn[2]}, {d.lmx[0], d.lmx[1], d.lmx[2]}},
+                 Box{{d.rmn[0], d.rmn[1], d.rmn[2]}, {d.rmx[0], d.rmx[1], d.rmx[2]}}};
+    const uint32_t cbeg[2] = {task.begin, mid}, cend[2] = {mid, task.end};
+    for (int k = 0; k < 2; k++) {
+        const uint32_t nc = cend[k] - cbeg[k];
+        child_task[2 * t + k] = -1;
+        if (nc <= 1 || cap) {  // leaf on entry: pad (run) + pad (make_leaf), binned_sah.rs:133-143
+            box_pad(cb[k], kPad);
+            make_leaf(nodes, left + k, cb[k], cbeg[k], nc);
+        } else if (nc <= kSmall) {
+            store_node(nodes, left + k, cb[k], 0, 0);
+            small_tasks[small] = SmallTask{left + k, cbeg[k], cend[k], depth + 1, small_nodes};
+            small++;
+            small_nodes += 2u * nc - 2u;
+        } else {
+            store_node(nodes, left + k, cb[k], 0, 0);
+            next_tasks[next] = Task{left + k, cbeg[k], cend[k]};
+            child_task[2 * t + k] = (int32_t)next++;
+        }
     }
 }
 
-// {pairs, next task count} of the level = last exclusive rank + last value
-__global__ void sah_totals_kernel(const uint32_t* pair_rank, const uint32_t* splitf, const uint32_t* task_rank,
-                                  const uint32_t* ntask, uint32_t A, uint32_t* out) {
-    out[0] = pair_rank[A - 1] + splitf[A - 1];
-    out[1] = task_rank[A - 1] + ntask[A - 1];
+// totals of the level = last exclusive rank + last value
+__global__ void sah_totals_kernel(const uint4* rank, const uint4* counts, uint32_t A, uint4* out) {
+    const uint4 r = rank[A - 1], c = counts[A - 1];
+    *out = make_uint4(r.x + c.x, r.y + c.y, r.z + c.z, r.w + c.w);
+}
+
+// ---- small subtrees: one warp runs BinnedSahBuildTask::run for every node below a <= 32-primitive task -----
+// Same decisions as the level kernels, computed without bins in memory: for split position s on an axis the
+// left box / count is the union / number of the primitives whose bin is < s — identical to the prefix of the
+// reference's bins because min/max/count do not depend on the order of accumulation.
+struct SmallEntry {
+    uint32_t node, b, e, depth;
+    Box box;
+};
+constexpr int kSmallWarps = 4;
+__global__ void __launch_bounds__(kSmallWarps * 32) sah_small_kernel(const SmallTask* __restrict__ tasks, uint32_t S,
+                                                                      uint32_t* __restrict__ idx, const float4* __restrict__ bb,
+                                                                      const float* __restrict__ cen, uint32_t cstride,
+                                                                      float4* nodes, uint32_t max_leaf,
+                                                                      uint32_t* __restrict__ used_nodes) {
+    __shared__ Box s_box[kSmallWarps][32];
+    __shared__ float s_cen[kSmallWarps][32][3];
+    __shared__ uint32_t s_idx[kSmallWarps][32];
+    __shared__ uint32_t s_bin[kSmallWarps][32];  // 3 x 8-bit bin ids
+    __shared__ float s_cost[kSmallWarps][48];
+    __shared__ SmallEntry s_stack[kSmallWarps][34];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * kSmallWarps + w;
+    if (t >= S) return;
+    const SmallTask task = tasks[t];
+    const uint32_t n = task.end - task.begin;
+    if ((uint32_t)lane < n) {
+        const uint32_t p = idx[task.begin + lane];
+        s_idx[w][lane] = p;
+        s_box[w][lane] = load_box(bb, p);
+        for (int k = 0; k < 3; k++) s_cen[w][lane][k] = cen[(size_t)p * cstride + k];
+    }
+    int sp = 0;
+    if (lane == 0) s_stack[w][0] = SmallEntry{task.node, 0u, n, task.depth, load_box(nodes, task.node)};
+    sp = 1;
+    uint32_t next_free = task.node_base;
+    __syncwarp();
+    while (sp > 0) {
+        const SmallEntry e = s_stack[w][--sp];
+        __syncwarp();
+        const uint32_t nn = e.e - e.b;
+        Box nb = e.box;
+        box_pad(nb, kPad);  // entry pad (binned_sah.rs:133)
+        if (nn <= 1 || e.depth >= (uint32_t)kMaxDepth) {
+            if (lane == 0) make_leaf(nodes, e.node, nb, task.begin + e.b, nn);
+            continue;
+        }
+        float k3[3], off3[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            k3[k] = fmul(fdiv(1.0f, fsub(nb.mx[k], nb.mn[k])), (float)kBins);
+            off3[k] = fmul(-nb.mn[k], k3[k]);
+        }
+        const bool in = (uint32_t)lane >= e.b && (uint32_t)lane < e.e;
+        uint32_t mybins = 0;
+        if (in) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) mybins |= (uint32_t)bin_index(s_cen[w][lane][k], k3[k], off3[k]) << (8 * k);
+            s_bin[w][lane] = mybins;
+        }
+        __syncwarp();
+        // 45 candidates (3 axes x split positions 1..15): lane c and lane c + 32
+        for (int cid = lane; cid < 45; cid += 32) {
+            const int ax = cid / 15;
+            const uint32_t sidx = (uint32_t)(cid % 15) + 1u;
+            Box L = box_empty(), R = box_empty();
+            uint32_t cl = 0, cr = 0;
+            for (uint32_t j = e.b; j < e.e; j++) {
+                const uint32_t bj = (s_bin[w][j] >> (8 * ax)) & 0xFFu;
+                if (bj < sidx) {
+                    L = box_union(L, s_box[w][j]);
+                    cl++;
+                } else {
+                    R = box_union(R, s_box[w][j]);
+                    cr++;
+                }
+            }
+            s_cost[w][cid] = fadd(fmul(box_half_area(L), (float)cl), fmul(box_half_area(R), (float)cr));
+        }
+        __syncwarp();
+        // find_split per axis: first strict minimum below f32::MAX in order s = 1..15 (binned_sah.rs:95-111)
+        float bc = FLT_MAX;
+        uint32_t bcount = (uint32_t)kBins;
+        if (lane < 3) {
+            for (int i = 0; i < 15; i++) {
+                const float c = s_cost[w][lane * 15 + i];
+                if (c < bc) {
+                    bc = c;
+                    bcount = (uint32_t)i + 1u;
+                }
+            }
+        }
+        float best_cost[3];
+        uint32_t best_count[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            best_cost[k] = __shfl_sync(0xFFFFFFFFu, bc, k);
+            best_count[k] = __shfl_sync(0xFFFFFFFFu, bcount, k);
+        }
+        int best_axis = 0;
+        if (best_cost[0] > best_cost[1]) best_axis = 1;
+        if ((best_axis == 0 ? best_cost[0] : best_cost[1]) > best_cost[2]) best_axis = 2;
+        uint32_t split_index = best_axis == 0 ? best_count[0] : (best_axis == 1 ? best_count[1] : best_count[2]);
+        const float axis_cost = best_axis == 0 ? best_cost[0] : (best_axis == 1 ? best_cost[1] : best_cost[2]);
+        const float max_split_cost = fmul(box_half_area(nb), fsub((float)nn, 1.0f));
+        bool do_split = true;
+        if (split_index == (uint32_t)kBins || axis_cost >= max_split_cost) {
+            if (nn > max_leaf) {  // fallback (binned_sah.rs:189-205)
+                best_axis = box_longest_axis(nb);
+                // per-bin counts on that axis: lane b < 16 counts the primitives of bin b
+                uint32_t cnt = 0;
+                if (lane < kBins)
+                    for (uint32_t j = e.b; j < e.e; j++) cnt += (((s_bin[w][j] >> (8 * best_axis)) & 0xFFu) == (uint32_t)lane) ? 1u : 0u;
+                uint32_t cum = cnt;
+#pragma unroll
+                for (int o = 1; o < kBins; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, cum, o);
+                    if (lane >= o) cum += v;
+                }
+                const uint32_t need = (uint32_t)(((uint64_t)nn * 2ull) / 5ull + 1ull);
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, lane < kBins - 1 && cum >= need);
+                if (m) split_index = (uint32_t)__ffs(m);
+            } else {
+                do_split = false;
+            }
+        }
+        const uint32_t mybin = (mybins >> (8 * best_axis)) & 0xFFu;
+        const bool goes_left = in && mybin < split_index;
+        const uint32_t lmask = __ballot_sync(0xFFFFFFFFu, goes_left);
+        const uint32_t inmask = __ballot_sync(0xFFFFFFFFu, in);
+        const uint32_t nleft = (uint32_t)__popc(lmask);
+        if (nleft == 0 || nleft == nn) do_split = false;
+        if (!do_split) {
+            if (lane == 0) make_leaf(nodes, e.node, nb, task.begin + e.b, nn);
+            continue;
+        }
+        // child boxes; quirk Q3: the left box uses the SAH split count of the final axis
+        const uint32_t q3 = best_axis == 0 ? best_count[0] : (best_axis == 1 ? best_count[1] : best_count[2]);
+        const Box mine = in ? s_box[w][lane] : box_empty();
+        const Box lb = warp_union((in && mybin < q3) ? mine : box_empty());
+        const Box rb = warp_union((in && mybin >= split_index) ? mine : box_empty());
+        // stable partition of [b, e) inside the warp
+        const uint32_t lt = (1u << lane) - 1u;
+        uint32_t dest = (uint32_t)lane;
+        if (in) dest = goes_left ? e.b + (uint32_t)__popc(lmask & lt) : e.b + nleft + (uint32_t)__popc((inmask & ~lmask) & lt);
+        const Box mybox = mine;
+        const uint32_t myidx = in ? s_idx[w][lane] : 0u;
+        float myc[3] = {0.f, 0.f, 0.f};
+        if (in)
+            for (int k = 0; k < 3; k++) myc[k] = s_cen[w][lane][k];
+        __syncwarp();
+        if (in) {
+            s_box[w][dest] = mybox;
+            s_idx[w][dest] = myidx;
+            for (int k = 0; k < 3; k++) s_cen[w][dest][k] = myc[k];
+        }
+        const uint32_t left = next_free;
+        next_free += 2;
+        if (lane == 0) {
+            store_node(nodes, e.node, nb, -1, (int)left);
+            s_stack[w][sp] = SmallEntry{left + 1, e.b + nleft, e.e, e.depth + 1, rb};
+            s_stack[w][sp + 1] = SmallEntry{left, e.b, e.b + nleft, e.depth + 1, lb};
+        }
+        sp += 2;
+        __syncwarp();
+    }
+    if ((uint32_t)lane < n) idx[task.begin + lane] = s_idx[w][lane];
+    if (lane == 0) used_nodes[t] = next_free - task.node_base;
+}
+
+// ---- compaction of the node array when small subtrees used fewer slots than reserved ---------------
+// waste_prefix[t] = exclusive scan of (reserved - used) over the small tasks (ordered by node_base).
+__device__ __forceinline__ uint32_t small_remap(uint32_t node, uint32_t level_nodes, const SmallTask* __restrict__ tasks,
+                                                const uint32_t* __restrict__ waste_prefix, uint32_t S) {
+    if (node < level_nodes) return node;
+    uint32_t lo = 0, hi = S;  // last task with node_base <= node
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tasks[mid].node_base <= node) lo = mid; else hi = mid;
+    }
+    return node - waste_prefix[lo];
+}
+__global__ void small_rebase_kernel(SmallTask* tasks, uint32_t S, uint32_t level_nodes) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < S) tasks[t].node_base += level_nodes;
+}
+__global__ void small_waste_kernel(const SmallTask* __restrict__ tasks, const uint32_t* __restrict__ used, uint32_t S,
+                                   uint32_t* __restrict__ waste) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S) return;
+    waste[t] = 2u * (tasks[t].end - tasks[t].begin) - 2u - used[t];
+}
+__global__ void compact_nodes_kernel(const float4* __restrict__ in, float4* __restrict__ out, uint32_t level_nodes,
+                                     const SmallTask* __restrict__ tasks, const uint32_t* __restrict__ used,
+                                     const uint32_t* __restrict__ waste_prefix, uint32_t S, uint32_t total_slots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_slots) return;
+    uint32_t dst = i;
+    if (i >= level_nodes) {
+        uint32_t lo = 0, hi = S;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (tasks[mid].node_base <= i) lo = mid; else hi = mid;
+        }
+        if (i - tasks[lo].node_base >= used[lo]) return;  // reserved but unused slot
+        dst = i - waste_prefix[lo];
+    }
+    float4 a = in[(size_t)i * 2], b = in[(size_t)i * 2 + 1];
+    const int count = __float_as_int(a.w), left = __float_as_int(b.w);
+    if (count < 0 && left >= 0) b.w = __int_as_float((int)small_remap((uint32_t)left, level_nodes, tasks, waste_prefix, S));
+    out[(size_t)dst * 2] = a;
+    out[(size_t)dst * 2 + 1] = b;
 }
 
 // partition predicate (binned_sah.rs:213-219) for every index position
@@ -886,13 +1114,20 @@ struct DeviceBvh {
     uint32_t node_count = 0, index_count = 0;
 };
 
+struct Uint4Add {
+    __host__ __device__ uint4 operator()(const uint4& a, const uint4& b) const {
+        return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+};
+
 static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen, uint32_t cstride, uint32_t n,
                                           uint32_t max_leaf, DeviceBvh* out) {
     const uint32_t max_nodes = 2 * n - 1;
-    RTB_CUDA(out->nodes.alloc((size_t)max_nodes * 32));
-    float4* nodes = out->nodes.as<float4>();
-    DevBuf idxA, idxB, ptA, ptB, tasksA, tasksB, aux, dec, bins, flag, rank, splitf, ntask, pair_rank, task_rank, child_task,
-        world, temp, totals;
+    DevBuf nodesA;
+    RTB_CUDA(nodesA.alloc((size_t)max_nodes * 32));
+    float4* nodes = nodesA.as<float4>();
+    DevBuf idxA, idxB, ptA, ptB, tasksA, tasksB, aux, dec, bins, flag, rank, counts, ranks4, child_task, world, temp, totals,
+        small_tasks, used, waste, waste_prefix;
     RTB_CUDA(idxA.alloc((size_t)n * 4));
     RTB_CUDA(idxB.alloc((size_t)n * 4));
     RTB_CUDA(ptA.alloc((size_t)n * 4));
@@ -901,6 +1136,9 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
     RTB_CUDA(rank.alloc((size_t)n * 4));
     RTB_CUDA(world.alloc(6 * 4));
     RTB_CUDA(totals.alloc(16));
+    // every small subtree holds >= 2 primitives, so there are at most n / 2 of them
+    const uint32_t small_cap = n / 2 + 1;
+    RTB_CUDA(small_tasks.alloc((size_t)small_cap * sizeof(SmallTask)));
     // root = union_of_list(aabbs) (binned_sah.rs:361)
     world_init_kernel<<<1, 32>>>(world.as<uint32_t>());
     world_reduce_kernel<<<std::min(blocks(n, 256), 148u * 8u), 256>>>(d_bb, n, world.as<uint32_t>());
@@ -916,26 +1154,26 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         // tasksA holds the current level and must survive growth
         DevBuf grown;
         if ((e = grown.alloc(cap * sizeof(Task))) != cudaSuccess) return e;
-        if (tasksA.p && A) cudaMemcpy(grown.p, tasksA.p, (size_t)A * sizeof(Task), cudaMemcpyDeviceToDevice);
+        if (tasksA.p && A) cudaMemcpyAsync(grown.p, tasksA.p, (size_t)A * sizeof(Task), cudaMemcpyDeviceToDevice, 0);
         std::swap(grown.p, tasksA.p);
         std::swap(grown.bytes, tasksA.bytes);
         if ((e = tasksB.alloc(cap * 2 * sizeof(Task))) != cudaSuccess) return e;
         if ((e = aux.alloc(cap * sizeof(TaskAux))) != cudaSuccess) return e;
         if ((e = dec.alloc(cap * sizeof(Decision))) != cudaSuccess) return e;
         if ((e = bins.alloc(cap * kTaskBinWords * 4)) != cudaSuccess) return e;
-        if ((e = splitf.alloc(cap * 4)) != cudaSuccess) return e;
-        if ((e = ntask.alloc(cap * 4)) != cudaSuccess) return e;
-        if ((e = pair_rank.alloc(cap * 4)) != cudaSuccess) return e;
-        if ((e = task_rank.alloc(cap * 4)) != cudaSuccess) return e;
+        if ((e = counts.alloc(cap * sizeof(uint4))) != cudaSuccess) return e;
+        if ((e = ranks4.alloc(cap * sizeof(uint4))) != cudaSuccess) return e;
         if ((e = child_task.alloc(cap * 8)) != cudaSuccess) return e;
         task_cap = cap;
         return cudaSuccess;
     };
-    // CUB temp storage: sized for the largest scan we run (n elements by key)
+    // CUB temp storage: sized for the largest scans we run
     size_t temp_bytes = 0, tb = 0;
     cub::DeviceScan::ExclusiveSumByKey(nullptr, tb, ptA.as<int32_t>(), flag.as<uint32_t>(), rank.as<uint32_t>(), (int)n);
     temp_bytes = tb;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.as<uint32_t>(), rank.as<uint32_t>(), (int)n);
+    cub::DeviceScan::ExclusiveScan(nullptr, tb, (uint4*)nullptr, (uint4*)nullptr, Uint4Add(), make_uint4(0, 0, 0, 0), (int)(n / 2 + 1));
+    temp_bytes = std::max(temp_bytes, tb);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)small_cap);
     temp_bytes = std::max(temp_bytes, tb);
     RTB_CUDA(temp.alloc(temp_bytes));
 
@@ -946,13 +1184,16 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         RTB_CUDA(ensure_tasks(1024));
         const Task root{0, 0, n};
         RTB_CUDA(cudaMemcpy(tasksA.p, &root, sizeof(Task), cudaMemcpyHostToDevice));
-        RTB_CUDA(cudaMemset(ptA.p, 0, (size_t)n * 4));  // every position belongs to task 0
+        RTB_CUDA(cudaMemsetAsync(ptA.p, 0, (size_t)n * 4, 0));  // every position belongs to task 0
         A = 1;
     }
     uint32_t* idx_cur = idxA.as<uint32_t>();
     uint32_t* idx_nxt = idxB.as<uint32_t>();
     int32_t* pt_cur = ptA.as<int32_t>();
     int32_t* pt_nxt = ptB.as<int32_t>();
+    uint32_t S = 0, small_slots = 0;  // small subtrees collected so far and the node slots reserved for them
+    // Node slots of small subtrees are numbered after all level nodes; until the level loop ends the final
+    // number of level nodes is unknown, so small node_base values are stored relative and rebased below.
     for (uint32_t depth = 0; A > 0; depth++) {
         RTB_CUDA(ensure_tasks(A));
         Task* t_cur = tasksA.as<Task>();
@@ -963,24 +1204,22 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         sah_bin_kernel<<<blocks(n, kBinBlock), kBinBlock>>>(idx_cur, pt_cur, n, aux.as<TaskAux>(), d_bb, d_cen, cstride,
                                                            bins.as<uint32_t>());
         sah_split_kernel<<<blocks((size_t)A * 32, 128), 128>>>(t_cur, A, bins.as<uint32_t>(), nodes, max_leaf, depth,
-                                                               dec.as<Decision>(), splitf.as<uint32_t>(), ntask.as<uint32_t>());
+                                                               dec.as<Decision>(), counts.as<uint4>());
         size_t tbytes = temp.bytes;
-        RTB_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tbytes, splitf.as<uint32_t>(), pair_rank.as<uint32_t>(), (int)A));
-        tbytes = temp.bytes;
-        RTB_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tbytes, ntask.as<uint32_t>(), task_rank.as<uint32_t>(), (int)A));
+        RTB_CUDA(cub::DeviceScan::ExclusiveScan(temp.p, tbytes, counts.as<uint4>(), ranks4.as<uint4>(), Uint4Add(),
+                                                make_uint4(0, 0, 0, 0), (int)A));
         // one small D2H per level: the host needs the next level's task count to size its launches
-        sah_totals_kernel<<<1, 1>>>(pair_rank.as<uint32_t>(), splitf.as<uint32_t>(), task_rank.as<uint32_t>(),
-                                    ntask.as<uint32_t>(), A, totals.as<uint32_t>());
-        uint32_t h[2];
-        RTB_CUDA(cudaMemcpy(h, totals.p, 8, cudaMemcpyDeviceToHost));
-        const uint32_t pairs = h[0], next_A = h[1];
+        sah_totals_kernel<<<1, 1>>>(ranks4.as<uint4>(), counts.as<uint4>(), A, totals.as<uint4>());
+        uint32_t h[4];
+        RTB_CUDA(cudaMemcpy(h, totals.p, 16, cudaMemcpyDeviceToHost));
+        const uint32_t pairs = h[0], next_A = h[1], new_small = h[2], new_slots = h[3];
         if ((size_t)next_A * 2 * sizeof(Task) > tasksB.bytes) {
             RTB_CUDA(tasksB.alloc((size_t)next_A * 2 * sizeof(Task)));
             t_nxt = tasksB.as<Task>();
         }
-        sah_emit_kernel<<<blocks(A, 128), 128>>>(t_cur, A, dec.as<Decision>(), pair_rank.as<uint32_t>(),
-                                                 task_rank.as<uint32_t>(), node_count, depth, nodes, t_nxt,
-                                                 child_task.as<int32_t>());
+        if (S + new_small > small_cap) return fail("binned SAH: small-subtree list overflow");
+        sah_emit_kernel<<<blocks(A, 128), 128>>>(t_cur, A, dec.as<Decision>(), ranks4.as<uint4>(), node_count, S, small_slots,
+                                                 depth, nodes, t_nxt, small_tasks.as<SmallTask>(), child_task.as<int32_t>());
         if (pairs > 0) {
             sah_flag_kernel<<<blocks(n, 256), 256>>>(idx_cur, pt_cur, n, aux.as<TaskAux>(), dec.as<Decision>(), d_cen, cstride,
                                                      flag.as<uint32_t>());
@@ -992,15 +1231,48 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
             std::swap(pt_cur, pt_nxt);
         }
         node_count += 2 * pairs;
+        S += new_small;
+        small_slots += new_slots;
         // next level's tasks become current
         std::swap(tasksA.p, tasksB.p);
         std::swap(tasksA.bytes, tasksB.bytes);
         A = next_A;
         RTB_CUDA(cudaGetLastError());
     }
+    const uint32_t level_nodes = node_count;
+    uint32_t total_nodes = level_nodes;
+    if (S > 0) {
+        // rebase the reserved ranges behind the level nodes, then let one warp finish each subtree
+        RTB_CUDA(used.alloc((size_t)S * 4));
+        small_rebase_kernel<<<blocks(S, 256), 256>>>(small_tasks.as<SmallTask>(), S, level_nodes);
+        sah_small_kernel<<<blocks(S, kSmallWarps), kSmallWarps * 32>>>(small_tasks.as<SmallTask>(), S, idx_cur, d_bb, d_cen, cstride,
+                                                                       nodes, max_leaf, used.as<uint32_t>());
+        // compaction only if some subtree ended early (leaves with several primitives)
+        RTB_CUDA(waste.alloc((size_t)S * 4));
+        RTB_CUDA(waste_prefix.alloc((size_t)(S + 1) * 4));
+        small_waste_kernel<<<blocks(S, 256), 256>>>(small_tasks.as<SmallTask>(), used.as<uint32_t>(), S, waste.as<uint32_t>());
+        size_t tbytes = temp.bytes;
+        RTB_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tbytes, waste.as<uint32_t>(), waste_prefix.as<uint32_t>(), (int)S));
+        uint32_t hw[2];
+        RTB_CUDA(cudaMemcpy(&hw[0], waste_prefix.as<uint32_t>() + (S - 1), 4, cudaMemcpyDeviceToHost));
+        RTB_CUDA(cudaMemcpy(&hw[1], waste.as<uint32_t>() + (S - 1), 4, cudaMemcpyDeviceToHost));
+        const uint32_t wasted = hw[0] + hw[1];
+        const uint32_t slots = level_nodes + small_slots;
+        total_nodes = slots - wasted;
+        if (wasted > 0) {
+            RTB_CUDA(out->nodes.alloc((size_t)total_nodes * 32));
+            compact_nodes_kernel<<<blocks(slots, 256), 256>>>(nodes, out->nodes.as<float4>(), level_nodes,
+                                                             small_tasks.as<SmallTask>(), used.as<uint32_t>(),
+                                                             waste_prefix.as<uint32_t>(), S, slots);
+        }
+    }
+    if (!out->nodes.p) {  // no compaction: hand the build buffer over
+        std::swap(out->nodes.p, nodesA.p);
+        std::swap(out->nodes.bytes, nodesA.bytes);
+    }
     RTB_CUDA(out->indices.alloc((size_t)n * 4));
-    RTB_CUDA(cudaMemcpy(out->indices.p, idx_cur, (size_t)n * 4, cudaMemcpyDeviceToDevice));
-    out->node_count = node_count;
+    RTB_CUDA(cudaMemcpyAsync(out->indices.p, idx_cur, (size_t)n * 4, cudaMemcpyDeviceToDevice, 0));
+    out->node_count = total_nodes;
     out->index_count = n;
     RTB_CUDA(cudaDeviceSynchronize());
     return Ok;

@@ -218,6 +218,21 @@ def test_five_triangle_case(A, O):
         assert m.nodes.tobytes() == O.Bvh(g.nodes.copy(), g.indices.copy()).collapse().nodes.tobytes()
 
 
+def test_duplicate_primitives_force_multi_prim_leaves(A, O, W):
+    # identical centroids cannot be separated: leaves keep several primitives although primitives_per_leaf = 1, the
+    # small-subtree path reserves more node slots than it uses and the node array must be compacted
+    base = W.soup(3000, seed=11)
+    tris = np.repeat(base, 3, axis=0)
+    aabbs, centers = O.prims_from_triangles(tris)
+    for leaf in (1, 2, 5):
+        g = A.Builder(aabbs, centers, leaf).construct_binned_sah()
+        rc, w = O.build(O.BINNED_SAH, aabbs, centers, leaf)
+        assert g.validate(len(tris))
+        assert_isomorphic(g.nodes, g.indices, w.nodes, w.indices)
+        m = A.Mbvh.construct(g)
+        assert m.nodes.tobytes() == O.Bvh(g.nodes.copy(), g.indices.copy()).collapse().nodes.tobytes()
+
+
 def test_point_primitives_without_aabbs(A, O):
     # create_bvh with aabbs == null: centers act as point primitives (rtbvh_ffi/src/lib.rs:396-422)
     pts = np.random.default_rng(5).random((5000, 3)).astype(np.float32)
