@@ -267,10 +267,24 @@ __device__ __forceinline__ int mbvh_visit_push(const MNode& nd, const RayRegs& r
             pay[2] = pay[3];
             pay[3] = tp;
         }
-        if (pay[3] >= 0) st.push(pay[3]);
-        if (pay[2] >= 0) st.push(pay[2]);
-        if (pay[1] >= 0) st.push(pay[1]);
-        if (pay[0] >= 0) st.push(pay[0]);
+        // Push order is pay[3], pay[2], pay[1], pay[0]; the entry pushed last is popped right away, so it is
+        // handed over in a register (no shared-memory round trip on the critical path) and only the others
+        // are stored.  `next` = first valid of pay[0], pay[1], pay[2], pay[3].
+        const int next = pay[0] >= 0 ? pay[0] : (pay[1] >= 0 ? pay[1] : (pay[2] >= 0 ? pay[2] : pay[3]));
+        const int skip = pay[0] >= 0 ? 0 : (pay[1] >= 0 ? 1 : (pay[2] >= 0 ? 2 : 3));
+        if (st.sp + 3 <= kSmemStack) {  // fast path: compact predicated stores
+            int* b = st.base + st.sp * kBlock;
+            int c = 0;
+            if (skip < 3 && pay[3] >= 0) { b[c * kBlock] = pay[3]; c++; }
+            if (skip < 2 && pay[2] >= 0) { b[c * kBlock] = pay[2]; c++; }
+            if (skip < 1 && pay[1] >= 0) { b[c * kBlock] = pay[1]; c++; }
+            st.sp += c;
+        } else {
+            if (skip < 3 && pay[3] >= 0) st.push(pay[3]);
+            if (skip < 2 && pay[2] >= 0) st.push(pay[2]);
+            if (skip < 1 && pay[1] >= 0) st.push(pay[1]);
+        }
+        return next;
     }
     return st.sp > 0 ? st.pop() : -1;
 }
@@ -311,6 +325,7 @@ __device__ __forceinline__ bool bvh_single_step(const DeviceTree& tree, RayRegs&
     const float4* __restrict__ nodes = tree.nodes;
     const F8 nd = ld256(nodes + (size_t)cur * 2);
     const int count = __float_as_int(nd.lo.w), left_first = __float_as_int(nd.hi.w);
+    int next = -1;
     if (count > -1) {
         for (int i = 0; i < count; i++) {
             const bool hit = tri_candidate<false>(tree.tris, left_first + i, r);
@@ -323,22 +338,26 @@ __device__ __forceinline__ bool bvh_single_step(const DeviceTree& tree, RayRegs&
         float kl = 0.f, kr = 0.f;
         const bool hl = aabb_single(l0, l1, r, kl);
         const bool hr = aabb_single(r0, r1, r, kr);
-        if (hl && hr) {  // BvhNode::sort_nodes (bvh_node.rs:150-177)
+        // BvhNode::sort_nodes (bvh_node.rs:150-177); the entry it pushes last is popped next, so it stays in a register
+        if (hl && hr) {
             if (kl < kr) {
                 st.push(left_first);
-                st.push(left_first + 1);
+                next = left_first + 1;
             } else {
                 st.push(left_first + 1);
-                st.push(left_first);
+                next = left_first;
             }
         } else if (hl) {
-            st.push(left_first);
+            next = left_first;
         } else if (hr) {
-            st.push(left_first + 1);
+            next = left_first + 1;
         }
     }
-    if (st.sp == 0) return true;
-    cur = st.pop();
+    if (next < 0) {
+        if (st.sp == 0) return true;
+        next = st.pop();
+    }
+    cur = next;
     return false;
 }
 
