@@ -86,6 +86,53 @@ def heightfield(nx: int = 2237, ny: int = 2237, seed: int = SEED_MESH) -> np.nda
     return np.stack([t0, t1], axis=2).reshape(-1, 3, 3).astype(np.float32)
 
 
+def displaced_sphere(nu: int = 708, nv: int = 707, seed: int = SEED_SCENE) -> np.ndarray:
+    """A UV sphere of 2*nu*nv triangles (1 001 112 by default) with a smooth radial displacement."""
+    f = np.float32
+    u = (np.arange(nu + 1, dtype=f) / f(nu)) * f(2 * np.pi)
+    v = (np.arange(nv + 1, dtype=f) / f(nv)) * f(np.pi)
+    uu, vv = np.meshgrid(u, v, indexing="xy")
+    r = (f(1.0) + f(0.05) * np.sin(f(9) * uu) * np.sin(f(7) * vv) + f(0.02) * np.sin(f(31) * vv + f(3) * uu)).astype(f)
+    p = np.stack([r * np.sin(vv) * np.cos(uu), r * np.cos(vv), r * np.sin(vv) * np.sin(uu)], axis=-1).astype(f)
+    p00, p10, p01, p11 = p[:-1, :-1], p[:-1, 1:], p[1:, :-1], p[1:, 1:]
+    t0 = np.stack([p00, p10, p11], axis=2)
+    t1 = np.stack([p00, p11, p01], axis=2)
+    return np.stack([t0, t1], axis=2).reshape(-1, 3, 3).astype(f)
+
+
+def instanced_scene(instances: int = 30, nu: int = 708, nv: int = 707, seed: int = SEED_SCENE) -> np.ndarray:
+    """Config 4: `instances` baked copies (random rigid transforms + uniform scale) of a displaced sphere above a
+    2-triangle ground and 4 walls (8 triangles).  30 x 1 001 112 + 10 = 30 033 370 triangles by default."""
+    f = np.float32
+    base = displaced_sphere(nu, nv, seed)
+    out = np.empty((instances * len(base) + 10, 3, 3), dtype=f)
+    side = int(np.ceil(instances ** (1.0 / 3.0)))
+    for i in range(instances):
+        h = [float(hash_unit(seed, np.array([i], dtype=np.uint64), k)[0]) for k in range(8)]
+        # rotation from a random unit quaternion
+        q = np.array([h[0] - 0.5, h[1] - 0.5, h[2] - 0.5, h[3] - 0.5], dtype=np.float64)
+        q /= np.linalg.norm(q) + 1e-12
+        w, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], dtype=f)
+        cell = np.array([i % side, (i // side) % side, i // (side * side)], dtype=f)
+        t = (cell * f(2.6) + np.array([h[4], h[5], h[6]], dtype=f) * f(0.3) + f(1.3)).astype(f)
+        sc = f(0.8 + 0.4 * h[7])
+        out[i * len(base):(i + 1) * len(base)] = (base.reshape(-1, 3) @ R.T * sc + t).reshape(-1, 3, 3)
+    ext = f(side * 2.6 + 0.5)
+    lo, hi = f(-0.5), ext
+    c = [np.array(p, dtype=f) for p in ((lo, lo, lo), (hi, lo, lo), (hi, lo, hi), (lo, lo, hi), (lo, hi, lo), (hi, hi, lo),
+                                        (hi, hi, hi), (lo, hi, hi))]
+    quads = [(0, 1, 2, 3), (0, 4, 5, 1), (1, 5, 6, 2), (2, 6, 7, 3), (3, 7, 4, 0)]  # ground + 4 walls, open top
+    k = instances * len(base)
+    for a, b, cc, d in quads:
+        out[k] = np.stack([c[a], c[b], c[cc]])
+        out[k + 1] = np.stack([c[a], c[cc], c[d]])
+        k += 2
+    return out
+
+
 def bounds(verts: np.ndarray):
     v = verts.reshape(-1, 3)
     return v.min(axis=0), v.max(axis=0)
