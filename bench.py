@@ -55,6 +55,16 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the traversal kernel per launch, from the committed
+    `ncu --set full` capture of this same workload (profiles/ncu_traffic.json); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -323,7 +333,7 @@ def run_gpu(args):
             launch_ms = ms / args.steps
             achieved = bytes_per_ray * rays_per_step / (launch_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": info.get("ncu_dram_bytes_per_launch"), "peak_source": peak_src,
+                    "traffic": ncu_traffic(), "peak_source": peak_src,
                     "bytes_per_ray": bytes_per_ray, "node_visits_per_ray": nm, "tri_tests_per_ray": npr,
                     "kernel": "trace_single_kernel<MBVH, closest>", "launch_ms": launch_ms}
         out = {
