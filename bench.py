@@ -226,6 +226,9 @@ def run_gpu(args):
             mbvh = api.Mbvh.from_arrays(arrays["mnodes"], arrays["indices"])
         info["replication"] = "tree built on rank 0, broadcast over NCCL, one replica per GPU"
     scene = api.Scene(tris, bvh=None, mbvh=mbvh)
+    sort_rays = os.environ.get("RTBVH_BENCH_SORT", "0") == "1"  # experiment knob; primary rays are coherent already
+    scene.set_ray_sorting(sort_rays)
+    info["ray_sorting"] = sort_rays
 
     fps = args.frames_per_step
     rays_per_step = fps * WIDTH * HEIGHT

@@ -80,6 +80,10 @@ const char *rtbvh_gpu_last_error(void);           /* message of the last Error o
 ResultCode rtbvh_gpu_scene_create(const RTBvh *bvh, const RTMbvh *mbvh, const float *vertices, size_t vertex_stride,
                                   size_t triangle_count, RTGpuScene *scene);
 ResultCode rtbvh_gpu_scene_free(RTGpuScene scene);
+/* Incoherent batches (shadow / bounce rays): enable = 1 makes the single-ray calls trace every batch in Morton
+ * order of (origin, direction) and scatter the results back.  Results are unchanged, bit for bit; only the
+ * order in which the device works through the batch changes.  Default 0 (camera rays are coherent already). */
+ResultCode rtbvh_gpu_scene_set_ray_sorting(RTGpuScene scene, int enable);
 
 /* ---- closest hit / any hit, host buffers (H2D + kernels + D2H inside the call) ------------------ */
 ResultCode rtbvh_gpu_intersect(RTGpuScene scene, RTTreeKind tree, const RTRay *rays, size_t ray_count, RTHit *hits);

@@ -46,7 +46,7 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_occluded_packets", "rtbvh_gpu_intersect_device", "rtbvh_gpu_occluded_device",
                "rtbvh_gpu_intersect_packets_device", "rtbvh_gpu_occluded_packets_device",
                "rtbvh_gpu_scene_stack_overflowed", "rtbvh_gpu_generate_camera_rays_device",
-               "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats")
+               "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats", "rtbvh_gpu_scene_set_ray_sorting")
 
 
 class RTBvh(C.Structure):  # rtbvh_ffi/src/lib.rs:210-220
@@ -110,6 +110,8 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_last_error.restype = C.c_char_p
     L.rtbvh_gpu_scene_create.restype = rc
     L.rtbvh_gpu_scene_create.argtypes = [C.POINTER(RTBvh), C.POINTER(RTMbvh), vp, sz, sz, C.POINTER(u64)]
+    L.rtbvh_gpu_scene_set_ray_sorting.restype = rc
+    L.rtbvh_gpu_scene_set_ray_sorting.argtypes = [u64, C.c_int]
     L.rtbvh_gpu_scene_free.restype = rc
     L.rtbvh_gpu_scene_free.argtypes = [u64]
     L.rtbvh_gpu_intersect.restype = rc
@@ -316,6 +318,10 @@ class Scene:
         self.handle = C.c_uint64(0)
         _check(lib().rtbvh_gpu_scene_create(C.byref(bvh.rt) if bvh else None, C.byref(mbvh.rt) if mbvh else None,
                                             _p(v), stride, v.shape[0] // 3, C.byref(self.handle)))
+
+    def set_ray_sorting(self, enable: bool = True):
+        """Trace every single-ray batch in Morton order of (origin, direction); results are unchanged."""
+        _check(lib().rtbvh_gpu_scene_set_ray_sorting(self.handle, int(enable)))
 
     def free(self):
         if self.handle.value:

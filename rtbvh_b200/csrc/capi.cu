@@ -3,6 +3,7 @@
 //
 // Ownership model mirrors rtbvh_ffi's StructureManager (rtbvh_ffi/src/lib.rs:12-127): a process-global
 // table guarded by a reader/writer lock, ids never reused.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -67,6 +68,9 @@ struct Scene {
     TriRec* d_tris_bvh = nullptr;   // leaf order of the Bvh's indices
     TriRec* d_tris_mbvh = nullptr;  // leaf order of the Mbvh's indices (may alias d_tris_bvh)
     uint32_t* d_overflow = nullptr;
+    float bounds[6] = {0, 0, 0, 1, 1, 1};  // root box (keys of the optional ray sort)
+    std::atomic<int> sort_rays{0};
+    const float* sort_bounds() const { return sort_rays.load() ? bounds : nullptr; }
     // work counters of the persistent kernels: every launch takes the next slot and zeroes it on its
     // own stream, so launches on different streams never share a counter
     unsigned long long* d_counters = nullptr;
@@ -223,9 +227,31 @@ ResultCode rtbvh_gpu_scene_create(const RTBvh* bvh, const RTMbvh* mbvh, const fl
     }
     cudaFree(d_verts);
     if (rc != Ok) return rc;
+    if (bvh && bvh->node_count) {
+        const RTAabb& r = bvh->nodes[0].aabb;
+        for (int k = 0; k < 3; k++) {
+            s->bounds[k] = r.min[k];
+            s->bounds[3 + k] = r.max[k];
+        }
+    } else if (mbvh && mbvh->node_count) {
+        const RTMbvhNode& r = mbvh->nodes[0];
+        const float* mn[3] = {r.min_x, r.min_y, r.min_z};
+        const float* mx[3] = {r.max_x, r.max_y, r.max_z};
+        for (int k = 0; k < 3; k++) {
+            s->bounds[k] = std::min(std::min(mn[k][0], mn[k][1]), std::min(mn[k][2], mn[k][3]));
+            s->bounds[3 + k] = std::max(std::max(mx[k][0], mx[k][1]), std::max(mx[k][2], mx[k][3]));
+        }
+    }
     std::unique_lock<std::shared_mutex> lk(g_scenes.mu);
     g_scenes.scenes.push_back(s);
     *scene = (RTGpuScene)g_scenes.scenes.size();
+    return Ok;
+}
+
+ResultCode rtbvh_gpu_scene_set_ray_sorting(RTGpuScene h, int enable) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    s->sort_rays.store(enable ? 1 : 0);
     return Ok;
 }
 
@@ -244,7 +270,7 @@ ResultCode rtbvh_gpu_intersect_device(RTGpuScene h, RTTreeKind tree, const RTRay
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
     RTB_CUDA(launch_trace_single(*t, tree, false, d_rays, n, d_hits, nullptr, s->counter_slot(), s->d_overflow,
-                                 persistent_mode(), (cudaStream_t)stream));
+                                 persistent_mode(), s->sort_bounds(), (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_occluded_device(RTGpuScene h, RTTreeKind tree, const RTRay* d_rays, size_t n, uint8_t* d_occ,
@@ -254,7 +280,7 @@ ResultCode rtbvh_gpu_occluded_device(RTGpuScene h, RTTreeKind tree, const RTRay*
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
     RTB_CUDA(launch_trace_single(*t, tree, true, d_rays, n, nullptr, d_occ, s->counter_slot(), s->d_overflow,
-                                 persistent_mode(), (cudaStream_t)stream));
+                                 persistent_mode(), s->sort_bounds(), (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* d_packets, size_t n,
@@ -294,7 +320,7 @@ ResultCode rtbvh_gpu_intersect(RTGpuScene h, RTTreeKind tree, const RTRay* rays,
     return run_host_batch(*s, rays, n, sizeof(RTRay), sizeof(RTHit), 1, hits,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_single(*t, tree, false, (const RTRay*)din, m, (RTHit*)dout, nullptr,
-                                                         s->counter_slot(), s->d_overflow, persistent_mode(), st);
+                                                         s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), st);
                           });
 }
 ResultCode rtbvh_gpu_occluded(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, uint8_t* occluded) {
@@ -305,7 +331,7 @@ ResultCode rtbvh_gpu_occluded(RTGpuScene h, RTTreeKind tree, const RTRay* rays, 
     return run_host_batch(*s, rays, n, sizeof(RTRay), 1, 1, occluded,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_single(*t, tree, true, (const RTRay*)din, m, nullptr, (uint8_t*)dout,
-                                                         s->counter_slot(), s->d_overflow, persistent_mode(), st);
+                                                         s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), st);
                           });
 }
 ResultCode rtbvh_gpu_intersect_packets(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* packets, size_t n,

@@ -20,6 +20,8 @@
 // (Bvh), fetched with 256-bit loads (4 resp. 2 LDG.256 per visit: one L1 wavefront per instruction
 // and lane).  Triangles are 64-byte leaf-ordered records (LDG.256 + LDG.128, no index indirection).  The
 // traversal stack lives in shared memory, [entry][thread] so it is bank-conflict free.
+#include <cub/cub.cuh>
+
 #include "traverse.cuh"
 
 namespace rtb {
@@ -482,11 +484,13 @@ template <int TREE, bool ANY>
 __global__ void __launch_bounds__(kBlock) trace_single_kernel(const DeviceTree tree, const RTRay* __restrict__ rays,
                                                               size_t n, RTHit* __restrict__ hits,
                                                               uint8_t* __restrict__ occluded,
+                                                              const uint32_t* __restrict__ perm,
                                                               uint32_t* __restrict__ overflow) {
     __shared__ int smem[kSmemStack * kBlock];
     int deep[kSpillStack];
-    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
+    const size_t slot = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (slot >= n) return;
+    const size_t i = perm ? (size_t)perm[slot] : slot;  // sorted launch order -> original ray index
     RayRegs r;
     load_ray(rays, i, r);
     Stack st{smem + threadIdx.x, deep, 0, overflow};
@@ -509,6 +513,7 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                                                                          const RTRay* __restrict__ rays, size_t n,
                                                                          RTHit* __restrict__ hits,
                                                                          uint8_t* __restrict__ occluded,
+                                                                         const uint32_t* __restrict__ perm,
                                                                          unsigned long long* __restrict__ counter,
                                                                          uint32_t* __restrict__ overflow) {
     __shared__ int smem[kSmemStack * kBlock];
@@ -543,6 +548,7 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                 const unsigned rank = __popc(idle & lt_mask);
                 if (!active && rank < take) {
                     my = (size_t)(res_next + rank);
+                    if (perm) my = (size_t)perm[my];
                     load_ray(rays, my, r);
                     st.reset();
                     cur = 0;
@@ -596,6 +602,7 @@ __global__ void __launch_bounds__(kBlock, 6) trace_mbvh_coop_kernel(const Device
                                                                                 const RTRay* __restrict__ rays, size_t n,
                                                                                 RTHit* __restrict__ hits,
                                                                                 uint8_t* __restrict__ occluded,
+                                                                                const uint32_t* __restrict__ perm,
                                                                                 unsigned long long* __restrict__ counter,
                                                                                 uint32_t* __restrict__ overflow) {
     __shared__ int smem[kSmemStack * kBlock];
@@ -633,6 +640,7 @@ __global__ void __launch_bounds__(kBlock, 6) trace_mbvh_coop_kernel(const Device
                 const unsigned rank = __popc(idle & lt_mask);
                 if (!active && rank < take) {
                     my = (size_t)(res_next + rank);
+                    if (perm) my = (size_t)perm[my];
                     load_ray(rays, my, r);
                     st.reset();
                     cur = 0;
@@ -783,6 +791,34 @@ __global__ void camera_rays_kernel(float3 pos, float3 p1, float3 right, float3 u
 }  // namespace
 
 // ---- launchers ----------------------------------------------------------------------------------
+// ---- optional ray sorting ----------------------------------------------------------------------------
+// Incoherent batches (shadow / bounce rays) are traced in Morton order of (origin, direction): neighbouring
+// lanes then walk neighbouring parts of the tree (fewer distinct lines per load, better L1/L2 hit rates).
+// Results are scattered back through the permutation, so every ray's result is unchanged, bit for bit.
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 0x3FFu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void ray_keys_kernel(const RTRay* __restrict__ rays, size_t n, float3 lo, float3 inv_ext,
+                                unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const F8 ab = ld256(reinterpret_cast<const float4*>(rays) + i * 2);
+    const float ox = (ab.lo.x - lo.x) * inv_ext.x, oy = (ab.lo.y - lo.y) * inv_ext.y, oz = (ab.lo.z - lo.z) * inv_ext.z;
+    const float len = sqrtf(ab.hi.x * ab.hi.x + ab.hi.y * ab.hi.y + ab.hi.z * ab.hi.z);
+    const float il = len > 0.f ? 0.5f / len : 0.f;
+    const float dx = ab.hi.x * il + 0.5f, dy = ab.hi.y * il + 0.5f, dz = ab.hi.z * il + 0.5f;
+    auto q = [](float v) { return (uint32_t)fminf(fmaxf(v * 1024.0f, 0.0f), 1023.0f); };  // NaN -> 0
+    const uint32_t ko = spread10(q(ox)) | (spread10(q(oy)) << 1) | (spread10(q(oz)) << 2);
+    const uint32_t kd = spread10(q(dx)) | (spread10(q(dy)) << 1) | (spread10(q(dz)) << 2);
+    keys[i] = ((unsigned long long)ko << 30) | kd;
+    idx[i] = (uint32_t)i;
+}
+
 // grid of a persistent kernel: resident blocks per SM x number of SMs (queried once per kernel)
 template <class K>
 static unsigned persistent_grid(K kernel) {
@@ -795,8 +831,8 @@ static unsigned persistent_grid(K kernel) {
 
 template <int TREE, bool ANY>
 static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
-                                   uint8_t* d_occluded, unsigned long long* d_counter, uint32_t* d_overflow,
-                                   int mode, cudaStream_t stream) {
+                                   uint8_t* d_occluded, const uint32_t* d_perm, unsigned long long* d_counter,
+                                   uint32_t* d_overflow, int mode, cudaStream_t stream) {
     const size_t blocks_needed = ceil_div(n, kBlock);
     const bool persistent = mode != kTraceStatic;
     if (TREE == RT_TREE_MBVH && mode == kTraceCoop) {
@@ -804,7 +840,7 @@ static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, 
         const unsigned grid = (unsigned)(blocks_needed < machine ? blocks_needed : machine);
         cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
-        trace_mbvh_coop_kernel<ANY><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow);
+        trace_mbvh_coop_kernel<ANY><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow);
         return cudaGetLastError();
     }
     if (persistent) {
@@ -812,24 +848,56 @@ static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, 
         const unsigned grid = (unsigned)(blocks_needed < machine ? blocks_needed : machine);
         cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
-        trace_single_persistent_kernel<TREE, ANY><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded,
+        trace_single_persistent_kernel<TREE, ANY><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_perm,
                                                                               d_counter, d_overflow);
     } else {
         trace_single_kernel<TREE, ANY><<<(unsigned)blocks_needed, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded,
-                                                                                     d_overflow);
+                                                                                     d_perm, d_overflow);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any, const RTRay* d_rays, size_t n,
                                 RTHit* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
-                                uint32_t* d_overflow, int mode, cudaStream_t stream) {
+                                uint32_t* d_overflow, int mode, const float* sort_bounds, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
+    uint32_t* d_perm = nullptr;
+    void* scratch = nullptr;
+    if (sort_bounds != nullptr && n >= 4096 && n < (size_t(1) << 32)) {
+        // scratch from the stream-ordered pool: keys in/out (8 B), indices in/out (4 B), CUB temp
+        size_t temp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                        (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 60, stream);
+        const size_t kb = (n * 8 + 255) & ~size_t(255), ib = (n * 4 + 255) & ~size_t(255);
+        cudaError_t e = cudaMallocAsync(&scratch, 2 * kb + 2 * ib + temp_bytes, stream);
+        if (e != cudaSuccess) return e;
+        char* p = (char*)scratch;
+        unsigned long long* k_in = (unsigned long long*)p;
+        unsigned long long* k_out = (unsigned long long*)(p + kb);
+        uint32_t* i_in = (uint32_t*)(p + 2 * kb);
+        uint32_t* i_out = (uint32_t*)(p + 2 * kb + ib);
+        void* temp = p + 2 * kb + 2 * ib;
+        const float3 lo = make_float3(sort_bounds[0], sort_bounds[1], sort_bounds[2]);
+        const float3 ie = make_float3(1.0f / fmaxf(sort_bounds[3] - sort_bounds[0], 1e-30f),
+                                      1.0f / fmaxf(sort_bounds[4] - sort_bounds[1], 1e-30f),
+                                      1.0f / fmaxf(sort_bounds[5] - sort_bounds[2], 1e-30f));
+        ray_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(d_rays, n, lo, ie, k_in, i_in);
+        e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k_in, k_out, i_in, i_out, (int)n, 0, 60, stream);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(scratch, stream);
+            return e;
+        }
+        d_perm = i_out;
+    }
+    cudaError_t e;
     if (tree_kind == RT_TREE_MBVH)
-        return any ? launch_single_t<RT_TREE_MBVH, true>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, mode, stream)
-                   : launch_single_t<RT_TREE_MBVH, false>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, mode, stream);
-    return any ? launch_single_t<RT_TREE_BVH, true>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, mode, stream)
-               : launch_single_t<RT_TREE_BVH, false>(tree, d_rays, n, d_hits, d_occluded, d_counter, d_overflow, mode, stream);
+        e = any ? launch_single_t<RT_TREE_MBVH, true>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, stream)
+                : launch_single_t<RT_TREE_MBVH, false>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, stream);
+    else
+        e = any ? launch_single_t<RT_TREE_BVH, true>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, stream)
+                : launch_single_t<RT_TREE_BVH, false>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, stream);
+    if (scratch) cudaFreeAsync(scratch, stream);
+    return e;
 }
 
 cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,

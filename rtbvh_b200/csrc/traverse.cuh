@@ -11,9 +11,11 @@ enum TraceMode {
     kTraceCoop = 2,        // same + lane-cooperative node fetch through shared memory (Mbvh; Bvh falls back to 1)
 };
 // d_counter: one 64-bit work counter owned by this launch (zeroed on `stream` by the launcher).
+// sort_bounds: null = trace in the caller's order; else {min xyz, max xyz} of the scene: the batch is traced in
+// Morton order of (origin, direction) and results are scattered back (same results, better coherence).
 cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any, const RTRay* d_rays, size_t n,
                                 RTHit* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
-                                uint32_t* d_overflow, int mode, cudaStream_t stream);
+                                uint32_t* d_overflow, int mode, const float* sort_bounds, cudaStream_t stream);
 cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,
                                  size_t n_packets, float t_min, RTHitPacket4* d_hits, uint8_t* d_occluded,
                                  uint32_t* d_overflow, cudaStream_t stream);

@@ -56,6 +56,9 @@ def main():
         if rank != 0:
             mbvh = api.Mbvh.from_arrays(arrays["mnodes"], arrays["indices"])
     scene = api.Scene(tris, bvh=None, mbvh=mbvh)
+    sort = os.environ.get("CFG4_SORT", "0") == "1"
+    scene.set_ray_sorting(sort)
+    info["ray_sorting"] = sort
     rays = W.shadow_rays(tris, rays_per_rank, first=rank * rays_per_rank)
     d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1).copy()).cuda()
     d_occ = torch.empty(rays_per_rank, dtype=torch.uint8, device="cuda")

@@ -41,6 +41,14 @@ def _check_all_paths(A, O, W, tris, bvh, m, rays, label):
             occ4_w, _, _ = O.trace_packets(otree, tris, packets, mode="any")
             assert np.array_equal(sc.occluded_packets(packets, kind), occ4_w), f"{label}: packet any-hit (tree {kind})"
         assert not sc.stack_overflowed()
+        # optional ray sorting changes the order of work, never a result
+        sc.set_ray_sorting(True)
+        for kind, otree in ((A.TREE_BVH, bvh), (A.TREE_MBVH, m)):
+            want, _, _ = O.trace(otree, tris, rays)
+            assert np.array_equal(sc.intersect(rays, kind), want), f"{label}: sorted launch differs (tree {kind})"
+            occ_w, _, _ = O.trace(otree, tris, rays, mode="any")
+            assert np.array_equal(sc.occluded(rays, kind), occ_w), f"{label}: sorted any-hit differs (tree {kind})"
+        sc.set_ray_sorting(False)
     finally:
         sc.free()
 
@@ -188,4 +196,44 @@ def test_full_size_properties_soup_1m(A, O, W):
     got2 = sc.intersect(again, A.TREE_MBVH)
     assert np.array_equal(got2["t"], got["t"][hit]) and np.array_equal(got2["prim"], got["prim"][hit])
     assert not sc.stack_overflowed()
+    sc.free()
+
+
+def _chain_tree(O, levels):
+    """A hand-made, maximally unbalanced reference-format tree: inner node k has a leaf child and the next inner node.
+    Every box contains the whole scene, so a ray that hits anything keeps one pending entry per level on the stack."""
+    tris = np.zeros((levels + 1, 3, 3), np.float32)
+    for k in range(levels + 1):
+        z = np.float32(1.0 + k)
+        tris[k] = [[-1, -1, z], [1, -1, z], [0, 1, z]]
+    nodes = np.zeros(2 * levels + 1, O.NODE_DTYPE)
+    nodes["min"] = [-2, -2, 0]
+    nodes["max"] = [2, 2, levels + 3]
+    for k in range(levels):
+        inner, leaf, nxt = (0 if k == 0 else 2 * k), 2 * k + 1, 2 * k + 2
+        nodes[inner]["count"], nodes[inner]["left_first"] = -1, leaf
+        nodes[leaf]["count"], nodes[leaf]["left_first"] = 1, k
+    nodes[2 * levels]["count"], nodes[2 * levels]["left_first"] = 1, levels
+    # make the leaf the NEAR child for +z rays so the far (inner) child is pushed first ... and popped last
+    for k in range(levels):
+        nodes[2 * k + 1]["max"] = [2, 2, 1.5 + k]
+    return tris, O.Bvh(nodes, np.arange(levels + 1, dtype=np.uint32))
+
+
+def test_deep_stack_spills_and_overflow_is_reported(A, O, W):
+    """The reference's stack has 32 entries (panic / UB beyond, quirk Q10).  Here entries 32..127 spill to local memory
+    and deeper rays raise an error instead of corrupting memory."""
+    tris, bvh = _chain_tree(O, 100)
+    m = bvh.collapse()
+    rng = np.random.default_rng(1)
+    o = np.stack([rng.uniform(-0.5, 0.5, 2000), rng.uniform(-0.5, 0.5, 2000), np.full(2000, -1.0)], axis=1).astype(np.float32)
+    d = np.tile(np.array([[0, 0, 1]], np.float32), (2000, 1)) + rng.normal(0, 0.01, (2000, 3)).astype(np.float32)
+    rays = W.make_rays(o, d)
+    _, _, c2 = O.trace(bvh, tris, rays, counters=True)
+    assert c2["max_stack"] > 32  # the oracle itself needs more than the reference's 32 entries here
+    _check_all_paths(A, O, W, tris, bvh, m, rays, "chain100")
+    tris, bvh = _chain_tree(O, 300)
+    sc = A.Scene(tris, bvh=A.Bvh.from_arrays(bvh.nodes, bvh.indices))
+    with pytest.raises(A.RtbvhError):
+        sc.intersect(rays, A.TREE_BVH)
     sc.free()
