@@ -1,4 +1,4 @@
-// host_iter.hpp — host-side mirror of the reference's index iterators, used ONLY by the legacy
+// rtbvh_iter.hpp — host-side mirror of the reference's index iterators, used ONLY by the legacy
 // per-candidate callback entry points of include/rtbvh.h (intersect, intersect_packet,
 // intersect_mbvh, intersect_mbvh_packet).  A host function pointer cannot be invoked from a kernel,
 // so these four entry points necessarily run where the callback lives; they are the compatibility
@@ -13,7 +13,7 @@
 #include <cmath>
 #include <cstdint>
 
-#include "../../include/rtbvh.h"
+#include "rtbvh.h"
 
 namespace rtbvh_host {
 

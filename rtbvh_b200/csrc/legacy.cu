@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "build.cuh"
-#include "host_iter.hpp"
+#include "../../include/rtbvh_iter.hpp"
 #include "../../include/rtbvh_gpu.h"
 
 using namespace rtb;
