@@ -289,7 +289,8 @@ ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene h, RTTreeKind tree, con
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
-    RTB_CUDA(launch_trace_packets(*t, tree, false, d_packets, n, t_min, d_hits, nullptr, s->d_overflow, (cudaStream_t)stream));
+    RTB_CUDA(launch_trace_packets(*t, tree, false, d_packets, n, t_min, d_hits, nullptr, s->counter_slot(), s->d_overflow,
+                                  persistent_mode(), (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* d_packets, size_t n,
@@ -298,7 +299,8 @@ ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene h, RTTreeKind tree, cons
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
-    RTB_CUDA(launch_trace_packets(*t, tree, true, d_packets, n, t_min, nullptr, d_occ, s->d_overflow, (cudaStream_t)stream));
+    RTB_CUDA(launch_trace_packets(*t, tree, true, d_packets, n, t_min, nullptr, d_occ, s->counter_slot(), s->d_overflow,
+                                  persistent_mode(), (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene h, uint32_t* overflowed) {
@@ -343,7 +345,8 @@ ResultCode rtbvh_gpu_intersect_packets(RTGpuScene h, RTTreeKind tree, const RTRa
     return run_host_batch(*s, packets, n, sizeof(RTRayPacket4), sizeof(RTHitPacket4), 4, hits,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_packets(*t, tree, false, (const RTRayPacket4*)din, m, t_min,
-                                                          (RTHitPacket4*)dout, nullptr, s->d_overflow, st);
+                                                          (RTHitPacket4*)dout, nullptr, s->counter_slot(), s->d_overflow,
+                                                          persistent_mode(), st);
                           });
 }
 ResultCode rtbvh_gpu_occluded_packets(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* packets, size_t n,
@@ -355,7 +358,7 @@ ResultCode rtbvh_gpu_occluded_packets(RTGpuScene h, RTTreeKind tree, const RTRay
     return run_host_batch(*s, packets, n, sizeof(RTRayPacket4), 4, 4, occluded,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_packets(*t, tree, true, (const RTRayPacket4*)din, m, t_min, nullptr,
-                                                          (uint8_t*)dout, s->d_overflow, st);
+                                                          (uint8_t*)dout, s->counter_slot(), s->d_overflow, persistent_mode(), st);
                           });
 }
 

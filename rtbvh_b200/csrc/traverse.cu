@@ -390,73 +390,80 @@ __device__ __forceinline__ bool packet_candidate(const TriRec* __restrict__ tris
     return false;
 }
 
+// One call = one node visit of the packet; returns true when the packet is done (quad-uniform).
 template <bool ANY>
-__device__ __forceinline__ void trace_mbvh_packet(const DeviceTree& tree, RayRegs& r, Stack& st, bool& retired) {
-    const float4* __restrict__ nodes = tree.nodes;
-    const uint32_t qm = quad_mask();
-    int cur = 0;
-    for (;;) {
-        const float4* n = nodes + (size_t)cur * 8;
-        const F8 q0 = ld256(n), q1 = ld256(n + 2), q2 = ld256(n + 4), q3 = ld256(n + 6);
-        const float4 mnx = q0.lo, mxx = q0.hi, mny = q1.lo, mxy = q1.hi, mnz = q2.lo, mxz = q2.hi;
-        const float4 chf = q3.lo, cnf = q3.hi;
-        const int4 ch = make_int4(__float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w));
-        const int4 cn = make_int4(__float_as_int(cnf.x), __float_as_int(cnf.y), __float_as_int(cnf.z), __float_as_int(cnf.w));
-        const uint32_t mine = r.exact ? mbvh_slabs_lane<true>(mnx, mxx, mny, mxy, mnz, mxz, r)
-                                      : mbvh_slabs_lane<false>(mnx, mxx, mny, mxy, mnz, mxz, r);
-        const uint32_t mask = __reduce_or_sync(qm, mine);  // result |= ... over the 4 rays (mbvh_node.rs:277-279)
-        // no ordering: ids = [0,1,2,3], slots visited 3, 2, 1, 0 (iter_indices.rs:390)
-#pragma unroll 1
-        for (int s = 3; s >= 0; s--) {
-            if (!((mask >> s) & 1u)) continue;
-            const int first = sel4(ch, s), count = sel4(cn, s);
-            if (count > -1) {
-                for (int j = 0; j < count; j++)
-                    if (packet_candidate<ANY>(tree.tris, first + j, r, retired, qm)) return;
-            } else if (first > -1) {
-                st.push(first);
-            }
-        }
-        if (st.sp == 0) return;
-        cur = st.pop();
+__device__ __forceinline__ bool mbvh_packet_step(const DeviceTree& tree, RayRegs& r, Stack& st, int& cur, bool& retired,
+                                                 uint32_t qm) {
+    const MNode nd = mnode_load_global(tree.nodes, cur);
+    const uint32_t mine = r.exact ? mbvh_slabs_lane<true>(nd.mnx, nd.mxx, nd.mny, nd.mxy, nd.mnz, nd.mxz, r)
+                                  : mbvh_slabs_lane<false>(nd.mnx, nd.mxx, nd.mny, nd.mxy, nd.mnz, nd.mxz, r);
+    const uint32_t mask = __reduce_or_sync(qm, mine);  // result |= ... over the 4 rays (mbvh_node.rs:277-279)
+    // no ordering: ids = [0,1,2,3], slots visited 3, 2, 1, 0 (iter_indices.rs:390).  As for single rays the slot
+    // results are frozen at node entry, so the inner slots are pushed first (same stack order) and the leaf
+    // slots are tested afterwards.
+    const int4 ch = nd.ch, cn = nd.cn;
+#pragma unroll
+    for (int s = 3; s >= 0; s--) {
+        const int first = sel4(ch, s), count = sel4(cn, s);
+        if (((mask >> s) & 1u) && count <= -1 && first > -1) st.push(first);
     }
+#pragma unroll 1
+    for (int s = 3; s >= 0; s--) {
+        if (!((mask >> s) & 1u)) continue;
+        const int first = sel4(ch, s), count = sel4(cn, s);
+        for (int j = 0; j < count; j++)
+            if (packet_candidate<ANY>(tree.tris, first + j, r, retired, qm)) return true;
+    }
+    if (st.sp == 0) return true;
+    cur = st.pop();
+    return false;
 }
 
+// One call = one popped node (the root is popped without a box test); returns true when the stack is empty.
 template <bool ANY>
-__device__ __forceinline__ void trace_bvh_packet(const DeviceTree& tree, RayRegs& r, Stack& st, bool& retired) {
+__device__ __forceinline__ bool bvh_packet_step(const DeviceTree& tree, RayRegs& r, Stack& st, int& cur, bool& retired,
+                                                uint32_t qm) {
     const float4* __restrict__ nodes = tree.nodes;
-    const uint32_t qm = quad_mask();
-    st.push(0);
-    while (st.sp > 0) {
-        const int cur = st.pop();
-        const F8 nd = ld256(nodes + (size_t)cur * 2);
-        const int count = __float_as_int(nd.lo.w), left_first = __float_as_int(nd.hi.w);
-        if (count > -1) {
-            for (int i = 0; i < count; i++)
-                if (packet_candidate<ANY>(tree.tris, left_first + i, r, retired, qm)) return;
-        } else if (left_first > -1) {
-            const float4* c = nodes + (size_t)left_first * 2;
-            const F8 lc = ld256(c), rc = ld256(c + 2);
-            const float4 l0 = lc.lo, l1 = lc.hi, r0 = rc.lo, r1 = rc.hi;
-            float kl, kr;
-            const bool ml = r.exact ? aabb_lane<true>(l0, l1, r, kl) : aabb_lane<false>(l0, l1, r, kl);
-            const bool mr = r.exact ? aabb_lane<true>(r0, r1, r, kr) : aabb_lane<false>(r0, r1, r, kr);
-            const bool hl = __any_sync(qm, ml) != 0, hr = __any_sync(qm, mr) != 0;
-            if (hl && hr) {  // BvhNode::sort_nodes4: any lane with t_near_left < t_near_right (bvh_node.rs:180-211)
-                if (__any_sync(qm, kl < kr)) {
-                    st.push(left_first);
-                    st.push(left_first + 1);
-                } else {
-                    st.push(left_first + 1);
-                    st.push(left_first);
-                }
-            } else if (hl) {
+    const F8 nd = ld256(nodes + (size_t)cur * 2);
+    const int count = __float_as_int(nd.lo.w), left_first = __float_as_int(nd.hi.w);
+    int next = -1;
+    if (count > -1) {
+        for (int i = 0; i < count; i++)
+            if (packet_candidate<ANY>(tree.tris, left_first + i, r, retired, qm)) return true;
+    } else if (left_first > -1) {
+        const float4* c = nodes + (size_t)left_first * 2;
+        const F8 lc = ld256(c), rc = ld256(c + 2);
+        const float4 l0 = lc.lo, l1 = lc.hi, r0 = rc.lo, r1 = rc.hi;
+        float kl, kr;
+        const bool ml = r.exact ? aabb_lane<true>(l0, l1, r, kl) : aabb_lane<false>(l0, l1, r, kl);
+        const bool mr = r.exact ? aabb_lane<true>(r0, r1, r, kr) : aabb_lane<false>(r0, r1, r, kr);
+        const bool hl = __any_sync(qm, ml) != 0, hr = __any_sync(qm, mr) != 0;
+        if (hl && hr) {  // BvhNode::sort_nodes4: any lane with t_near_left < t_near_right (bvh_node.rs:180-211)
+            if (__any_sync(qm, kl < kr)) {
                 st.push(left_first);
-            } else if (hr) {
+                next = left_first + 1;
+            } else {
                 st.push(left_first + 1);
+                next = left_first;
             }
+        } else if (hl) {
+            next = left_first;
+        } else if (hr) {
+            next = left_first + 1;
         }
     }
+    if (next < 0) {
+        if (st.sp == 0) return true;
+        next = st.pop();
+    }
+    cur = next;
+    return false;
+}
+
+template <int TREE, bool ANY>
+__device__ __forceinline__ bool packet_step(const DeviceTree& tree, RayRegs& r, Stack& st, int& cur, bool& retired, uint32_t qm) {
+    if (TREE == RT_TREE_MBVH) return mbvh_packet_step<ANY>(tree, r, st, cur, retired, qm);
+    return bvh_packet_step<ANY>(tree, r, st, cur, retired, qm);
 }
 
 // ================================================================================================
@@ -691,6 +698,27 @@ __global__ void __launch_bounds__(kBlock, 6) trace_mbvh_coop_kernel(const Device
     cp_async_wait_all();
 }
 
+__device__ __forceinline__ void load_packet_lane(const RTRayPacket4* __restrict__ packets, size_t p, int ql, float t_min,
+                                                 RayRegs& r) {
+    const float* pk = reinterpret_cast<const float*>(packets + p);
+    r.ox = __ldg(pk + 0 + ql); r.oy = __ldg(pk + 4 + ql); r.oz = __ldg(pk + 8 + ql);
+    r.dx = __ldg(pk + 12 + ql); r.dy = __ldg(pk + 16 + ql); r.dz = __ldg(pk + 20 + ql);
+    r.t = __ldg(pk + 24 + ql);
+    r.t_min = t_min;
+    finish_ray_setup(r);
+}
+template <bool ANY>
+__device__ __forceinline__ void store_packet_lane(const RayRegs& r, bool retired, size_t p, int ql,
+                                                  RTHitPacket4* __restrict__ hits, uint8_t* __restrict__ occluded) {
+    if (ANY) {
+        occluded[p * 4 + ql] = retired ? 1 : 0;
+    } else {
+        hits[p].t[ql] = r.t;
+        hits[p].prim[ql] = r.prim;
+    }
+}
+
+// Static assignment: quad q of the grid traces packet q (A/B: RTBVH_TRACE_MODE=static).
 template <int TREE, bool ANY>
 __global__ void __launch_bounds__(kBlock) trace_packet_kernel(const DeviceTree tree,
                                                               const RTRayPacket4* __restrict__ packets, size_t n_packets,
@@ -700,15 +728,10 @@ __global__ void __launch_bounds__(kBlock) trace_packet_kernel(const DeviceTree t
     __shared__ int smem[kSmemStack * kBlock];
     const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;  // ray index; packet = i / 4
     const size_t p = i >> 2;
-    const int lane = (int)(i & 3);
+    const int ql = (int)(i & 3);
     if (p >= n_packets) return;  // whole quads leave together
-    const float* pk = reinterpret_cast<const float*>(packets + p);
     RayRegs r;
-    r.ox = __ldg(pk + 0 + lane); r.oy = __ldg(pk + 4 + lane); r.oz = __ldg(pk + 8 + lane);
-    r.dx = __ldg(pk + 12 + lane); r.dy = __ldg(pk + 16 + lane); r.dz = __ldg(pk + 20 + lane);
-    r.t = __ldg(pk + 24 + lane);
-    r.t_min = t_min;
-    finish_ray_setup(r);
+    load_packet_lane(packets, p, ql, t_min, r);
     const uint32_t qm = quad_mask();
     int deep[kSpillStack];
     Stack st{smem + threadIdx.x, deep, 0, overflow};
@@ -717,16 +740,78 @@ __global__ void __launch_bounds__(kBlock) trace_packet_kernel(const DeviceTree t
     // MbvhPacketIndexIterator has no such check (the NaN lane just never passes a comparison).
     const bool reject = (TREE == RT_TREE_BVH) && (__any_sync(qm, r.nan) != 0);
     if (tree.node_count != 0 && !reject) {
-        if (TREE == RT_TREE_MBVH)
-            trace_mbvh_packet<ANY>(tree, r, st, retired);
-        else
-            trace_bvh_packet<ANY>(tree, r, st, retired);
+        int cur = 0;
+        while (!packet_step<TREE, ANY>(tree, r, st, cur, retired, qm)) {
+        }
     }
-    if (ANY) {
-        occluded[i] = retired ? 1 : 0;
-    } else {
-        hits[p].t[lane] = r.t;
-        hits[p].prim[lane] = r.prim;
+    store_packet_lane<ANY>(r, retired, p, ql, hits, occluded);
+}
+
+// Persistent warps for packets: 8 quads per warp, idle quads are refilled with the next packets.
+template <int TREE, bool ANY>
+__global__ void __launch_bounds__(kBlock) trace_packet_persistent_kernel(const DeviceTree tree,
+                                                                         const RTRayPacket4* __restrict__ packets,
+                                                                         size_t n_packets, float t_min,
+                                                                         RTHitPacket4* __restrict__ hits,
+                                                                         uint8_t* __restrict__ occluded,
+                                                                         unsigned long long* __restrict__ counter,
+                                                                         uint32_t* __restrict__ overflow) {
+    __shared__ int smem[kSmemStack * kBlock];
+    const unsigned lane = threadIdx.x & 31u;
+    const int ql = (int)(lane & 3u);
+    const unsigned below = (1u << (lane & 28u)) - 1u;  // lanes of lower quads
+    const uint32_t qm = quad_mask();
+    int deep[kSpillStack];
+    Stack st{smem + threadIdx.x, deep, 0, overflow};
+    RayRegs r;
+    int cur = 0;
+    size_t my = 0;
+    bool active = false, retired = false;  // active is quad-uniform
+    unsigned long long res_next = 0, res_end = 0;
+    bool exhausted = false;
+    constexpr unsigned kPacketChunk = kRayChunk / 4;
+    for (;;) {
+        unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (idle == 0xFFFFFFFFu || (!exhausted && __popc(idle) >= kRefillIdle)) {
+            while (idle != 0 && !exhausted) {
+                if (res_next >= res_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(counter, (unsigned long long)kPacketChunk);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (base >= n_packets) {
+                        exhausted = true;
+                        break;
+                    }
+                    res_next = base;
+                    res_end = base + kPacketChunk < n_packets ? base + kPacketChunk : n_packets;
+                }
+                const unsigned long long avail = res_end - res_next;
+                const unsigned want = (unsigned)__popc(idle) >> 2;  // idle quads
+                const unsigned take = avail < want ? (unsigned)avail : want;
+                const unsigned rank = (unsigned)__popc(idle & below) >> 2;  // rank of this quad among the idle quads
+                if (!active && rank < take) {
+                    my = (size_t)(res_next + rank);
+                    load_packet_lane(packets, my, ql, t_min, r);
+                    st.reset();
+                    cur = 0;
+                    retired = false;
+                    const bool reject = (TREE == RT_TREE_BVH) && (__any_sync(qm, r.nan) != 0);
+                    if (tree.node_count != 0 && !reject)
+                        active = true;
+                    else
+                        store_packet_lane<ANY>(r, retired, my, ql, hits, occluded);
+                }
+                res_next += take;
+                idle = __ballot_sync(0xFFFFFFFFu, !active);
+            }
+            if (idle == 0xFFFFFFFFu) break;
+        }
+        if (active) {
+            if (packet_step<TREE, ANY>(tree, r, st, cur, retired, qm)) {
+                store_packet_lane<ANY>(r, retired, my, ql, hits, occluded);
+                active = false;
+            }
+        }
     }
 }
 
@@ -900,23 +985,34 @@ cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any,
     return e;
 }
 
-cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,
-                                 size_t n_packets, float t_min, RTHitPacket4* d_hits, uint8_t* d_occluded,
-                                 uint32_t* d_overflow, cudaStream_t stream) {
-    if (n_packets == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)ceil_div(n_packets * 4, kBlock);
-    if (tree_kind == RT_TREE_MBVH) {
-        if (any)
-            trace_packet_kernel<RT_TREE_MBVH, true><<<grid, kBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_overflow);
-        else
-            trace_packet_kernel<RT_TREE_MBVH, false><<<grid, kBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_overflow);
+template <int TREE, bool ANY>
+static cudaError_t launch_packets_t(const DeviceTree& tree, const RTRayPacket4* d_packets, size_t n_packets, float t_min,
+                                    RTHitPacket4* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
+                                    uint32_t* d_overflow, int mode, cudaStream_t stream) {
+    const size_t blocks_needed = ceil_div(n_packets * 4, kBlock);
+    if (mode != kTraceStatic) {
+        static const unsigned machine = persistent_grid(trace_packet_persistent_kernel<TREE, ANY>);
+        const unsigned grid = (unsigned)(blocks_needed < machine ? blocks_needed : machine);
+        cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+        trace_packet_persistent_kernel<TREE, ANY><<<grid, kBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits,
+                                                                              d_occluded, d_counter, d_overflow);
     } else {
-        if (any)
-            trace_packet_kernel<RT_TREE_BVH, true><<<grid, kBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_overflow);
-        else
-            trace_packet_kernel<RT_TREE_BVH, false><<<grid, kBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_overflow);
+        trace_packet_kernel<TREE, ANY><<<(unsigned)blocks_needed, kBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits,
+                                                                                     d_occluded, d_overflow);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,
+                                 size_t n_packets, float t_min, RTHitPacket4* d_hits, uint8_t* d_occluded,
+                                 unsigned long long* d_counter, uint32_t* d_overflow, int mode, cudaStream_t stream) {
+    if (n_packets == 0) return cudaSuccess;
+    if (tree_kind == RT_TREE_MBVH)
+        return any ? launch_packets_t<RT_TREE_MBVH, true>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_counter, d_overflow, mode, stream)
+                   : launch_packets_t<RT_TREE_MBVH, false>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_counter, d_overflow, mode, stream);
+    return any ? launch_packets_t<RT_TREE_BVH, true>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_counter, d_overflow, mode, stream)
+               : launch_packets_t<RT_TREE_BVH, false>(tree, d_packets, n_packets, t_min, d_hits, d_occluded, d_counter, d_overflow, mode, stream);
 }
 
 cudaError_t launch_gather_tris(const float* d_verts, uint32_t stride_floats, const uint32_t* d_indices,

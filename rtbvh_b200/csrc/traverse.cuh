@@ -18,7 +18,7 @@ cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any,
                                 uint32_t* d_overflow, int mode, const float* sort_bounds, cudaStream_t stream);
 cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,
                                  size_t n_packets, float t_min, RTHitPacket4* d_hits, uint8_t* d_occluded,
-                                 uint32_t* d_overflow, cudaStream_t stream);
+                                 unsigned long long* d_counter, uint32_t* d_overflow, int mode, cudaStream_t stream);
 cudaError_t launch_gather_tris(const float* d_verts, uint32_t stride_floats, const uint32_t* d_indices,
                                uint32_t index_count, uint32_t tri_count, TriRec* d_out, cudaStream_t stream);
 cudaError_t launch_camera_rays(const float pos[3], const float p1[3], const float right[3], const float up[3],
