@@ -262,6 +262,17 @@ ResultCode rtbvh_gpu_scene_free(RTGpuScene h) {
     return Ok;
 }
 
+// Packets: measured (profiles/r1q_matrix.json vs r1h_matrix.json) the static quad-per-packet kernel beats the
+// persistent one by 2-35 % on every scene (coherent packets finish together, the refill bookkeeping only costs),
+// so it is the default; RTBVH_PACKET_MODE=persistent selects the refill kernel.
+int packet_mode() {
+    static const int v = [] {
+        const char* e = std::getenv("RTBVH_PACKET_MODE");
+        return (e && std::string(e) == "persistent") ? (int)kTracePersistent : (int)kTraceStatic;
+    }();
+    return v;
+}
+
 // ---- device-resident, asynchronous ---------------------------------------------------------------
 ResultCode rtbvh_gpu_intersect_device(RTGpuScene h, RTTreeKind tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
                                       void* stream) {
@@ -290,7 +301,7 @@ ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene h, RTTreeKind tree, con
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
     RTB_CUDA(launch_trace_packets(*t, tree, false, d_packets, n, t_min, d_hits, nullptr, s->counter_slot(), s->d_overflow,
-                                  persistent_mode(), (cudaStream_t)stream));
+                                  packet_mode(), (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* d_packets, size_t n,
@@ -300,7 +311,7 @@ ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene h, RTTreeKind tree, cons
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
     RTB_CUDA(launch_trace_packets(*t, tree, true, d_packets, n, t_min, nullptr, d_occ, s->counter_slot(), s->d_overflow,
-                                  persistent_mode(), (cudaStream_t)stream));
+                                  packet_mode(), (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene h, uint32_t* overflowed) {
@@ -346,7 +357,7 @@ ResultCode rtbvh_gpu_intersect_packets(RTGpuScene h, RTTreeKind tree, const RTRa
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_packets(*t, tree, false, (const RTRayPacket4*)din, m, t_min,
                                                           (RTHitPacket4*)dout, nullptr, s->counter_slot(), s->d_overflow,
-                                                          persistent_mode(), st);
+                                                          packet_mode(), st);
                           });
 }
 ResultCode rtbvh_gpu_occluded_packets(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* packets, size_t n,
@@ -358,7 +369,7 @@ ResultCode rtbvh_gpu_occluded_packets(RTGpuScene h, RTTreeKind tree, const RTRay
     return run_host_batch(*s, packets, n, sizeof(RTRayPacket4), 4, 4, occluded,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_packets(*t, tree, true, (const RTRayPacket4*)din, m, t_min, nullptr,
-                                                          (uint8_t*)dout, s->counter_slot(), s->d_overflow, persistent_mode(), st);
+                                                          (uint8_t*)dout, s->counter_slot(), s->d_overflow, packet_mode(), st);
                           });
 }
 
