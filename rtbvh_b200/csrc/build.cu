@@ -248,64 +248,74 @@ __device__ __forceinline__ void bin_accumulate(uint32_t* b, const Box& box) {
     atomicAdd(&b[6], 1u);
 }
 
-// Fill bins with primitives (binned_sah.rs:157-172).  One thread per index position.
+// Fill bins with primitives (binned_sah.rs:157-172).  Every block walks a contiguous span of index positions in
+// chunks of kBinBlock; while consecutive chunks lie inside ONE task (always, on the top levels) the bins are
+// accumulated in shared memory and flushed once per (block, task): the root level then issues grid x 336 global
+// atomics instead of (n / 256) x 336.  Chunks that straddle tasks fall back to direct global atomics (deep
+// levels: small tasks, low contention).
 constexpr int kBinBlock = 256;
+__device__ __forceinline__ void bins_smem_init(uint32_t* sb) {
+    for (int w = threadIdx.x; w < kTaskBinWords; w += kBinBlock) {
+        const int f = w % kBinWords;
+        sb[w] = f < 3 ? fkey(1e34f) : (f < 6 ? fkey(-1e34f) : 0u);
+    }
+}
+__device__ __forceinline__ void bins_smem_flush(const uint32_t* sb, uint32_t* g) {
+    for (int w = threadIdx.x; w < kTaskBinWords; w += kBinBlock) {
+        const int f = w % kBinWords;
+        const uint32_t v = sb[w];
+        if (f < 3) {
+            if (v != fkey(1e34f)) atomicMin(&g[w], v);
+        } else if (f < 6) {
+            if (v != fkey(-1e34f)) atomicMax(&g[w], v);
+        } else if (v) {
+            atomicAdd(&g[w], v);
+        }
+    }
+}
 __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __restrict__ idx, const int32_t* __restrict__ pos_task,
-                                                            uint32_t n, const TaskAux* __restrict__ aux,
+                                                            uint32_t n, uint32_t span, const TaskAux* __restrict__ aux,
                                                             const float4* __restrict__ bb, const float* __restrict__ cen,
                                                             uint32_t cstride, uint32_t* __restrict__ bins) {
     __shared__ uint32_t sb[kTaskBinWords];
-    __shared__ int s_uniform;
-    const uint32_t first = blockIdx.x * kBinBlock;
-    const uint32_t last = min(first + kBinBlock, n) - 1;
-    const uint32_t i = first + threadIdx.x;
-    if (threadIdx.x == 0) {
-        const int32_t a = pos_task[first], b = pos_task[last];
-        s_uniform = (a == b && a >= 0) ? a : -1;  // ranges are contiguous: equal ends => one task
+    const uint64_t begin64 = (uint64_t)blockIdx.x * span;
+    if (begin64 >= n) return;
+    const uint32_t begin = (uint32_t)begin64;
+    const uint32_t end = (uint32_t)min((uint64_t)n, begin64 + span);
+    int cur = -1;  // task whose bins live in shared memory (block-uniform)
+    for (uint32_t c0 = begin; c0 < end; c0 += kBinBlock) {
+        const uint32_t c1 = min(c0 + kBinBlock, end);
+        const int32_t ta = pos_task[c0], tb = pos_task[c1 - 1];
+        const int uni = (ta == tb && ta >= 0) ? ta : -1;  // ranges are contiguous: equal ends => one task
+        if (uni != cur) {
+            if (cur >= 0) {
+                __syncthreads();
+                bins_smem_flush(sb, bins + (size_t)cur * kTaskBinWords);
+            }
+            __syncthreads();
+            if (uni >= 0) bins_smem_init(sb);
+            __syncthreads();
+            cur = uni;
+        }
+        const uint32_t i = c0 + threadIdx.x;
+        if (i < c1) {
+            const int32_t t = uni >= 0 ? uni : pos_task[i];
+            if (t >= 0) {
+                const uint32_t p = idx[i];
+                const TaskAux a = aux[t];
+                const Box box = load_box(bb, p);
+                uint32_t* dst = uni >= 0 ? sb : bins + (size_t)t * kTaskBinWords;
+#pragma unroll
+                for (int ax = 0; ax < 3; ax++) {
+                    const int b = bin_index(cen[(size_t)p * cstride + ax], a.k[ax], a.off[ax]);
+                    bin_accumulate(&dst[(ax * kBins + b) * kBinWords], box);
+                }
+            }
+        }
     }
-    __syncthreads();
-    const int uni = s_uniform;
-    if (uni >= 0) {
-        for (int w = threadIdx.x; w < kTaskBinWords; w += kBinBlock) {
-            const int f = w % kBinWords;
-            sb[w] = f < 3 ? fkey(1e34f) : (f < 6 ? fkey(-1e34f) : 0u);
-        }
+    if (cur >= 0) {
         __syncthreads();
-        if (i < n) {
-            const uint32_t p = idx[i];
-            const TaskAux a = aux[uni];
-            const Box box = load_box(bb, p);
-#pragma unroll
-            for (int ax = 0; ax < 3; ax++) {
-                const int b = bin_index(cen[(size_t)p * cstride + ax], a.k[ax], a.off[ax]);
-                bin_accumulate(&sb[(ax * kBins + b) * kBinWords], box);
-            }
-        }
-        __syncthreads();
-        uint32_t* g = bins + (size_t)uni * kTaskBinWords;
-        for (int w = threadIdx.x; w < kTaskBinWords; w += kBinBlock) {
-            const int f = w % kBinWords;
-            const uint32_t v = sb[w];
-            if (f < 3) {
-                if (v != fkey(1e34f)) atomicMin(&g[w], v);
-            } else if (f < 6) {
-                if (v != fkey(-1e34f)) atomicMax(&g[w], v);
-            } else if (v) {
-                atomicAdd(&g[w], v);
-            }
-        }
-    } else if (i < n) {
-        const int32_t t = pos_task[i];
-        if (t < 0) return;
-        const uint32_t p = idx[i];
-        const TaskAux a = aux[t];
-        const Box box = load_box(bb, p);
-        uint32_t* g = bins + (size_t)t * kTaskBinWords;
-#pragma unroll
-        for (int ax = 0; ax < 3; ax++) {
-            const int b = bin_index(cen[(size_t)p * cstride + ax], a.k[ax], a.off[ax]);
-            bin_accumulate(&g[(ax * kBins + b) * kBinWords], box);
-        }
+        bins_smem_flush(sb, bins + (size_t)cur * kTaskBinWords);
     }
 }
 
@@ -706,12 +716,29 @@ __global__ void __launch_bounds__(kSmallWarps * 32) sah_small_kernel(const Small
         }
         const uint32_t left = next_free;
         next_free += 2;
+        // children that are leaves on entry (one primitive, or the depth cap) are finalised here: entry pad +
+        // make_leaf pad (binned_sah.rs:133-143); only real subtrees go onto the stack
+        const bool cap = e.depth + 1 >= (uint32_t)kMaxDepth;
+        const bool r_leaf = (nn - nleft) <= 1 || cap, l_leaf = nleft <= 1 || cap;
         if (lane == 0) {
             store_node(nodes, e.node, nb, -1, (int)left);
-            s_stack[w][sp] = SmallEntry{left + 1, e.b + nleft, e.e, e.depth + 1, rb};
-            s_stack[w][sp + 1] = SmallEntry{left, e.b, e.b + nleft, e.depth + 1, lb};
+            int k = sp;
+            if (r_leaf) {
+                Box b2 = rb;
+                box_pad(b2, kPad);
+                make_leaf(nodes, left + 1, b2, task.begin + e.b + nleft, nn - nleft);
+            } else {
+                s_stack[w][k++] = SmallEntry{left + 1, e.b + nleft, e.e, e.depth + 1, rb};
+            }
+            if (l_leaf) {
+                Box b2 = lb;
+                box_pad(b2, kPad);
+                make_leaf(nodes, left, b2, task.begin + e.b, nleft);
+            } else {
+                s_stack[w][k++] = SmallEntry{left, e.b, e.b + nleft, e.depth + 1, lb};
+            }
         }
-        sp += 2;
+        sp += (r_leaf ? 0 : 1) + (l_leaf ? 0 : 1);
         __syncwarp();
     }
     if ((uint32_t)lane < n) idx[task.begin + lane] = s_idx[w][lane];
@@ -1192,6 +1219,10 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
     int32_t* pt_cur = ptA.as<int32_t>();
     int32_t* pt_nxt = ptB.as<int32_t>();
     uint32_t S = 0, small_slots = 0;  // small subtrees collected so far and the node slots reserved for them
+    // bin kernel: a machine-sized grid, every block owns a contiguous span (multiple of the chunk size)
+    const uint32_t bin_chunks = blocks(n, kBinBlock);
+    const uint32_t bin_grid = std::min(bin_chunks, 148u * 8u);
+    const uint32_t bin_span = ((bin_chunks + bin_grid - 1) / bin_grid) * kBinBlock;
     // Node slots of small subtrees are numbered after all level nodes; until the level loop ends the final
     // number of level nodes is unknown, so small node_base values are stored relative and rebased below.
     for (uint32_t depth = 0; A > 0; depth++) {
@@ -1201,8 +1232,8 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         sah_prepare_kernel<<<blocks(A, 128), 128>>>(t_cur, A, nodes, aux.as<TaskAux>());
         const size_t words = (size_t)A * kTaskBinWords;
         sah_bins_init_kernel<<<blocks(words, 256), 256>>>(bins.as<uint32_t>(), words);
-        sah_bin_kernel<<<blocks(n, kBinBlock), kBinBlock>>>(idx_cur, pt_cur, n, aux.as<TaskAux>(), d_bb, d_cen, cstride,
-                                                           bins.as<uint32_t>());
+        sah_bin_kernel<<<bin_grid, kBinBlock>>>(idx_cur, pt_cur, n, bin_span, aux.as<TaskAux>(), d_bb, d_cen, cstride,
+                                                bins.as<uint32_t>());
         sah_split_kernel<<<blocks((size_t)A * 32, 128), 128>>>(t_cur, A, bins.as<uint32_t>(), nodes, max_leaf, depth,
                                                                dec.as<Decision>(), counts.as<uint4>());
         size_t tbytes = temp.bytes;
