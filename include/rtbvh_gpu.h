@@ -118,6 +118,9 @@ ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene scene, uint32_t *overflow
  * The result is stored like create_bvh's (free with free_bvh, collapse with create_mbvh). */
 ResultCode rtbvh_gpu_create_bvh_triangles(const float *vertices, size_t vertex_stride, size_t triangle_count,
                                           size_t prims_per_leaf, BvhType bvh_type, RTBvh *result);
+/* Mbvh::construct (src/bvh.rs:381-404) on the GPU for a binary tree that is NOT in this library's table, e.g. a
+ * reference-built spatial-split tree: bvh->nodes / bvh->indices are trusted host pointers.  Free with free_mbvh. */
+ResultCode rtbvh_gpu_create_mbvh_from(const RTBvh *bvh, RTMbvh *mbvh);
 /* Timing of the last create_bvh / create_mbvh / refit / rtbvh_gpu_create_bvh_triangles on this thread:
  * device_ms = kernels only (CUDA events, inputs resident -> tree resident), total_ms = incl. the H2D of the
  * inputs and the D2H of the host mirror; iterations = LOCB clustering iterations. */

@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
     L.rto_bvh_build.restype = C.c_int
     L.rto_bvh_build.argtypes = [C.c_int, vp, sz, vp, sz, sz, sz, C.c_int, C.POINTER(vp), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double)]
+    L.rto_bvh_build_spatial.restype = C.c_int
+    L.rto_bvh_build_spatial.argtypes = [vp, sz, sz, C.c_int, C.POINTER(vp), C.POINTER(C.c_double), vp]
     L.rto_bvh_from_raw.restype = vp
     L.rto_bvh_from_raw.argtypes = [vp, sz, vp, sz]
     L.rto_bvh_free.argtypes = [vp]
@@ -222,6 +224,24 @@ def build(bvh_type: int, aabbs, centers: np.ndarray, prims_per_leaf: int = 1, pa
     L = lib()
     out = Bvh(_copy(L.rto_bvh_nodes(h), L.rto_bvh_node_count(h), NODE_DTYPE),
               _copy(L.rto_bvh_indices(h), L.rto_bvh_index_count(h), np.uint32), ms.value, kappa.value)
+    L.rto_bvh_free(h)
+    return 0, out
+
+
+def build_spatial(verts: np.ndarray, prims_per_leaf: int = 1, fix_child_ranges: bool = True):
+    """Builder::construct_spatial_sah (src/bvh.rs:58-85, src/builders/spatial_sah.rs:925-1033) on the CPU.
+    Returns (result_code, Bvh | None); Bvh.stats = (spatial splits, object splits, references used)."""
+    verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 9)
+    h, ms = C.c_void_p(), C.c_double()
+    stats = np.zeros(3, dtype=np.uint64)
+    rc = lib().rto_bvh_build_spatial(_p(verts), verts.shape[0], prims_per_leaf, int(fix_child_ranges), C.byref(h), C.byref(ms),
+                                     _p(stats))
+    if rc != 0:
+        return rc, None
+    L = lib()
+    out = Bvh(_copy(L.rto_bvh_nodes(h), L.rto_bvh_node_count(h), NODE_DTYPE),
+              _copy(L.rto_bvh_indices(h), L.rto_bvh_index_count(h), np.uint32), ms.value, 0.0)
+    out.stats = tuple(int(x) for x in stats)
     L.rto_bvh_free(h)
     return 0, out
 

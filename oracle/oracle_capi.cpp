@@ -170,6 +170,42 @@ int rto_bvh_build(int type, const void* aabbs, size_t aabb_count, const float* c
     *out = b;
     return 0;
 }
+// Builder::construct_spatial_sah (bvh.rs:58-85) for triangles given as n x 9 floats; aabb = Primitive::aabb
+// (un-padded), center = (v0+v1+v2)*(1/3) like the bench Triangle.  fix_child_ranges: see rtbvh_oracle.hpp.
+int rto_bvh_build_spatial(const float* verts, size_t n, size_t prims_per_leaf, int fix_child_ranges, Bvh** out,
+                          double* build_ms, uint64_t* stats /* spatial splits, object splits, references */) {
+    if (!verts || !out) return 1;
+    if (n == 0) return 2;
+    std::vector<Tri> tris(n);
+    std::vector<Aabb> bbs(n);
+    std::vector<Vec3> c(n);
+    for (size_t i = 0; i < n; i++) {
+        tris[i] = load_tri(verts, i);
+        Aabb bb = aabb_new();
+        grow(bb, tris[i].v0);
+        grow(bb, tris[i].v1);
+        grow(bb, tris[i].v2);
+        bbs[i] = bb;
+        c[i] = (tris[i].v0 + tris[i].v1 + tris[i].v2) * (1.0f / 3.0f);
+    }
+    double t0 = now_ms();
+    SpatialSahBuilder sb;
+    sb.aabbs = bbs.data();
+    sb.tris = tris.data();
+    sb.centers = c.data();
+    sb.n = n;
+    sb.max_leaf_size = prims_per_leaf ? prims_per_leaf : 1;
+    sb.fix_child_ranges = fix_child_ranges != 0;
+    Bvh* b = new Bvh(sb.build());
+    if (build_ms) *build_ms = now_ms() - t0;
+    if (stats) {
+        stats[0] = sb.spatial_splits;
+        stats[1] = sb.object_splits;
+        stats[2] = sb.reference_count;
+    }
+    *out = b;
+    return 0;
+}
 Bvh* rto_bvh_from_raw(const void* nodes, size_t n_nodes, const uint32_t* indices, size_t n_idx) {
     Bvh* b = new Bvh();
     b->nodes.resize(n_nodes);

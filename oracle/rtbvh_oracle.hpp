@@ -973,6 +973,392 @@ struct LocbBuilder {
 };
 
 // ----------------------------------------------------------------------------------
+// Spatial-split SAH (builders/spatial_sah.rs:279-1034) — CPU only: the north star uploads such a
+// tree "unchanged", it is never built on the GPU.  Restated verbatim including its quirks:
+//   * SpatialTriangle::split interpolates edges as a*t*(b-a) instead of a+t*(b-a) (Q9, :91-94);
+//   * run_binning_pass counts `exit` on the FIRST bin and sweeps the already suffix-accumulated boxes (:498-523);
+//   * the "all references on one side" repair uses left_count / 2 as an absolute index (:651-655);
+//   * prim_indices has length N + floor(0.75 N) with unused trailing zeros (:936-940).
+// One behaviour is NOT reproduced by default (fix_child_ranges = true), because it silently drops
+// primitives from every tree: allocate_children moves the right child's references up by
+// left_split_count to make split space for the left child, but then describes the children with the
+// OLD positions (:375-423): the right child sees the first left_split_count references twice and never
+// sees the last left_split_count.  With fix_child_ranges = false the verbatim ranges are used (kept for
+// the test that documents the defect).  Rust's slice::sort_by only ever asks `cmp == Less`, so the
+// reference's non-total comparators (:322-332, :446-454) reduce to stable sorts by `a < b` / by mark.
+// ----------------------------------------------------------------------------------
+struct SpatialReference {
+    Aabb aabb;
+    Vec3 center;
+    uint32_t prim_id;
+};
+static inline void shrink(Aabb& a, const Aabb& b) {  // aabb.rs:287-297
+    for (int i = 0; i < 3; i++) {
+        a.min[i] = f32_max(a.min[i], b.min[i]);
+        a.max[i] = f32_min(a.max[i], b.max[i]);
+    }
+}
+static inline float area(const Aabb& a) {  // aabb.rs:330-335
+    Vec3 e = amax(a) - amin(a);
+    float v = e.x * e.y + e.x * e.z + e.y * e.z;
+    return f32_max(0.0f, v);
+}
+// SpatialTriangle::split (spatial_sah.rs:85-129)
+static inline void tri_split(const Tri& tr, int axis, float position, Aabb* left_out, Aabb* right_out) {
+    const Vec3 p[3] = {tr.v0, tr.v1, tr.v2};
+    Aabb left = aabb_new(), right = aabb_new();
+    auto split_edge = [&](Vec3 a, Vec3 b) {
+        float t = (position - a[axis]) / (b[axis] - a[axis]);
+        return (a * t) * (b - a);  // sic
+    };
+    const bool q0 = p[0][axis] <= position, q1 = p[1][axis] <= position, q2 = p[2][axis] <= position;
+    auto grow_if = [&](bool q, Vec3 pos) { if (q) grow(left, pos); else grow(right, pos); };
+    grow_if(q0, p[0]);
+    grow_if(q1, p[1]);
+    grow_if(q2, p[2]);
+    if (q0 ^ q1) { Vec3 m = split_edge(p[0], p[1]); grow(left, m); grow(right, m); }
+    if (q1 ^ q2) { Vec3 m = split_edge(p[1], p[2]); grow(left, m); grow(right, m); }
+    if (q2 ^ q0) { Vec3 m = split_edge(p[2], p[0]); grow(left, m); grow(right, m); }
+    *left_out = left;
+    *right_out = right;
+}
+static inline size_t f32_as_usize(float f) {  // Rust `as usize`
+    if (!(f > 0.0f)) return 0;
+    if (f >= 1.8446744e19f) return ~size_t(0);
+    return (size_t)f;
+}
+
+struct SpatialSahBuilder {
+    const Aabb* aabbs;
+    const Tri* tris;
+    const Vec3* centers;
+    size_t n;
+    size_t max_leaf_size;
+    bool fix_child_ranges = true;
+    // spatial_sah.rs:866-883
+    size_t binning_pass_count = 2, max_depth = 64, bin_count = 16;
+    float traversal_cost = 1.0f, alpha = 1e-5f, split_factor = 0.75f;
+
+    struct Item {
+        size_t node, begin, end, split_end, depth;
+        bool is_sorted;
+        size_t work() const { return end - begin; }
+    };
+    struct ObjectSplit {
+        float cost = std::numeric_limits<float>::max();
+        long index = -1;  // Option<isize>
+        int axis = 0;
+        Aabb left_box = aabb_new(), right_box = aabb_new();
+    };
+    struct SpatialSplit {
+        float cost = std::numeric_limits<float>::max();
+        float position = 0.0f;
+        int axis = 0;
+    };
+    std::vector<BvhNode> nodes;
+    std::vector<uint32_t> prim_indices;
+    std::vector<Aabb> accumulated;
+    std::vector<SpatialReference> refs[3];
+    std::vector<uint8_t> marks;
+    size_t reference_count = 0, node_count = 1;
+    float spatial_threshold = 0.0f;
+    uint64_t spatial_splits = 0, object_splits = 0;
+
+    void make_leaf(BvhNode& node, size_t begin, size_t end) {  // :727-738
+        size_t prim_count = end - begin;
+        size_t first_prim = reference_count;
+        reference_count += prim_count;
+        for (size_t i = 0; i < prim_count; i++) prim_indices[first_prim + i] = refs[0][begin + i].prim_id;
+        node.extra2 = (int32_t)first_prim;
+        node.extra1 = (int32_t)prim_count;
+    }
+
+    ObjectSplit find_object_split(size_t begin, size_t end, bool is_sorted) {  // :314-368
+        if (!is_sorted) {
+            for (int axis = 0; axis < 3; axis++)
+                std::stable_sort(refs[axis].begin() + begin, refs[axis].begin() + end,
+                                 [axis](const SpatialReference& a, const SpatialReference& b) { return a.center[axis] < b.center[axis]; });
+        }
+        ObjectSplit best;
+        for (int axis = 0; axis < 3; axis++) {
+            Aabb bb = aabb_new();
+            for (size_t i = end - 1; i > begin; i--) {
+                grow_bb(bb, refs[axis][i].aabb);
+                accumulated[i] = bb;
+            }
+            bb = aabb_new();
+            for (size_t i = begin; i < end - 1; i++) {
+                grow_bb(bb, refs[axis][i].aabb);
+                float cost = half_area(bb) * (float)(i + 1 - begin) + half_area(accumulated[i + 1]) * (float)(end - (i + 1));
+                if (cost < best.cost) {
+                    best.cost = cost;
+                    best.axis = axis;
+                    best.index = (long)i + 1;
+                    best.left_box = bb;
+                    best.right_box = accumulated[i + 1];
+                }
+            }
+        }
+        return best;
+    }
+
+    void allocate_children(const Item& it, size_t right_begin, size_t right_end, const Aabb& left_box, const Aabb& right_box,
+                           bool is_sorted, Item* a, Item* b) {  // :370-424
+        size_t left = node_count;
+        node_count += 2;
+        BvhNode& parent = nodes[it.node];
+        parent.extra2 = (int32_t)left;
+        parent.extra1 = -1;
+        offset_by(parent, 0.0001f);
+        nodes[left] = left_box;
+        nodes[left + 1] = right_box;
+        size_t remaining = it.split_end - right_end;
+        float left_cost = half_area(left_box) * (float)(right_begin - it.begin);
+        float right_cost = half_area(right_box) * (float)(right_end - right_begin);
+        size_t left_split_count = remaining == 0 ? 0 : f32_as_usize((float)remaining * (left_cost / (left_cost + right_cost)));
+        if (left_split_count > 0) {
+            for (int k = 0; k < 3; k++)  // move_backward(refs + right_begin, refs + right_end, refs + right_end + lsc)
+                std::move_backward(refs[k].begin() + right_begin, refs[k].begin() + right_end,
+                                   refs[k].begin() + right_end + left_split_count);
+        }
+        size_t left_end = right_begin;
+        if (fix_child_ranges) {
+            *a = Item{left, it.begin, left_end, right_begin + left_split_count, it.depth + 1, is_sorted};
+            *b = Item{left + 1, right_begin + left_split_count, right_end + left_split_count, it.split_end, it.depth + 1, is_sorted};
+        } else {  // verbatim (:405-421)
+            *a = Item{left, it.begin, left_end, right_begin, it.depth + 1, is_sorted};
+            *b = Item{left + 1, right_begin, right_end, it.split_end, it.depth + 1, is_sorted};
+        }
+    }
+
+    void apply_object_split(const Item& it, const ObjectSplit& split, Item* a, Item* b) {  // :426-470
+        size_t split_index = (size_t)split.index;
+        int o0 = (split.axis + 1) % 3, o1 = (split.axis + 2) % 3;
+        for (size_t i = it.begin; i < split_index; i++) marks[refs[split.axis][i].prim_id] = 1;
+        for (size_t i = split_index; i < it.end; i++) marks[refs[split.axis][i].prim_id] = 0;
+        auto marked = [&](const SpatialReference& r) { return marks[r.prim_id] != 0; };
+        std::stable_partition(refs[o0].begin() + it.begin, refs[o0].begin() + it.end, marked);
+        std::stable_partition(refs[o1].begin() + it.begin, refs[o1].begin() + it.end, marked);
+        object_splits++;
+        allocate_children(it, split_index, it.end, split.left_box, split.right_box, true, a, b);
+    }
+
+    bool run_binning_pass(const Item&, SpatialSplit& split, int axis, size_t begin, size_t end, float min, float max, float* lo,
+                          float* hi) {  // :472-535
+        struct Bin {
+            Aabb aabb = aabb_new();
+            size_t entry = 0, exit = 0;
+        };
+        std::vector<Bin> bins(bin_count);
+        float bin_size = (max - min) / (float)bin_count;
+        float inv_size = 1.0f / bin_size;
+        for (size_t i = begin; i < end; i++) {
+            const SpatialReference& ref = refs[0][i];
+            size_t first_bin = std::min(bin_count - 1, f32_as_usize(f32_max(inv_size * (ref.aabb.min[axis] - min), 0.0f)));
+            size_t last_bin = std::min(bin_count - 1, f32_as_usize(f32_max(inv_size * (ref.aabb.max[axis] - min), 0.0f)));
+            if (!is_valid(ref.aabb)) break;
+            Aabb current = ref.aabb;
+            for (size_t j = 0; first_bin + j < last_bin; j++) {
+                Aabb lb, rb;
+                tri_split(tris[ref.prim_id], axis, min + (float)(j + first_bin + 1) * bin_size, &lb, &rb);
+                shrink(lb, current);
+                grow_bb(bins[first_bin + j].aabb, lb);
+                shrink(current, rb);
+            }
+            grow_bb(bins[last_bin].aabb, current);
+            bins[first_bin].entry += 1;
+            bins[first_bin].exit += 1;  // sic
+        }
+        Aabb cur = aabb_new();
+        for (size_t i = bin_count; i > 0; i--) {
+            grow_bb(cur, bins[i - 1].aabb);
+            bins[i - 1].aabb = cur;
+        }
+        size_t left_count = 0, right_count = end - begin;
+        cur = aabb_new();
+        bool found = false;
+        for (size_t i = 0; i + 1 < bin_count; i++) {
+            left_count += bins[i].entry;
+            right_count -= bins[i].exit;
+            grow_bb(cur, bins[i].aabb);
+            float cost = (float)left_count * half_area(cur) + (float)right_count * half_area(bins[i + 1].aabb);
+            if (cost < split.cost) {
+                split.cost = cost;
+                split.axis = axis;
+                split.position = min + (float)(i + 1) * bin_size;
+                found = true;
+            }
+        }
+        if (found) {
+            *lo = split.position - bin_size;
+            *hi = split.position + bin_size;
+        }
+        return found;
+    }
+
+    SpatialSplit find_spatial_split(const Item& it) {  // :537-557
+        SpatialSplit split;
+        for (int axis = 0; axis < 3; axis++) {
+            float mn = nodes[it.node].min[axis], mx = nodes[it.node].max[axis];
+            for (size_t pass = 0; pass < binning_pass_count; pass++) {
+                float lo, hi;
+                if (run_binning_pass(it, split, axis, it.begin, it.end, mn, mx, &lo, &hi)) {
+                    mn = lo;
+                    mx = hi;
+                } else {
+                    break;
+                }
+            }
+        }
+        return split;
+    }
+
+    void apply_spatial_split(const Item& it, const SpatialSplit& split, Item* a, Item* b) {  // :559-716
+        size_t left_end = it.begin, right_begin = it.end, right_end = it.end;
+        Aabb left_box = aabb_new(), right_box = aabb_new();
+        std::vector<SpatialReference>& r = refs[split.axis];
+        size_t i = it.begin;
+        while (i < right_begin) {
+            const Aabb& bb = r[i].aabb;
+            if (bb.max[split.axis] <= split.position) {
+                grow_bb(left_box, bb);
+                std::swap(r[i], r[left_end]);
+                i++;
+                left_end++;
+            } else if (bb.min[split.axis] >= split.position) {
+                grow_bb(right_box, bb);
+                right_begin--;
+                std::swap(r[i], r[right_begin]);
+            } else {
+                i++;
+            }
+        }
+        size_t left_count = left_end - it.begin, right_count = right_end - right_begin;
+        if ((left_count == 0 || right_count == 0) && left_end == right_begin) {
+            if (left_count > 0) left_end = left_count / 2;  // sic: not begin + left_count / 2
+            else left_end += right_count / 2;
+            right_begin = left_end;
+            left_box = aabb_new();
+            right_box = aabb_new();
+            for (size_t k = it.begin; k < left_end; k++) grow_bb(left_box, r[k].aabb);
+            for (size_t k = left_end; k < it.end; k++) grow_bb(right_box, r[k].aabb);
+        }
+        while (left_end < right_begin) {
+            SpatialReference ref = r[left_end];
+            Aabb lp, rp;
+            tri_split(tris[ref.prim_id], split.axis, split.position, &lp, &rp);
+            shrink(lp, ref.aabb);
+            shrink(rp, ref.aabb);
+            if (it.split_end - right_end > 0) {
+                grow_bb(left_box, lp);
+                grow_bb(right_box, rp);
+                r[right_end] = SpatialReference{rp, center(rp), ref.prim_id};
+                r[left_end] = SpatialReference{lp, center(lp), ref.prim_id};
+                right_end++;
+                left_end++;
+                left_count++;
+                right_count++;
+            } else if (left_count < right_count) {
+                grow_bb(left_box, ref.aabb);
+                left_end++;
+                left_count++;
+            } else {
+                grow_bb(right_box, ref.aabb);
+                right_begin--;
+                std::swap(r[right_begin], r[left_end]);
+                right_count++;
+            }
+        }
+        for (int k = 1; k <= 2; k++) {
+            std::vector<SpatialReference>& o = refs[(split.axis + k) % 3];
+            std::copy(r.begin() + it.begin, r.begin() + right_end, o.begin() + it.begin);
+        }
+        spatial_splits++;
+        allocate_children(it, right_begin, right_end, left_box, right_box, false, a, b);
+    }
+
+    bool run(const Item& it, Item* a, Item* b) {  // :720-838
+        BvhNode& node = nodes[it.node];
+        if (it.work() <= 1 || it.depth >= max_depth) {
+            make_leaf(node, it.begin, it.end);
+            return false;
+        }
+        ObjectSplit os = find_object_split(it.begin, it.end, it.is_sorted);
+        SpatialSplit ss;
+        Aabb overlap_box = os.left_box;
+        shrink(overlap_box, os.right_box);
+        float overlap = area(overlap_box);
+        if (overlap > spatial_threshold && (it.split_end - it.end) > 0) ss = find_spatial_split(it);
+        float best_cost = f32_min(ss.cost, os.cost);
+        bool use_spatial = best_cost < os.cost;
+        float max_split_cost = half_area(nodes[it.node]) * ((float)it.work() - traversal_cost);
+        if (best_cost >= max_split_cost) {
+            if (it.work() > max_leaf_size) {
+                use_spatial = false;
+                os.index = (long)((it.begin + it.end) / 2);
+                os.axis = longest_axis(nodes[it.node]);
+                os.left_box = aabb_new();
+                os.right_box = aabb_new();
+                for (size_t i = it.begin; i < (size_t)os.index; i++) grow_bb(os.left_box, refs[os.axis][i].aabb);
+                for (size_t i = (size_t)os.index; i < it.end; i++) grow_bb(os.right_box, refs[os.axis][i].aabb);
+            } else {
+                make_leaf(nodes[it.node], it.begin, it.end);
+                return false;
+            }
+        }
+        if (use_spatial) {
+            apply_spatial_split(it, ss, a, b);
+        } else if (os.index >= 0) {
+            if ((size_t)os.index < it.begin || (size_t)os.index >= it.end) {  // the reference assert!s (panics) here
+                make_leaf(nodes[it.node], it.begin, it.end);
+                return false;
+            }
+            apply_object_split(it, os, a, b);
+        } else {
+            make_leaf(nodes[it.node], it.begin, it.end);
+            return false;
+        }
+        return true;
+    }
+
+    Bvh build() {  // :925-1033
+        Bvh out;
+        if (n == 0) return out;
+        size_t max_ref = n + f32_as_usize((float)n * split_factor);
+        nodes.assign(2 * max_ref + 1, aabb_new());
+        prim_indices.assign(max_ref, 0u);
+        accumulated.assign(max_ref, aabb_new());
+        marks.assign(n, 0);
+        SpatialReference dflt{aabb_new(), v3(0, 0, 0), 0};
+        for (int k = 0; k < 3; k++) {
+            refs[k].assign(max_ref, dflt);
+            for (size_t i = 0; i < n; i++) refs[k][i] = SpatialReference{aabbs[i], centers[i], (uint32_t)i};
+        }
+        Aabb root_bounds = union_of_list(aabbs, n);
+        spatial_threshold = alpha * 2.0f * half_area(root_bounds);
+        node_count = 1;
+        reference_count = 0;
+        nodes[0] = root_bounds;
+        std::vector<Item> stack{Item{0, 0, n, max_ref, 0, false}};
+        while (!stack.empty()) {  // TaskSpawner::run_task, single-thread order (utils.rs:243-288)
+            Item it = stack.back();
+            stack.pop_back();
+            Item a, b;
+            if (run(it, &a, &b)) {
+                if (a.work() < b.work()) std::swap(a, b);
+                stack.push_back(b);
+                stack.push_back(a);
+            }
+        }
+        nodes.resize(node_count);
+        out.nodes = std::move(nodes);
+        out.prim_indices = std::move(prim_indices);
+        out.build_type = 3;
+        return out;
+    }
+};
+
+// ----------------------------------------------------------------------------------
 // Collapse to MBVH (mbvh_node.rs:297-411, bvh.rs:381-404)
 // ----------------------------------------------------------------------------------
 static inline void merge_nodes(size_t m_index, size_t cur_node, const std::vector<BvhNode>& bvh_pool,

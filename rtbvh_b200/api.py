@@ -46,7 +46,7 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_occluded_packets", "rtbvh_gpu_intersect_device", "rtbvh_gpu_occluded_device",
                "rtbvh_gpu_intersect_packets_device", "rtbvh_gpu_occluded_packets_device",
                "rtbvh_gpu_scene_stack_overflowed", "rtbvh_gpu_generate_camera_rays_device",
-               "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats", "rtbvh_gpu_scene_set_ray_sorting")
+               "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats", "rtbvh_gpu_scene_set_ray_sorting", "rtbvh_gpu_create_mbvh_from")
 
 
 class RTBvh(C.Structure):  # rtbvh_ffi/src/lib.rs:210-220
@@ -134,6 +134,8 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_scene_stack_overflowed.argtypes = [u64, C.POINTER(u32)]
     L.rtbvh_gpu_create_bvh_triangles.restype = rc
     L.rtbvh_gpu_create_bvh_triangles.argtypes = [vp, sz, sz, sz, u32, C.POINTER(RTBvh)]
+    L.rtbvh_gpu_create_mbvh_from.restype = rc
+    L.rtbvh_gpu_create_mbvh_from.argtypes = [C.POINTER(RTBvh), C.POINTER(RTMbvh)]
     L.rtbvh_gpu_last_build_stats.restype = rc
     L.rtbvh_gpu_last_build_stats.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u32)]
     L.rtbvh_gpu_generate_camera_rays_device.restype = rc
@@ -229,7 +231,10 @@ class Mbvh:
     @classmethod
     def construct(cls, bvh: Bvh) -> "Mbvh":  # Mbvh::construct / From<Bvh>
         out = RTMbvh(0xFFFFFFFF, 0, None, 0, None)
-        _check(lib().create_mbvh(bvh.rt, C.byref(out)))
+        if bvh.rt.id == 0xFFFFFFFF:  # caller-owned arrays (e.g. a reference-built tree): collapse by pointer
+            _check(lib().rtbvh_gpu_create_mbvh_from(C.byref(bvh.rt), C.byref(out)))
+        else:
+            _check(lib().create_mbvh(bvh.rt, C.byref(out)))
         return cls(out, owned=True)
 
     from_bvh = construct

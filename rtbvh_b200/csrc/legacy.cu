@@ -90,6 +90,20 @@ ResultCode rtbvh_gpu_create_bvh_triangles(const float* vertices, size_t vertex_s
     return Ok;
 }
 
+// rtbvh_gpu.h: Mbvh::construct for a tree that does not live in this library's table (e.g. a reference-built one):
+// the struct's pointers are trusted like intersect() trusts them; the result is stored like create_mbvh's.
+ResultCode rtbvh_gpu_create_mbvh_from(const RTBvh* bvh, RTMbvh* mbvh) {
+    if (!bvh || !mbvh || !bvh->nodes || !bvh->indices) return Error;
+    HostBvh copy;
+    copy.nodes.assign(bvh->nodes, bvh->nodes + bvh->node_count);
+    copy.indices.assign(bvh->indices, bvh->indices + bvh->index_count);
+    auto m = std::make_unique<HostMbvh>();
+    const ResultCode rc = gpu_collapse(copy, m.get());
+    if (rc != Ok) return rc;
+    *mbvh = g_manager.store_mbvh(std::move(m));
+    return Ok;
+}
+
 ResultCode rtbvh_gpu_last_build_stats(double* device_ms, double* total_ms, uint32_t* iterations) {
     if (device_ms) *device_ms = g_build_stats.device_ms;
     if (total_ms) *total_ms = g_build_stats.total_ms;

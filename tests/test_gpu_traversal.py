@@ -237,3 +237,26 @@ def test_deep_stack_spills_and_overflow_is_reported(A, O, W):
     with pytest.raises(A.RtbvhError):
         sc.intersect(rays, A.TREE_BVH)
     sc.free()
+
+
+@pytest.mark.parametrize("fix", [True, False])
+def test_reference_built_spatial_tree_uploaded_unchanged(A, O, W, fix):
+    """Config 5 path: a spatial-split SAH tree built on the CPU (oracle restatement of spatial_sah.rs) is uploaded
+    unchanged — prim_indices of length N + 0.75 N with an unused tail, scheduling-order node numbering — and traversed.
+    The verbatim tree (fix=False) drops primitives on this scene; parity is against the tree as built either way."""
+    tris = W.soup(20_000, seed=W.SEED_SOUP + 5, aniso=(8, 1, 1))
+    rc, bvh = O.build_spatial(tris, 1, fix_child_ranges=fix)
+    assert rc == 0
+    m = bvh.collapse()
+    rays = np.concatenate([W.camera_rays(W.soup_camera(200, 200)), W.random_rays(40_000, *W.bounds(tris))])
+    _check_all_paths(A, O, W, tris, bvh, m, rays, f"sbvh/fix={fix}")
+    # GPU collapse of the (non level-ordered) binary tree equals merge_nodes on the CPU
+    gb = A.Bvh.from_arrays(bvh.nodes, bvh.indices)
+    gm = A.Mbvh.construct(gb)
+    assert gm.nodes.tobytes() == m.nodes.tobytes()
+    gm.free()
+    if fix:
+        bf = O.brute_force(tris, rays)
+        sc = A.Scene(tris, bvh=gb)
+        assert np.array_equal(sc.intersect(rays, A.TREE_BVH), bf)
+        sc.free()
