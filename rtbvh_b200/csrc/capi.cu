@@ -40,8 +40,8 @@ ResultCode fail(const char* what) {
 
 namespace {
 
-constexpr int kPipeStreams = 3;                  // H2D / kernel / D2H of consecutive chunks overlap
-constexpr size_t kChunkRays = size_t(1) << 21;   // 2 Mi rays (64 MiB of RTRay) per pipeline stage
+constexpr int kPipeStreams = 4;                  // H2D / kernel / D2H of consecutive chunks overlap
+constexpr size_t kChunkRays = size_t(1) << 21;   // capacity of one pipeline stage: 2 Mi rays (64 MiB of RTRay)
 constexpr uint32_t kCounterSlots = 1024;
 
 // RTBVH_TRACE_MODE selects the single-ray kernel variant (A/B measurements); default: see kDefaultTraceMode
@@ -77,9 +77,9 @@ struct Scene {
     std::atomic<uint32_t> next_counter{0};
     unsigned long long* counter_slot() { return d_counters + (next_counter.fetch_add(1) % kCounterSlots); }
     // host-buffer pipeline (lazily created)
-    cudaStream_t streams[kPipeStreams] = {nullptr, nullptr, nullptr};
-    void* d_in[kPipeStreams] = {nullptr, nullptr, nullptr};
-    void* d_out[kPipeStreams] = {nullptr, nullptr, nullptr};
+    cudaStream_t streams[kPipeStreams] = {};
+    void* d_in[kPipeStreams] = {};
+    void* d_out[kPipeStreams] = {};
     std::mutex pipe_mutex;
 
     ~Scene() {
@@ -137,7 +137,16 @@ ResultCode run_host_batch(Scene& s, const void* in, size_t units, size_t unit_in
     if (ensure_pipeline(s) != Ok) return Error;
     RTB_CUDA(cudaMemsetAsync(s.d_overflow, 0, sizeof(uint32_t), s.streams[0]));
     RTB_CUDA(cudaStreamSynchronize(s.streams[0]));
-    const size_t chunk_units = kChunkRays / rays_per_unit;
+    // Chunk size: the call drains its pipeline before returning, so the first H2D and the last kernel + D2H are not
+    // overlapped with anything; many small chunks keep that fill/drain cost low (a batch is cut into >= 16 chunks),
+    // a floor of 256 Ki rays keeps every launch big enough to fill the machine.  RTBVH_CHUNK_RAYS overrides.
+    static const size_t forced = [] {
+        const char* e = std::getenv("RTBVH_CHUNK_RAYS");
+        return e ? (size_t)std::strtoull(e, nullptr, 10) : size_t(0);
+    }();
+    size_t chunk_rays = forced ? forced : std::max<size_t>(size_t(1) << 18, (units * rays_per_unit + 15) / 16);
+    chunk_rays = std::min(chunk_rays, kChunkRays);
+    const size_t chunk_units = std::max<size_t>(1, chunk_rays / rays_per_unit);
     size_t done = 0;
     for (int c = 0; done < units; c++) {
         const int k = c % kPipeStreams;
