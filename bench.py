@@ -254,14 +254,24 @@ def run_gpu(args):
 
     # hit records of every rank are gathered over NVLink (all_gather, 8 B per ray), asynchronously so that the
     # transfer of step k overlaps the traversal of step k+1
-    gather = world > 1 and not args.no_gather
-    g_out = [torch.empty(world * rays_per_step * 2, dtype=torch.float32, device="cuda") for _ in range(2)] if gather else None
+    gather = "none" if (world == 1 or args.no_gather) else args.gather
+    g_out = ([torch.empty(world * rays_per_step * 2, dtype=torch.float32, device="cuda") for _ in range(2)]
+             if gather == "nccl" else None)
     works = []
+    fused = None
+    if gather == "fused":
+        # the gather is part of the traversal kernel: every record is stored into all ranks' gather buffers (P2P over
+        # NVLink) as its ray finishes; a one-block device barrier closes each step (rtbvh_b200/multigpu.py FusedGather)
+        from rtbvh_b200 import multigpu as MG
+        fused = MG.FusedGather(rays_per_step, 8)
 
     def step(k):
         b = k % ring
+        if fused is not None:
+            fused.intersect(scene, d_rays[b], rays_per_step, k, d_hits=d_hits[b], stream=stream)
+            return
         scene.intersect_device(d_rays[b], rays_per_step, d_hits[b], api.TREE_MBVH, stream=stream)
-        if gather:
+        if gather == "nccl":
             if len(works) >= 2:
                 works[-2].wait()  # the output buffer about to be reused
             works.append(dist.all_gather_into_tensor(g_out[k % 2], d_hits[b], async_op=True))
@@ -284,6 +294,15 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     if scene.stack_overflowed():
         raise RuntimeError("traversal stack overflow")
+    if fused is not None:
+        # the last timed step's gather buffer must hold every rank's records: compare against an NCCL all_gather
+        k_last = args.warmup + args.steps - 1
+        ref = torch.empty(world * rays_per_step * 2, dtype=torch.float32, device="cuda")
+        dist.all_gather_into_tensor(ref, d_hits[k_last % ring])
+        got = api.device_view(fused.buffer_ptr(k_last), world * rays_per_step * 8)
+        info["fused_gather_equals_all_gather"] = bool(torch.equal(got, ref.view(torch.uint8)))
+        if not info["fused_gather_equals_all_gather"]:
+            raise RuntimeError("fused gather buffer differs from the NCCL all_gather of the same records")
 
     # ---- e2e: host buffers through rtbvh_gpu_intersect -------------------------------------------
     n_host = min(3, ring)
@@ -349,9 +368,12 @@ def run_gpu(args):
                        "rays_per_step": rays_per_step, "frames_per_step": fps, "ray_ring_batches": ring,
                        "l2": "inputs larger than L2 (256 MB rays per step, distinct buffers)",
                        "trace_mode": os.environ.get("RTBVH_TRACE_MODE", "persistent"),
-                       "sharding": ("rays sharded by frame range, tree replicated; hit records all_gathered over NVLink "
-                                    f"({world * rays_per_step * 8} B per step per GPU, overlapped)" if gather else
-                                    "single GPU" if world == 1 else "rays sharded, tree replicated, no gather"), **info},
+                       "sharding": ("rays sharded by frame range, tree replicated; hit records all_gathered over NVLink by "
+                                    f"NCCL ({world * rays_per_step * 8} B per step per GPU, overlapped)" if gather == "nccl" else
+                                    "rays sharded by frame range, tree replicated; gather fused into the traversal kernel: "
+                                    f"P2P stores into every rank's gather buffer ({world * rays_per_step * 8} B per step per "
+                                    "GPU) + one-block device barrier per step, no NCCL on the data path" if gather == "fused"
+                                    else "single GPU" if world == 1 else "rays sharded, tree replicated, no gather"), **info},
             "clocks": clocks, "gpu_launches": args.steps,
             "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": rays_per_step * 32,
                     "d2h_bytes_per_step": rays_per_step * 8, "steps": e2e_steps, "host_equals_resident": same},
@@ -361,6 +383,8 @@ def run_gpu(args):
         os.dup2(real_stdout, 1)
         print(json.dumps(out), flush=True)
         os.dup2(2, 1)
+    if fused is not None:
+        fused.close()
     scene.free()
     if world > 1:
         dist.barrier()
@@ -406,7 +430,9 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / roofline sample (profiling runs)")
-    ap.add_argument("--no-gather", action="store_true", help="N > 1: do not all_gather the hit records")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: do not gather the hit records")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: fused = P2P stores from inside the traversal kernel; nccl = all_gather on a side stream")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: `python bench.py --gpus N` re-launches itself one rank per GPU (the driver uses torchrun directly)

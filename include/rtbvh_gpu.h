@@ -110,6 +110,31 @@ ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene scene, RTTreeKind tree, 
  * Synchronises the device.  Host-buffer calls return Error in that case. */
 ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene scene, uint32_t *overflowed);
 
+/* ---- multi-GPU gather fused into the traversal kernel ---------------------------------------------------------- */
+/* One process per GPU.  Every rank creates a gather buffer (cudaMalloc + cudaIpc handle, 64 bytes), exchanges the
+ * handles out of band (e.g. torch.distributed / MPI), opens its peers' buffers, and passes all destinations (own
+ * pointer + opened peer pointers, at most 8) to the *_scatter calls: each result record is written the moment its ray
+ * finishes to dests[k][dest_offset + i] for every k — P2P stores over NVLink / NVSwitch, overlapped with the traversal,
+ * no collective afterwards.  d_hits / d_occluded (local copy in ray order) may be null.  Synchronise the ranks (a
+ * barrier after the stream has drained) before reading a gather buffer. */
+ResultCode rtbvh_gpu_peer_buffer_create(size_t bytes, void **d_ptr, unsigned char *handle64);
+ResultCode rtbvh_gpu_peer_buffer_open(const unsigned char *handle64, void **d_ptr);
+ResultCode rtbvh_gpu_peer_buffer_close(void *d_ptr);
+ResultCode rtbvh_gpu_peer_buffer_free(void *d_ptr);
+/* Step barrier across the ranks, enqueued on `stream` (one tiny kernel, no host involvement): flag_arrays[k] is rank
+ * k's flag buffer (a zero-initialised peer buffer of >= 8 * count bytes; own pointer at index `rank`).  Publishes `value`
+ * (strictly increasing per call, e.g. step + 1) to every rank and waits until every rank has published it: afterwards
+ * all records scattered by kernels enqueued before the barrier on ANY rank are visible in this rank's gather buffer,
+ * and every rank has finished the kernels it enqueued before ITS barrier (so with two gather buffers used alternately
+ * the buffer of step k-1 may be overwritten by step k+1). */
+ResultCode rtbvh_gpu_peer_barrier(void *const *flag_arrays, int count, int rank, uint64_t value, void *stream);
+ResultCode rtbvh_gpu_intersect_device_scatter(RTGpuScene scene, RTTreeKind tree, const RTRay *d_rays, size_t ray_count,
+                                              RTHit *d_hits, void *const *dests, int dest_count, size_t dest_offset,
+                                              void *stream);
+ResultCode rtbvh_gpu_occluded_device_scatter(RTGpuScene scene, RTTreeKind tree, const RTRay *d_rays, size_t ray_count,
+                                             uint8_t *d_occluded, void *const *dests, int dest_count, size_t dest_offset,
+                                             void *stream);
+
 /* ---- builders ---------------------------------------------------------------------------------- */
 /* create_bvh (rtbvh.h) is the drop-in builder entry: it takes what rtbvh_ffi takes (aabbs + centers).
  * This variant is Builder{aabbs: None, primitives: &[Triangle]}.construct_* (src/bvh.rs:87-137) for

@@ -46,7 +46,9 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_occluded_packets", "rtbvh_gpu_intersect_device", "rtbvh_gpu_occluded_device",
                "rtbvh_gpu_intersect_packets_device", "rtbvh_gpu_occluded_packets_device",
                "rtbvh_gpu_scene_stack_overflowed", "rtbvh_gpu_generate_camera_rays_device",
-               "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats", "rtbvh_gpu_scene_set_ray_sorting", "rtbvh_gpu_create_mbvh_from")
+               "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats", "rtbvh_gpu_scene_set_ray_sorting", "rtbvh_gpu_create_mbvh_from", "rtbvh_gpu_peer_buffer_create",
+               "rtbvh_gpu_peer_buffer_open", "rtbvh_gpu_peer_buffer_close", "rtbvh_gpu_peer_buffer_free",
+               "rtbvh_gpu_intersect_device_scatter", "rtbvh_gpu_occluded_device_scatter", "rtbvh_gpu_peer_barrier")
 
 
 class RTBvh(C.Structure):  # rtbvh_ffi/src/lib.rs:210-220
@@ -134,6 +136,20 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_scene_stack_overflowed.argtypes = [u64, C.POINTER(u32)]
     L.rtbvh_gpu_create_bvh_triangles.restype = rc
     L.rtbvh_gpu_create_bvh_triangles.argtypes = [vp, sz, sz, sz, u32, C.POINTER(RTBvh)]
+    L.rtbvh_gpu_peer_buffer_create.restype = rc
+    L.rtbvh_gpu_peer_buffer_create.argtypes = [sz, C.POINTER(vp), vp]
+    L.rtbvh_gpu_peer_buffer_open.restype = rc
+    L.rtbvh_gpu_peer_buffer_open.argtypes = [vp, C.POINTER(vp)]
+    L.rtbvh_gpu_peer_buffer_close.restype = rc
+    L.rtbvh_gpu_peer_buffer_close.argtypes = [vp]
+    L.rtbvh_gpu_peer_buffer_free.restype = rc
+    L.rtbvh_gpu_peer_buffer_free.argtypes = [vp]
+    L.rtbvh_gpu_peer_barrier.restype = rc
+    L.rtbvh_gpu_peer_barrier.argtypes = [C.POINTER(vp), C.c_int, C.c_int, u64, vp]
+    L.rtbvh_gpu_intersect_device_scatter.restype = rc
+    L.rtbvh_gpu_intersect_device_scatter.argtypes = [u64, C.c_int, vp, sz, vp, C.POINTER(vp), C.c_int, sz, vp]
+    L.rtbvh_gpu_occluded_device_scatter.restype = rc
+    L.rtbvh_gpu_occluded_device_scatter.argtypes = [u64, C.c_int, vp, sz, vp, C.POINTER(vp), C.c_int, sz, vp]
     L.rtbvh_gpu_create_mbvh_from.restype = rc
     L.rtbvh_gpu_create_mbvh_from.argtypes = [C.POINTER(RTBvh), C.POINTER(RTMbvh)]
     L.rtbvh_gpu_last_build_stats.restype = rc
@@ -377,10 +393,72 @@ class Scene:
         _check(lib().rtbvh_gpu_occluded_packets_device(self.handle, tree, _dev_ptr(d_packets), n, t_min, _dev_ptr(d_occ),
                                                        C.c_void_p(stream)))
 
+    # ---- multi-GPU: gather fused into the kernel (P2P stores into peer buffers) ----------------
+    def intersect_device_scatter(self, d_rays, n: int, dests: list[int], dest_offset: int, d_hits=None,
+                                 tree: int = TREE_MBVH, stream: int = 0):
+        arr = (C.c_void_p * len(dests))(*dests)
+        _check(lib().rtbvh_gpu_intersect_device_scatter(self.handle, tree, _dev_ptr(d_rays), n,
+                                                        _dev_ptr(d_hits) if d_hits is not None else None, arr, len(dests),
+                                                        dest_offset, C.c_void_p(stream)))
+
+    def occluded_device_scatter(self, d_rays, n: int, dests: list[int], dest_offset: int, d_occ=None,
+                                tree: int = TREE_MBVH, stream: int = 0):
+        arr = (C.c_void_p * len(dests))(*dests)
+        _check(lib().rtbvh_gpu_occluded_device_scatter(self.handle, tree, _dev_ptr(d_rays), n,
+                                                       _dev_ptr(d_occ) if d_occ is not None else None, arr, len(dests),
+                                                       dest_offset, C.c_void_p(stream)))
+
     def stack_overflowed(self) -> bool:
         v = C.c_uint32(0)
         _check(lib().rtbvh_gpu_scene_stack_overflowed(self.handle, C.byref(v)))
         return bool(v.value)
+
+
+class PeerBuffer:
+    """A gather buffer other ranks can write into: cudaMalloc + cudaIpc handle (64 bytes, exchange out of band)."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        self.handle = (C.c_ubyte * 64)()
+        self.nbytes = nbytes
+        _check(lib().rtbvh_gpu_peer_buffer_create(nbytes, C.byref(self.ptr), self.handle))
+
+    def handle_bytes(self) -> bytes:
+        return bytes(self.handle)
+
+    @staticmethod
+    def open(handle: bytes) -> int:
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _check(lib().rtbvh_gpu_peer_buffer_open(h, C.byref(p)))
+        return p.value
+
+    @staticmethod
+    def close(ptr: int):
+        _check(lib().rtbvh_gpu_peer_buffer_close(C.c_void_p(ptr)))
+
+    def free(self):
+        if self.ptr:
+            lib().rtbvh_gpu_peer_buffer_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+class _DevView:
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def device_view(ptr: int, nbytes: int):
+    """A torch uint8 tensor aliasing raw device memory (e.g. a gather buffer), for stream-ordered consumers."""
+    import torch
+    return torch.as_tensor(_DevView(ptr, nbytes), device="cuda")
+
+
+def peer_barrier(flag_arrays: list[int], rank: int, value: int, stream: int = 0):
+    """Cross-rank step barrier enqueued on `stream` (rtbvh_gpu_peer_barrier)."""
+    arr = (C.c_void_p * len(flag_arrays))(*flag_arrays)
+    _check(lib().rtbvh_gpu_peer_barrier(arr, len(flag_arrays), rank, value, C.c_void_p(stream)))
 
 
 def generate_camera_rays_device(cam: dict, row0: int, rows: int, d_rays, jitter_seed: int = 0, frame: int = 0,

@@ -290,7 +290,7 @@ ResultCode rtbvh_gpu_intersect_device(RTGpuScene h, RTTreeKind tree, const RTRay
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
     RTB_CUDA(launch_trace_single(*t, tree, false, d_rays, n, d_hits, nullptr, s->counter_slot(), s->d_overflow,
-                                 persistent_mode(), s->sort_bounds(), (cudaStream_t)stream));
+                                 persistent_mode(), s->sort_bounds(), nullptr, (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_occluded_device(RTGpuScene h, RTTreeKind tree, const RTRay* d_rays, size_t n, uint8_t* d_occ,
@@ -300,7 +300,7 @@ ResultCode rtbvh_gpu_occluded_device(RTGpuScene h, RTTreeKind tree, const RTRay*
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
     RTB_CUDA(launch_trace_single(*t, tree, true, d_rays, n, nullptr, d_occ, s->counter_slot(), s->d_overflow,
-                                 persistent_mode(), s->sort_bounds(), (cudaStream_t)stream));
+                                 persistent_mode(), s->sort_bounds(), nullptr, (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* d_packets, size_t n,
@@ -323,6 +323,87 @@ ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene h, RTTreeKind tree, cons
                                   packet_mode(), (cudaStream_t)stream));
     return Ok;
 }
+// ---- multi-GPU: gather fused into the traversal kernel (P2P stores into cudaIpc-mapped peer buffers) -----------
+static ResultCode scatter_call(RTGpuScene h, RTTreeKind tree, bool any, const RTRay* d_rays, size_t n, void* d_local,
+                               void* const* dests, int dest_count, size_t dest_offset, void* stream) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    if (dest_count < 0 || dest_count > 8 || (dest_count > 0 && !dests)) return fail("0..8 destinations");
+    PeerDests pd{};
+    for (int k = 0; k < dest_count; k++) pd.p[k] = dests[k];
+    pd.count = dest_count;
+    pd.offset = dest_offset;
+    RTB_CUDA(launch_trace_single(*t, tree, any, d_rays, n, any ? nullptr : (RTHit*)d_local, any ? (uint8_t*)d_local : nullptr,
+                                 s->counter_slot(), s->d_overflow, kTracePersistent, s->sort_bounds(), &pd, (cudaStream_t)stream));
+    return Ok;
+}
+ResultCode rtbvh_gpu_intersect_device_scatter(RTGpuScene h, RTTreeKind tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
+                                              void* const* dests, int dest_count, size_t dest_offset, void* stream) {
+    return scatter_call(h, tree, false, d_rays, n, d_hits, dests, dest_count, dest_offset, stream);
+}
+ResultCode rtbvh_gpu_occluded_device_scatter(RTGpuScene h, RTTreeKind tree, const RTRay* d_rays, size_t n, uint8_t* d_occ,
+                                             void* const* dests, int dest_count, size_t dest_offset, void* stream) {
+    return scatter_call(h, tree, true, d_rays, n, d_occ, dests, dest_count, dest_offset, stream);
+}
+ResultCode rtbvh_gpu_peer_buffer_create(size_t bytes, void** d_ptr, unsigned char* handle64) {
+    if (!d_ptr || !handle64) return fail("null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    RTB_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 256));
+    RTB_CUDA(cudaMemset(*d_ptr, 0, bytes ? bytes : 256));
+    cudaIpcMemHandle_t hnd;
+    RTB_CUDA(cudaIpcGetMemHandle(&hnd, *d_ptr));
+    std::memcpy(handle64, &hnd, 64);
+    return Ok;
+}
+ResultCode rtbvh_gpu_peer_buffer_open(const unsigned char* handle64, void** d_ptr) {
+    if (!d_ptr || !handle64) return fail("null argument");
+    cudaIpcMemHandle_t hnd;
+    std::memcpy(&hnd, handle64, 64);
+    RTB_CUDA(cudaIpcOpenMemHandle(d_ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+    return Ok;
+}
+// Cross-GPU step barrier on a stream (one tiny kernel): thread k publishes `value` into slot `rank` of peer k's
+// flag array (system-scope release after a system fence, so every P2P record written by earlier kernels of this
+// stream is visible first), then spins until slot k of the own flag array has reached `value`.
+__global__ void peer_barrier_kernel(PeerDests flags, int rank, unsigned long long value) {
+    const int k = threadIdx.x;
+    if (k >= flags.count) return;
+    __threadfence_system();
+    void* pk = nullptr;
+    void* pr = nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (j == k) pk = flags.p[j];
+        if (j == rank) pr = flags.p[j];
+    }
+    unsigned long long* remote = static_cast<unsigned long long*>(pk) + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(value) : "memory");
+    const unsigned long long* mine = static_cast<const unsigned long long*>(pr) + k;
+    unsigned long long seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+    } while (seen < value);
+}
+ResultCode rtbvh_gpu_peer_barrier(void* const* flag_arrays, int count, int rank, uint64_t value, void* stream) {
+    if (!flag_arrays || count < 1 || count > 8 || rank < 0 || rank >= count) return fail("1..8 flag arrays, rank < count");
+    PeerDests pd{};
+    for (int k = 0; k < count; k++) pd.p[k] = flag_arrays[k];
+    pd.count = count;
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pd, rank, (unsigned long long)value);
+    RTB_CUDA(cudaGetLastError());
+    return Ok;
+}
+ResultCode rtbvh_gpu_peer_buffer_close(void* d_ptr) {
+    RTB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return Ok;
+}
+ResultCode rtbvh_gpu_peer_buffer_free(void* d_ptr) {
+    RTB_CUDA(cudaFree(d_ptr));
+    return Ok;
+}
+
 ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene h, uint32_t* overflowed) {
     auto s = get_scene(h);
     if (!s || !overflowed) return fail("unknown scene");
@@ -342,7 +423,7 @@ ResultCode rtbvh_gpu_intersect(RTGpuScene h, RTTreeKind tree, const RTRay* rays,
     return run_host_batch(*s, rays, n, sizeof(RTRay), sizeof(RTHit), 1, hits,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_single(*t, tree, false, (const RTRay*)din, m, (RTHit*)dout, nullptr,
-                                                         s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), st);
+                                                         s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), nullptr, st);
                           });
 }
 ResultCode rtbvh_gpu_occluded(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, uint8_t* occluded) {
@@ -353,7 +434,7 @@ ResultCode rtbvh_gpu_occluded(RTGpuScene h, RTTreeKind tree, const RTRay* rays, 
     return run_host_batch(*s, rays, n, sizeof(RTRay), 1, 1, occluded,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_single(*t, tree, true, (const RTRay*)din, m, nullptr, (uint8_t*)dout,
-                                                         s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), st);
+                                                         s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), nullptr, st);
                           });
 }
 ResultCode rtbvh_gpu_intersect_packets(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* packets, size_t n,

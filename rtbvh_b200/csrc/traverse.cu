@@ -479,6 +479,26 @@ __device__ __forceinline__ void load_ray(const RTRay* __restrict__ rays, size_t 
     r.dx = b.x; r.dy = b.y; r.dz = b.z; r.t = b.w;
     finish_ray_setup(r);
 }
+// Result store.  With peer destinations (multi-GPU gather fused into the kernel) the record is also written,
+// the moment its ray finishes, into the gather buffer of every peer GPU (P2P stores over NVLink / NVSwitch to
+// cudaIpc-mapped memory): the transfer overlaps the traversal ray by ray and no collective follows the kernel.
+template <bool ANY>
+__device__ __forceinline__ void store_result(const RayRegs& r, size_t i, RTHit* __restrict__ hits,
+                                             uint8_t* __restrict__ occluded, const PeerDests& pd) {
+    if (ANY) {
+        const uint8_t v = r.prim != kNoHit ? 1 : 0;
+        if (occluded) occluded[i] = v;
+#pragma unroll
+        for (int k = 0; k < 8; k++)  // unrolled: pd stays in the constant bank (no local copy for dynamic indexing)
+            if (k < pd.count) static_cast<uint8_t*>(pd.p[k])[pd.offset + i] = v;
+    } else {
+        const float2 v = make_float2(r.t, __uint_as_float(r.prim));
+        if (hits) reinterpret_cast<float2*>(hits)[i] = v;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < pd.count) static_cast<float2*>(pd.p[k])[pd.offset + i] = v;
+    }
+}
 template <bool ANY>
 __device__ __forceinline__ void store_result(const RayRegs& r, size_t i, RTHit* __restrict__ hits,
                                              uint8_t* __restrict__ occluded) {
@@ -525,7 +545,8 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                                                                          uint8_t* __restrict__ occluded,
                                                                          const uint32_t* __restrict__ perm,
                                                                          unsigned long long* __restrict__ counter,
-                                                                         uint32_t* __restrict__ overflow) {
+                                                                         uint32_t* __restrict__ overflow,
+                                                                         const PeerDests pd) {
     __shared__ int smem[kSmemStack * kBlock];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -565,7 +586,7 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                     if (tree.node_count != 0 && !r.nan)
                         active = true;
                     else
-                        store_result<ANY>(r, my, hits, occluded);
+                        store_result<ANY>(r, my, hits, occluded, pd);
                 }
                 res_next += take;
                 idle = __ballot_sync(0xFFFFFFFFu, !active);
@@ -574,7 +595,7 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
         }
         if (active) {
             if (single_step<TREE, ANY>(tree, r, st, cur)) {
-                store_result<ANY>(r, my, hits, occluded);
+                store_result<ANY>(r, my, hits, occluded, pd);
                 active = false;
             }
         }
@@ -920,7 +941,8 @@ static unsigned persistent_grid(K kernel) {
 template <int TREE, bool ANY>
 static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
                                    uint8_t* d_occluded, const uint32_t* d_perm, unsigned long long* d_counter,
-                                   uint32_t* d_overflow, int mode, cudaStream_t stream) {
+                                   uint32_t* d_overflow, int mode, const PeerDests& pd, cudaStream_t stream) {
+    if (pd.count > 0 && mode != kTracePersistent) return cudaErrorNotSupported;  // the fused gather lives in the default kernel
     const size_t blocks_needed = ceil_div(n, kBlock);
     const bool persistent = mode != kTraceStatic;
     if (TREE == RT_TREE_MBVH && mode == kTraceCoop) {
@@ -937,7 +959,7 @@ static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, 
         cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
         trace_single_persistent_kernel<TREE, ANY><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_perm,
-                                                                              d_counter, d_overflow);
+                                                                              d_counter, d_overflow, pd);
     } else {
         trace_single_kernel<TREE, ANY><<<(unsigned)blocks_needed, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded,
                                                                                      d_perm, d_overflow);
@@ -947,8 +969,11 @@ static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, 
 
 cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any, const RTRay* d_rays, size_t n,
                                 RTHit* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
-                                uint32_t* d_overflow, int mode, const float* sort_bounds, cudaStream_t stream) {
+                                uint32_t* d_overflow, int mode, const float* sort_bounds, const PeerDests* peers,
+                                cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
+    PeerDests pd{};
+    if (peers) pd = *peers;
     uint32_t* d_perm = nullptr;
     void* scratch = nullptr;
     if (sort_bounds != nullptr && n >= 4096 && n < (size_t(1) << 32)) {
@@ -979,11 +1004,11 @@ cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any,
     }
     cudaError_t e;
     if (tree_kind == RT_TREE_MBVH)
-        e = any ? launch_single_t<RT_TREE_MBVH, true>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, stream)
-                : launch_single_t<RT_TREE_MBVH, false>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, stream);
+        e = any ? launch_single_t<RT_TREE_MBVH, true>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, pd, stream)
+                : launch_single_t<RT_TREE_MBVH, false>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, pd, stream);
     else
-        e = any ? launch_single_t<RT_TREE_BVH, true>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, stream)
-                : launch_single_t<RT_TREE_BVH, false>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, stream);
+        e = any ? launch_single_t<RT_TREE_BVH, true>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, pd, stream)
+                : launch_single_t<RT_TREE_BVH, false>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow, mode, pd, stream);
     if (scratch) cudaFreeAsync(scratch, stream);
     return e;
 }

@@ -11,11 +11,19 @@ enum TraceMode {
     kTraceCoop = 2,        // same + lane-cooperative node fetch through shared memory (Mbvh; Bvh falls back to 1)
 };
 // d_counter: one 64-bit work counter owned by this launch (zeroed on `stream` by the launcher).
+// Destinations of the fused multi-GPU gather: up to 8 buffers (own + cudaIpc-mapped peers); record i goes to
+// p[k][offset + i] for every k.  count == 0: plain single-GPU store.
+struct PeerDests {
+    void* p[8];
+    int count;
+    size_t offset;
+};
 // sort_bounds: null = trace in the caller's order; else {min xyz, max xyz} of the scene: the batch is traced in
 // Morton order of (origin, direction) and results are scattered back (same results, better coherence).
 cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any, const RTRay* d_rays, size_t n,
                                 RTHit* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
-                                uint32_t* d_overflow, int mode, const float* sort_bounds, cudaStream_t stream);
+                                uint32_t* d_overflow, int mode, const float* sort_bounds, const PeerDests* peers,
+                                cudaStream_t stream);
 cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,
                                  size_t n_packets, float t_min, RTHitPacket4* d_hits, uint8_t* d_occluded,
                                  unsigned long long* d_counter, uint32_t* d_overflow, int mode, cudaStream_t stream);

@@ -55,3 +55,64 @@ def all_gather_ragged(local, counts: list[int]):
     if all(c == m for c in counts):
         return out
     return torch.cat([out[r * m: r * m + counts[r]] for r in range(world)])
+
+
+class FusedGather:
+    """Gather of the hit records fused into the traversal kernel (rtbvh_gpu_*_device_scatter): every rank owns
+    `buffers` gather buffers of `world * rays_per_rank` records that its peers map with cudaIpc; the kernel writes
+    each record, the moment its ray finishes, into slot [rank * rays_per_rank + i] of EVERY rank's buffer (P2P stores
+    over NVLink / NVSwitch), and a one-block device barrier (rtbvh_gpu_peer_barrier) closes the step — no NCCL call on
+    the data path.  Handles travel once, out of band, through torch.distributed (any backend).
+
+    Buffer discipline: step k uses buffer k % buffers; after `barrier(k)` returns (stream-ordered) buffer k % buffers
+    holds the records of all ranks, and every rank has finished step k's kernel, hence its stream-ordered reads of
+    step k-1: with two buffers, step k+1 may overwrite the buffer of step k-1."""
+
+    def __init__(self, rays_per_rank: int, record_bytes: int, buffers: int = 2):
+        import torch.distributed as dist
+        from . import api
+        self.api = api
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.rays_per_rank, self.record_bytes = rays_per_rank, record_bytes
+        self.own = [api.PeerBuffer(self.world * rays_per_rank * record_bytes) for _ in range(buffers)]
+        self.flags = api.PeerBuffer(64)
+        mine = [b.handle_bytes() for b in self.own] + [self.flags.handle_bytes()]
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        self.opened = []
+        self.dests = []       # dests[b][r] = pointer to rank r's buffer b as seen from this rank
+        for b in range(buffers + 1):
+            row = []
+            for r in range(self.world):
+                if r == self.rank:
+                    row.append((self.own[b] if b < buffers else self.flags).ptr.value)
+                else:
+                    p = api.PeerBuffer.open(everyone[r][b])
+                    self.opened.append(p)
+                    row.append(p)
+            self.dests.append(row)
+        self.flag_dests = self.dests.pop()
+        self.step = 0
+        dist.barrier()
+
+    def buffer_ptr(self, k: int) -> int:
+        return self.own[k % len(self.own)].ptr.value
+
+    def intersect(self, scene, d_rays, n: int, k: int, d_hits=None, tree=None, stream: int = 0, any_hit: bool = False):
+        """Traces this rank's shard for step k, scattering into every rank's buffer k % buffers, then the barrier."""
+        tree = self.api.TREE_MBVH if tree is None else tree
+        fn = scene.occluded_device_scatter if any_hit else scene.intersect_device_scatter
+        fn(d_rays, n, self.dests[k % len(self.own)], self.rank * self.rays_per_rank, d_hits, tree, stream)
+        self.step += 1
+        self.api.peer_barrier(self.flag_dests, self.rank, self.step, stream)
+
+    def close(self):
+        import torch.distributed as dist
+        dist.barrier()
+        for p in self.opened:
+            self.api.PeerBuffer.close(p)
+        self.opened = []
+        dist.barrier()
+        for b in self.own:
+            b.free()
+        self.flags.free()
