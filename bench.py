@@ -9,8 +9,9 @@ fov, hashed sub-pixel jitter per (frame, pixel).  One STEP = `--frames-per-step`
 
   value  : Mrays/s, rays already resident in HBM, one traversal kernel launch per step, CUDA events on the
            launching stream, max over ranks.
-  e2e    : Mrays/s through the host-buffer C-ABI call (rtbvh_gpu_intersect): pinned host rays -> H2D ->
-           kernel -> D2H hits inside the timed region every step.
+  e2e    : Mrays/s through the host-buffer C-ABI calls: pinned host rays -> H2D -> kernel -> D2H hit records inside
+           the timed region every step.  value = submit/wait flavour (rtbvh_gpu_intersect_async + rtbvh_gpu_wait,
+           two steps in flight); sync_call_value = the blocking rtbvh_gpu_intersect.
   roofline.achieved : algorithmic bytes per ray (32 + 8 + 128*n_m + 40*n_p; n_m, n_p = node visits / triangle
            tests per ray counted by the instrumented CPU oracle on a sample of the same rays, SURVEY.md
            section 8d) x rays per launch / mean launch duration; peak = MEASURED_PEAKS.json hbm_gbs.
@@ -318,14 +319,28 @@ def run_gpu(args):
     for k in range(e2e_steps):
         scene.intersect_ptr(h_rays[k % n_host].data_ptr(), rays_per_step, h_hits[k % n_host].data_ptr(), api.TREE_MBVH)
     torch.cuda.synchronize()
+    e2e_sync_ms = (time.perf_counter() - t0) * 1e3
+    # the same steps through the submit / wait flavour of the call, double-buffered the way a renderer streams frames:
+    # step k is submitted while step k-1 is in flight; before a host buffer pair is reused its step has been waited for
+    barrier()
+    tickets = []
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        if k >= 2:
+            scene.wait(tickets[k - 2])
+        tickets.append(scene.intersect_async(h_rays[k % n_host].data_ptr(), rays_per_step, h_hits[k % n_host].data_ptr(),
+                                             api.TREE_MBVH))
+    scene.wait(0)
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    same_async = bool(torch.equal(h_hits[(e2e_steps - 1) % n_host].view(torch.int32),
+                                  d_hits[(e2e_steps - 1) % n_host].cpu().view(torch.int32)))
     # the host-buffer path must agree with the resident path on the same rays
     same = bool(torch.equal(h_hits[0].view(torch.int32), d_hits[0].cpu().view(torch.int32)))
 
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_ms, e2e_sync_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, e2e_sync_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         total_rays = world * args.steps * rays_per_step
@@ -376,7 +391,12 @@ def run_gpu(args):
                                     else "single GPU" if world == 1 else "rays sharded, tree replicated, no gather"), **info},
             "clocks": clocks, "gpu_launches": args.steps,
             "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": rays_per_step * 32,
-                    "d2h_bytes_per_step": rays_per_step * 8, "steps": e2e_steps, "host_equals_resident": same},
+                    "d2h_bytes_per_step": rays_per_step * 8, "steps": e2e_steps,
+                    "host_equals_resident": same and same_async,
+                    "call": "rtbvh_gpu_intersect_async + rtbvh_gpu_wait, pinned host rays in / host hit records out every "
+                            "step, two steps in flight (double-buffered)",
+                    "sync_call_value": world * e2e_steps * rays_per_step / e2e_sync_ms / 1e3,
+                    "sync_call": "rtbvh_gpu_intersect (blocking: the pipeline fills and drains inside every call)"},
             "roofline": roof, "cpu_baseline": cpu,
         }
         sys.stdout.flush()

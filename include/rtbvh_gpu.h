@@ -89,6 +89,20 @@ ResultCode rtbvh_gpu_scene_set_ray_sorting(RTGpuScene scene, int enable);
 ResultCode rtbvh_gpu_intersect(RTGpuScene scene, RTTreeKind tree, const RTRay *rays, size_t ray_count, RTHit *hits);
 ResultCode rtbvh_gpu_occluded(RTGpuScene scene, RTTreeKind tree, const RTRay *rays, size_t ray_count,
                               uint8_t *occluded);
+/* Asynchronous flavour of the two calls above for callers that stream batches (a renderer double-buffers its ray
+ * and hit buffers): submit returns at once with a ticket; rtbvh_gpu_wait(scene, ticket) blocks until that batch's
+ * records are in its output buffer (ticket 0: everything submitted so far) and reports Error if a traversal stack
+ * overflowed.  Batches complete in submission order.  Consecutive submissions share the staging pipeline, so batch
+ * k+1 uploads while batch k still traces and downloads.  The host buffers must stay untouched until the wait returns
+ * and should be page-locked (rtbvh_gpu_host_alloc, cudaHostAlloc or cudaHostRegister); pageable buffers work but make
+ * submit block.  At most 64 tickets may be outstanding per scene (an older one is waited for implicitly). */
+ResultCode rtbvh_gpu_intersect_async(RTGpuScene scene, RTTreeKind tree, const RTRay *rays, size_t ray_count, RTHit *hits,
+                                     uint64_t *ticket);
+ResultCode rtbvh_gpu_occluded_async(RTGpuScene scene, RTTreeKind tree, const RTRay *rays, size_t ray_count,
+                                    uint8_t *occluded, uint64_t *ticket);
+ResultCode rtbvh_gpu_wait(RTGpuScene scene, uint64_t ticket);
+ResultCode rtbvh_gpu_host_alloc(size_t bytes, void **ptr); /* page-locked host memory */
+ResultCode rtbvh_gpu_host_free(void *ptr);
 /* Packets follow SpatialTriangle::intersect4 (eps 1e-6, t >= t_min): pass t_min = 1e-4f to match
  * examples/benchmark.rs:58.  occluded: 4 bytes per packet. */
 ResultCode rtbvh_gpu_intersect_packets(RTGpuScene scene, RTTreeKind tree, const RTRayPacket4 *packets,

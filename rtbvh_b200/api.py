@@ -48,7 +48,9 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_scene_stack_overflowed", "rtbvh_gpu_generate_camera_rays_device",
                "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats", "rtbvh_gpu_scene_set_ray_sorting", "rtbvh_gpu_create_mbvh_from", "rtbvh_gpu_peer_buffer_create",
                "rtbvh_gpu_peer_buffer_open", "rtbvh_gpu_peer_buffer_close", "rtbvh_gpu_peer_buffer_free",
-               "rtbvh_gpu_intersect_device_scatter", "rtbvh_gpu_occluded_device_scatter", "rtbvh_gpu_peer_barrier")
+               "rtbvh_gpu_intersect_device_scatter", "rtbvh_gpu_occluded_device_scatter", "rtbvh_gpu_peer_barrier",
+               "rtbvh_gpu_intersect_async", "rtbvh_gpu_occluded_async", "rtbvh_gpu_wait", "rtbvh_gpu_host_alloc",
+               "rtbvh_gpu_host_free")
 
 
 class RTBvh(C.Structure):  # rtbvh_ffi/src/lib.rs:210-220
@@ -144,6 +146,16 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_peer_buffer_close.argtypes = [vp]
     L.rtbvh_gpu_peer_buffer_free.restype = rc
     L.rtbvh_gpu_peer_buffer_free.argtypes = [vp]
+    L.rtbvh_gpu_intersect_async.restype = rc
+    L.rtbvh_gpu_intersect_async.argtypes = [u64, C.c_int, vp, sz, vp, C.POINTER(u64)]
+    L.rtbvh_gpu_occluded_async.restype = rc
+    L.rtbvh_gpu_occluded_async.argtypes = [u64, C.c_int, vp, sz, vp, C.POINTER(u64)]
+    L.rtbvh_gpu_wait.restype = rc
+    L.rtbvh_gpu_wait.argtypes = [u64, u64]
+    L.rtbvh_gpu_host_alloc.restype = rc
+    L.rtbvh_gpu_host_alloc.argtypes = [sz, C.POINTER(vp)]
+    L.rtbvh_gpu_host_free.restype = rc
+    L.rtbvh_gpu_host_free.argtypes = [vp]
     L.rtbvh_gpu_peer_barrier.restype = rc
     L.rtbvh_gpu_peer_barrier.argtypes = [C.POINTER(vp), C.c_int, C.c_int, u64, vp]
     L.rtbvh_gpu_intersect_device_scatter.restype = rc
@@ -377,6 +389,20 @@ class Scene:
     # ---- raw host pointers (pinned torch tensors etc.) ----------------------------------------
     def intersect_ptr(self, rays_ptr: int, n: int, hits_ptr: int, tree: int = TREE_MBVH):
         _check(lib().rtbvh_gpu_intersect(self.handle, tree, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr)))
+
+    # ---- asynchronous host-buffer calls: submit -> ticket, wait(ticket) ------------------------
+    def intersect_async(self, rays_ptr: int, n: int, hits_ptr: int, tree: int = TREE_MBVH) -> int:
+        t = C.c_uint64(0)
+        _check(lib().rtbvh_gpu_intersect_async(self.handle, tree, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr), C.byref(t)))
+        return t.value
+
+    def occluded_async(self, rays_ptr: int, n: int, occ_ptr: int, tree: int = TREE_MBVH) -> int:
+        t = C.c_uint64(0)
+        _check(lib().rtbvh_gpu_occluded_async(self.handle, tree, C.c_void_p(rays_ptr), n, C.c_void_p(occ_ptr), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int = 0):
+        _check(lib().rtbvh_gpu_wait(self.handle, ticket))
 
     # ---- device-resident, asynchronous on `stream` (a cudaStream_t as int) --------------------
     def intersect_device(self, d_rays, n: int, d_hits, tree: int = TREE_MBVH, stream: int = 0):

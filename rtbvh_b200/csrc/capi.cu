@@ -40,9 +40,14 @@ ResultCode fail(const char* what) {
 
 namespace {
 
+constexpr int kTickets = 64;                     // outstanding asynchronous submissions per scene
 constexpr int kPipeStreams = 4;                  // H2D / kernel / D2H of consecutive chunks overlap
 constexpr size_t kChunkRays = size_t(1) << 21;   // capacity of one pipeline stage: 2 Mi rays (64 MiB of RTRay)
 constexpr uint32_t kCounterSlots = 1024;
+constexpr size_t kSubChunkRays = size_t(1) << 18;  // gated pipeline: watermark granularity (8 MiB of RTRay per H2D copy)
+constexpr size_t kMinChunkRays = size_t(1) << 17;  // gated pipeline: smallest launch (the tail of a batch ramps down to this)
+constexpr int kReadySlots = 64;
+constexpr int kMarkSlots = 4096;
 
 // RTBVH_TRACE_MODE selects the single-ray kernel variant (A/B measurements); default: see kDefaultTraceMode
 constexpr int kDefaultTraceMode = kTracePersistent;
@@ -81,6 +86,18 @@ struct Scene {
     void* d_in[kPipeStreams] = {};
     void* d_out[kPipeStreams] = {};
     std::mutex pipe_mutex;
+    uint64_t chunk_seq = 0;  // staging slot rotation across batches
+    struct Ticket {
+        uint64_t id = 0;
+        cudaEvent_t ev[kPipeStreams] = {};
+    };
+    Ticket tickets[kTickets];
+    uint64_t next_ticket = 1;
+    // gated pipeline (single rays): one copy stream feeds launches that start before their input has arrived
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_start[kPipeStreams] = {}, ev_done[kPipeStreams] = {};
+    unsigned long long* d_ready = nullptr;   // kReadySlots watermarks (rays delivered per launch)
+    unsigned long long* h_marks = nullptr;   // pinned source values of the watermark copies
 
     ~Scene() {
         cudaSetDevice(device);
@@ -88,7 +105,15 @@ struct Scene {
             if (streams[i]) cudaStreamDestroy(streams[i]);
             cudaFree(d_in[i]);
             cudaFree(d_out[i]);
+            if (ev_start[i]) cudaEventDestroy(ev_start[i]);
+            if (ev_done[i]) cudaEventDestroy(ev_done[i]);
         }
+        for (auto& t : tickets)
+            for (auto e : t.ev)
+                if (e) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        cudaFree(d_ready);
+        if (h_marks) cudaFreeHost(h_marks);
         cudaFree(d_bvh_nodes);
         cudaFree(d_mbvh_nodes);
         if (d_tris_mbvh != d_tris_bvh) cudaFree(d_tris_mbvh);
@@ -121,25 +146,52 @@ ResultCode ensure_pipeline(Scene& s) {
         RTB_CUDA(cudaStreamCreateWithFlags(&s.streams[i], cudaStreamNonBlocking));
         RTB_CUDA(cudaMalloc(&s.d_in[i], kChunkRays * sizeof(RTRay)));  // a packet chunk is kChunkRays/4 * 112 B < this
         RTB_CUDA(cudaMalloc(&s.d_out[i], kChunkRays * sizeof(RTHit)));
+        RTB_CUDA(cudaEventCreateWithFlags(&s.ev_start[i], cudaEventDisableTiming));
+        RTB_CUDA(cudaEventCreateWithFlags(&s.ev_done[i], cudaEventDisableTiming));
+    }
+    RTB_CUDA(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+    RTB_CUDA(cudaMalloc(&s.d_ready, kReadySlots * sizeof(unsigned long long)));
+    RTB_CUDA(cudaHostAlloc(&s.h_marks, kMarkSlots * sizeof(unsigned long long), cudaHostAllocDefault));
+    return Ok;
+}
+
+enum HostMode { kHostStaged = 0, kHostGated = 1 };
+// Measured on B200 (profiles/r2_host_pipeline.md): staged 1.33 Grays/s; gated 1.30-1.34; kernels reading pinned host
+// rays directly over PCIe 1.11; reading rays and writing records directly 0.74.  Staged stays the default.
+constexpr int kDefaultHostMode = kHostStaged;
+int host_mode() {
+    static const int v = [] {
+        const char* e = std::getenv("RTBVH_HOST_MODE");
+        if (!e) return kDefaultHostMode;
+        const std::string m(e);
+        if (m == "staged") return (int)kHostStaged;
+        if (m == "gated") return (int)kHostGated;
+        return kDefaultHostMode;
+    }();
+    return v;
+}
+
+// Reads (and clears) the scene's stack-overflow flag once the pipeline streams have drained.
+ResultCode check_overflow(Scene& s) {
+    uint32_t ovf = 0;
+    RTB_CUDA(cudaMemcpy(&ovf, s.d_overflow, sizeof(ovf), cudaMemcpyDeviceToHost));
+    if (ovf) {
+        RTB_CUDA(cudaMemset(s.d_overflow, 0, sizeof(uint32_t)));
+        return fail("traversal stack overflow (> 64 entries)");
     }
     return Ok;
 }
 
-// One host-buffer batch: chunks flow through kPipeStreams streams, each doing H2D -> kernel -> D2H.
+// Enqueues one host-buffer batch: chunks flow through kPipeStreams streams, each doing H2D -> kernel -> D2H into its
+// own staging slot, so the copy engines and the SMs overlap across chunks — and across consecutive batches when the
+// caller does not wait in between (the *_async entry points).  The caller holds s.pipe_mutex.
 // unit_in / unit_out are bytes per ray (single) or per packet; rays_per_unit is 1 or 4.
 template <class Launch>
-ResultCode run_host_batch(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit,
-                          void* out, Launch&& launch) {
-    if (units == 0) return Ok;
-    if (!in || !out) return fail("null host buffer");
-    std::lock_guard<std::mutex> lk(s.pipe_mutex);
-    RTB_CUDA(cudaSetDevice(s.device));
-    if (ensure_pipeline(s) != Ok) return Error;
-    RTB_CUDA(cudaMemsetAsync(s.d_overflow, 0, sizeof(uint32_t), s.streams[0]));
-    RTB_CUDA(cudaStreamSynchronize(s.streams[0]));
-    // Chunk size: the call drains its pipeline before returning, so the first H2D and the last kernel + D2H are not
-    // overlapped with anything; many small chunks keep that fill/drain cost low (a batch is cut into >= 16 chunks),
-    // a floor of 256 Ki rays keeps every launch big enough to fill the machine.  RTBVH_CHUNK_RAYS overrides.
+ResultCode enqueue_host_batch(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit,
+                              void* out, Launch&& launch) {
+    // Chunk size: a synchronous call drains its pipeline before returning, so the first H2D and the last kernel + D2H
+    // are not overlapped with anything; many small chunks keep that fill/drain cost low (a batch is cut into >= 16
+    // chunks), a floor of 256 Ki rays keeps every launch big enough to fill the machine.  RTBVH_CHUNK_RAYS overrides.
     static const size_t forced = [] {
         const char* e = std::getenv("RTBVH_CHUNK_RAYS");
         return e ? (size_t)std::strtoull(e, nullptr, 10) : size_t(0);
@@ -148,20 +200,201 @@ ResultCode run_host_batch(Scene& s, const void* in, size_t units, size_t unit_in
     chunk_rays = std::min(chunk_rays, kChunkRays);
     const size_t chunk_units = std::max<size_t>(1, chunk_rays / rays_per_unit);
     size_t done = 0;
-    for (int c = 0; done < units; c++) {
-        const int k = c % kPipeStreams;
+    static const bool trace = std::getenv("RTBVH_PIPE_TRACE") != nullptr;  // debug: per-chunk timeline on stderr
+    std::vector<cudaEvent_t> ev;
+    if (trace) {
+        ev.resize(1);
+        cudaEventCreate(&ev[0]);
+        cudaEventRecord(ev[0], s.streams[0]);
+    }
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+    };
+    while (done < units) {
+        const int k = (int)(s.chunk_seq++ % kPipeStreams);  // slots rotate across batches
         const size_t m = units - done < chunk_units ? units - done : chunk_units;
         cudaStream_t st = s.streams[k];
+        mark(st);
         RTB_CUDA(cudaMemcpyAsync(s.d_in[k], (const char*)in + done * unit_in, m * unit_in, cudaMemcpyHostToDevice, st));
+        mark(st);
         RTB_CUDA(launch(s.d_in[k], m, s.d_out[k], st));
+        mark(st);
         RTB_CUDA(cudaMemcpyAsync((char*)out + done * unit_out, s.d_out[k], m * unit_out, cudaMemcpyDeviceToHost, st));
+        mark(st);
         done += m;
     }
-    for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s.streams[i]));
-    uint32_t ovf = 0;
-    RTB_CUDA(cudaMemcpy(&ovf, s.d_overflow, sizeof(ovf), cudaMemcpyDeviceToHost));
-    if (ovf) return fail("traversal stack overflow (> 64 entries)");
+    if (trace) {
+        for (int i = 0; i < kPipeStreams; i++) cudaStreamSynchronize(s.streams[i]);
+        for (size_t c = 0; 1 + 4 * c + 3 < ev.size(); c++) {
+            float t[4];
+            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], ev[0], ev[1 + 4 * c + j]);
+            std::fprintf(stderr, "chunk %2zu: h2d %.3f-%.3f  kernel -%.3f  d2h -%.3f ms\n", c, t[0], t[1], t[2], t[3]);
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+    }
     return Ok;
+}
+
+// Synchronous host-buffer call: enqueue, drain, check.
+template <class Launch>
+ResultCode run_host_batch(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit,
+                          void* out, Launch&& launch) {
+    if (units == 0) return Ok;
+    if (!in || !out) return fail("null host buffer");
+    std::lock_guard<std::mutex> lk(s.pipe_mutex);
+    RTB_CUDA(cudaSetDevice(s.device));
+    if (ensure_pipeline(s) != Ok) return Error;
+    if (enqueue_host_batch(s, in, units, unit_in, unit_out, rays_per_unit, out, launch) != Ok) return Error;
+    for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s.streams[i]));
+    return check_overflow(s);
+}
+
+// Asynchronous host-buffer call: enqueue and hand out a ticket; rtbvh_gpu_wait(ticket) blocks until this batch's records
+// are in `out`.  Consecutive submissions share the staging slots and streams, so batch k+1 uploads while batch k still
+// traces / downloads: the per-call pipeline fill and drain disappear from a steady stream of batches.
+template <class Launch>
+ResultCode submit_host_batch(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit,
+                             void* out, uint64_t* ticket, Launch&& launch) {
+    if (!ticket) return fail("null ticket");
+    if (units != 0 && (!in || !out)) return fail("null host buffer");
+    std::unique_lock<std::mutex> lk(s.pipe_mutex);
+    RTB_CUDA(cudaSetDevice(s.device));
+    if (ensure_pipeline(s) != Ok) return Error;
+    const uint64_t id = s.next_ticket++;
+    Scene::Ticket& t = s.tickets[id % kTickets];
+    if (t.id != 0) {  // the ring wrapped onto a ticket nobody waited for: it must have completed before its events are reused
+        for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaEventSynchronize(t.ev[i]));
+    }
+    if (units != 0 && enqueue_host_batch(s, in, units, unit_in, unit_out, rays_per_unit, out, launch) != Ok) return Error;
+    for (int i = 0; i < kPipeStreams; i++) {
+        if (!t.ev[i]) RTB_CUDA(cudaEventCreateWithFlags(&t.ev[i], cudaEventDisableTiming));
+        RTB_CUDA(cudaEventRecord(t.ev[i], s.streams[i]));
+    }
+    t.id = id;
+    *ticket = id;
+    return Ok;
+}
+
+ResultCode wait_ticket(Scene& s, uint64_t ticket) {
+    RTB_CUDA(cudaSetDevice(s.device));
+    cudaEvent_t ev[kPipeStreams] = {};
+    {
+        std::lock_guard<std::mutex> lk(s.pipe_mutex);
+        if (!s.streams[0]) return Ok;  // nothing was ever submitted
+        if (ticket == 0) {             // everything submitted so far
+            for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s.streams[i]));
+            return check_overflow(s);
+        }
+        if (ticket >= s.next_ticket) return fail("unknown ticket");
+        const Scene::Ticket& t = s.tickets[ticket % kTickets];
+        // a recycled slot means submit_host_batch already waited for this ticket before reusing its events
+        if (t.id != ticket) return check_overflow(s);
+        for (int i = 0; i < kPipeStreams; i++) ev[i] = t.ev[i];
+    }
+    for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaEventSynchronize(ev[i]));
+    return check_overflow(s);
+}
+
+// Host-buffer batch of single rays, gated: the batch is cut into a few launches (<= 2 Mi rays, ramping down to 128 Ki
+// at the end); ONE copy stream uploads the rays back to back in 8 MiB pieces, each followed by an 8-byte watermark copy,
+// and every launch starts as soon as its slot is free — its warps wait on the watermark for ranges that have not arrived
+// (PeerDests::ready).  The copy engine therefore never waits for a kernel boundary, kernels of consecutive launches
+// overlap (streams), and what is left after the last byte has crossed PCIe is the traversal of the last 128 Ki rays and
+// a 1 MiB D2H.  launch(din, m, dout, ready, stream).
+template <class Launch>
+ResultCode run_host_batch_gated(Scene& s, const RTRay* in, size_t n, size_t unit_out, void* out, Launch&& launch) {
+    if (n == 0) return Ok;
+    if (!in || !out) return fail("null host buffer");
+    std::lock_guard<std::mutex> lk(s.pipe_mutex);
+    RTB_CUDA(cudaSetDevice(s.device));
+    if (ensure_pipeline(s) != Ok) return Error;
+    cudaStream_t cp = s.copy_stream;
+    // watermark writes: cuStreamWriteValue64 when the driver exports it (fetched at run time: no link-time libcuda
+    // dependency), else an 8-byte H2D copy from a pinned table
+    typedef int (*WriteValue64)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
+    static const WriteValue64 write_value = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (std::getenv("RTBVH_GATE_MEMCPY") != nullptr) return (WriteValue64) nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (WriteValue64) nullptr;
+        }
+        return (WriteValue64)fn;
+    }();
+    static const size_t sub_rays = [] {
+        const char* e = std::getenv("RTBVH_SUBCHUNK_RAYS");
+        const size_t v = e ? (size_t)std::strtoull(e, nullptr, 10) : 0;
+        return v ? v : kSubChunkRays;
+    }();
+    int marks = 0;
+    size_t done = 0;
+    static const bool trace = std::getenv("RTBVH_PIPE_TRACE") != nullptr;  // debug: per-launch timeline on stderr
+    std::vector<cudaEvent_t> ev;
+    std::vector<size_t> ev_m;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+    };
+    mark(cp);
+    for (int c = 0; done < n; c++) {
+        const int k = c % kPipeStreams;
+        const size_t left = n - done;
+        size_t m = std::min(kChunkRays, std::max(kMinChunkRays, ((left / 2 + kMinChunkRays - 1) / kMinChunkRays) * kMinChunkRays));
+        if (m > left || left - m < kMinChunkRays / 2) m = std::min(left, kChunkRays);
+        unsigned long long* ready = s.d_ready + (c % kReadySlots);
+        // slot k is free once the launch that used it has finished (its D2H follows it on streams[k] anyway)
+        if (c >= kPipeStreams) RTB_CUDA(cudaStreamWaitEvent(cp, s.ev_done[k], 0));
+        RTB_CUDA(cudaMemsetAsync(ready, 0, sizeof(unsigned long long), cp));
+        RTB_CUDA(cudaEventRecord(s.ev_start[k], cp));
+        RTB_CUDA(cudaStreamWaitEvent(s.streams[k], s.ev_start[k], 0));
+        mark(s.streams[k]);
+        RTB_CUDA(launch(s.d_in[k], m, s.d_out[k], ready, s.streams[k]));
+        RTB_CUDA(cudaEventRecord(s.ev_done[k], s.streams[k]));
+        mark(s.streams[k]);
+        mark(cp);
+        ev_m.push_back(m);
+        for (size_t off = 0; off < m; off += sub_rays) {
+            const size_t sub = std::min(sub_rays, m - off);
+            RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + off * sizeof(RTRay), in + done + off, sub * sizeof(RTRay),
+                                     cudaMemcpyHostToDevice, cp));
+            if (marks == kMarkSlots) {  // the pinned source values of in-flight watermark copies must stay intact
+                RTB_CUDA(cudaStreamSynchronize(cp));
+                marks = 0;
+            }
+            if (write_value) {  // stream memory operation: no DMA set-up, ordered behind the copy like any stream work
+                if (write_value(cp, (unsigned long long)(uintptr_t)ready, off + sub, 0) != 0) return fail("cuStreamWriteValue64 failed");
+            } else {
+                s.h_marks[marks] = off + sub;
+                RTB_CUDA(cudaMemcpyAsync(ready, &s.h_marks[marks], sizeof(unsigned long long), cudaMemcpyHostToDevice, cp));
+                marks++;
+            }
+        }
+        // enqueued after the uploads: with a pageable `out` this call blocks until the launch has finished
+        mark(cp);
+        RTB_CUDA(cudaMemcpyAsync((char*)out + done * unit_out, s.d_out[k], m * unit_out, cudaMemcpyDeviceToHost, s.streams[k]));
+        mark(s.streams[k]);
+        done += m;
+    }
+    RTB_CUDA(cudaStreamSynchronize(cp));
+    for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s.streams[i]));
+    if (trace) {
+        for (size_t c = 0; 1 + 5 * c + 4 < ev.size(); c++) {
+            float t[5];
+            for (int j = 0; j < 5; j++) cudaEventElapsedTime(&t[j], ev[0], ev[1 + 5 * c + j]);
+            std::fprintf(stderr, "launch %2zu (%7zu rays): h2d %.3f-%.3f  kernel %.3f-%.3f  d2h -%.3f ms\n", c, ev_m[c], t[2], t[3],
+                         t[0], t[1], t[4]);
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+    return check_overflow(s);
 }
 
 ResultCode upload(void** dst, const void* src, size_t bytes) {
@@ -420,6 +653,14 @@ ResultCode rtbvh_gpu_intersect(RTGpuScene h, RTTreeKind tree, const RTRay* rays,
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
+    if (host_mode() == kHostGated && !s->sort_bounds() && persistent_mode() == kTracePersistent)
+        return run_host_batch_gated(*s, rays, n, sizeof(RTHit), hits,
+                                    [&](void* din, size_t m, void* dout, const unsigned long long* ready, cudaStream_t st) {
+                                        PeerDests pd{};
+                                        pd.ready = ready;
+                                        return launch_trace_single(*t, tree, false, (const RTRay*)din, m, (RTHit*)dout, nullptr,
+                                                                   s->counter_slot(), s->d_overflow, kTracePersistent, nullptr, &pd, st);
+                                    });
     return run_host_batch(*s, rays, n, sizeof(RTRay), sizeof(RTHit), 1, hits,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_single(*t, tree, false, (const RTRay*)din, m, (RTHit*)dout, nullptr,
@@ -431,12 +672,58 @@ ResultCode rtbvh_gpu_occluded(RTGpuScene h, RTTreeKind tree, const RTRay* rays, 
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
+    if (host_mode() == kHostGated && !s->sort_bounds() && persistent_mode() == kTracePersistent)
+        return run_host_batch_gated(*s, rays, n, 1, occluded,
+                                    [&](void* din, size_t m, void* dout, const unsigned long long* ready, cudaStream_t st) {
+                                        PeerDests pd{};
+                                        pd.ready = ready;
+                                        return launch_trace_single(*t, tree, true, (const RTRay*)din, m, nullptr, (uint8_t*)dout,
+                                                                   s->counter_slot(), s->d_overflow, kTracePersistent, nullptr, &pd, st);
+                                    });
     return run_host_batch(*s, rays, n, sizeof(RTRay), 1, 1, occluded,
                           [&](void* din, size_t m, void* dout, cudaStream_t st) {
                               return launch_trace_single(*t, tree, true, (const RTRay*)din, m, nullptr, (uint8_t*)dout,
                                                          s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), nullptr, st);
                           });
 }
+// ---- host buffers, asynchronous: submit / wait ------------------------------------------------------------------
+ResultCode rtbvh_gpu_intersect_async(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, RTHit* hits, uint64_t* ticket) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    return submit_host_batch(*s, rays, n, sizeof(RTRay), sizeof(RTHit), 1, hits, ticket,
+                             [&](void* din, size_t m, void* dout, cudaStream_t st) {
+                                 return launch_trace_single(*t, tree, false, (const RTRay*)din, m, (RTHit*)dout, nullptr,
+                                                            s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), nullptr, st);
+                             });
+}
+ResultCode rtbvh_gpu_occluded_async(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, uint8_t* occluded, uint64_t* ticket) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    return submit_host_batch(*s, rays, n, sizeof(RTRay), 1, 1, occluded, ticket,
+                             [&](void* din, size_t m, void* dout, cudaStream_t st) {
+                                 return launch_trace_single(*t, tree, true, (const RTRay*)din, m, nullptr, (uint8_t*)dout,
+                                                            s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), nullptr, st);
+                             });
+}
+ResultCode rtbvh_gpu_wait(RTGpuScene h, uint64_t ticket) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    return wait_ticket(*s, ticket);
+}
+ResultCode rtbvh_gpu_host_alloc(size_t bytes, void** ptr) {
+    if (!ptr) return fail("null argument");
+    RTB_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    return Ok;
+}
+ResultCode rtbvh_gpu_host_free(void* ptr) {
+    RTB_CUDA(cudaFreeHost(ptr));
+    return Ok;
+}
+
 ResultCode rtbvh_gpu_intersect_packets(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* packets, size_t n,
                                        float t_min, RTHitPacket4* hits) {
     auto s = get_scene(h);

@@ -479,6 +479,16 @@ __device__ __forceinline__ void load_ray(const RTRay* __restrict__ rays, size_t 
     r.dx = b.x; r.dy = b.y; r.dz = b.z; r.t = b.w;
     finish_ray_setup(r);
 }
+// Gated launches read rays the copy engine has just written: L2-only loads (each ray is read once anyway).
+__device__ __forceinline__ void load_ray_cg(const RTRay* __restrict__ rays, size_t i, RayRegs& r) {
+    const float4* p = reinterpret_cast<const float4*>(rays) + i * 2;
+    float4 a, b;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p) : "memory");
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 1) : "memory");
+    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.t_min = a.w;
+    r.dx = b.x; r.dy = b.y; r.dz = b.z; r.t = b.w;
+    finish_ray_setup(r);
+}
 // Result store.  With peer destinations (multi-GPU gather fused into the kernel) the record is also written,
 // the moment its ray finishes, into the gather buffer of every peer GPU (P2P stores over NVLink / NVSwitch to
 // cudaIpc-mapped memory): the transfer overlaps the traversal ray by ray and no collective follows the kernel.
@@ -572,6 +582,17 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                     }
                     res_next = base;
                     res_end = base + kRayChunk < n ? base + kRayChunk : n;
+                    if (pd.ready) {  // host-buffer pipeline: wait until the copy engine has delivered this range
+                        if (lane == 0) {
+                            unsigned long long have;
+                            for (;;) {
+                                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(have) : "l"(pd.ready) : "memory");
+                                if (have >= res_end) break;
+                                __nanosleep(500);
+                            }
+                        }
+                        __syncwarp();
+                    }
                 }
                 const unsigned long long avail = res_end - res_next;
                 const unsigned want = __popc(idle);
@@ -580,7 +601,10 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                 if (!active && rank < take) {
                     my = (size_t)(res_next + rank);
                     if (perm) my = (size_t)perm[my];
-                    load_ray(rays, my, r);
+                    if (pd.ready)
+                        load_ray_cg(rays, my, r);
+                    else
+                        load_ray(rays, my, r);
                     st.reset();
                     cur = 0;
                     if (tree.node_count != 0 && !r.nan)
@@ -942,7 +966,7 @@ template <int TREE, bool ANY>
 static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
                                    uint8_t* d_occluded, const uint32_t* d_perm, unsigned long long* d_counter,
                                    uint32_t* d_overflow, int mode, const PeerDests& pd, cudaStream_t stream) {
-    if (pd.count > 0 && mode != kTracePersistent) return cudaErrorNotSupported;  // the fused gather lives in the default kernel
+    if ((pd.count > 0 || pd.ready) && mode != kTracePersistent) return cudaErrorNotSupported;  // fused gather / input gate live in the default kernel
     const size_t blocks_needed = ceil_div(n, kBlock);
     const bool persistent = mode != kTraceStatic;
     if (TREE == RT_TREE_MBVH && mode == kTraceCoop) {
@@ -974,6 +998,7 @@ cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any,
     if (n == 0) return cudaSuccess;
     PeerDests pd{};
     if (peers) pd = *peers;
+    if (pd.ready && (sort_bounds != nullptr || mode != kTracePersistent)) return cudaErrorNotSupported;  // gate: default kernel, caller's order
     uint32_t* d_perm = nullptr;
     void* scratch = nullptr;
     if (sort_bounds != nullptr && n >= 4096 && n < (size_t(1) << 32)) {

@@ -17,6 +17,10 @@ struct PeerDests {
     void* p[8];
     int count;
     size_t offset;
+    // Input gate of the host-buffer pipeline (null: all rays are resident).  *ready = number of rays of this launch
+    // whose H2D copy has completed (written by the copy engine, stream-ordered behind each sub-chunk): a warp that
+    // reserves rays [a, b) waits until *ready >= b, so ONE launch can start while its input is still arriving.
+    const unsigned long long* ready;
 };
 // sort_bounds: null = trace in the caller's order; else {min xyz, max xyz} of the scene: the batch is traced in
 // Morton order of (origin, direction) and results are scattered back (same results, better coherence).

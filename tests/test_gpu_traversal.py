@@ -260,3 +260,79 @@ def test_reference_built_spatial_tree_uploaded_unchanged(A, O, W, fix):
         sc = A.Scene(tris, bvh=gb)
         assert np.array_equal(sc.intersect(rays, A.TREE_BVH), bf)
         sc.free()
+
+
+def test_async_submit_wait(A, O, W, teapot, teapot_trees):
+    """rtbvh_gpu_intersect_async / rtbvh_gpu_occluded_async / rtbvh_gpu_wait: several batches in flight through the
+    shared staging pipeline, pinned and pageable buffers, waits in and out of order — every batch equals the oracle."""
+    import torch
+    tris = teapot["tris"]
+    bvh, m = teapot_trees["sah"]
+    sc = _scene(A, tris, bvh, m)
+    try:
+        batches, want, want_occ = [], [], []
+        for k, n in enumerate((300_001, 70_000, 1, 524_288)):
+            rays = W.random_rays(n, *W.bounds(tris), seed=0xA51C + k)
+            batches.append(rays)
+            want.append(O.trace(m, tris, rays)[0])
+            want_occ.append(O.trace(m, tris, rays, mode="any")[0])
+        h_rays = [torch.from_numpy(r.view(np.float32).reshape(-1).copy()).pin_memory() for r in batches]
+        h_hits = [torch.zeros(len(r) * 2, dtype=torch.float32).pin_memory() for r in batches]
+        h_occ = [torch.zeros(len(r), dtype=torch.uint8).pin_memory() for r in batches]
+        tickets = [sc.intersect_async(h_rays[k].data_ptr(), len(batches[k]), h_hits[k].data_ptr(), A.TREE_MBVH)
+                   for k in range(len(batches))]
+        tickets_o = [sc.occluded_async(h_rays[k].data_ptr(), len(batches[k]), h_occ[k].data_ptr(), A.TREE_MBVH)
+                     for k in range(len(batches))]
+        assert tickets == sorted(tickets) and len(set(tickets + tickets_o)) == 2 * len(batches)
+        for k in (2, 0, 3, 1):  # batches complete in submission order; waiting out of order is allowed
+            sc.wait(tickets[k])
+            got = h_hits[k].numpy().view(A.HIT_DTYPE).reshape(-1)
+            assert np.array_equal(got, want[k]), f"async batch {k} differs from the oracle"
+        sc.wait(0)
+        for k in range(len(batches)):
+            assert np.array_equal(h_occ[k].numpy(), want_occ[k]), f"async any-hit batch {k} differs"
+        sc.wait(tickets[0])  # waiting twice is fine
+        with pytest.raises(A.RtbvhError):
+            sc.wait(10_000)  # never issued
+        # pageable buffers: submit blocks inside the copies, results are the same
+        out = np.zeros(len(batches[1]), dtype=A.HIT_DTYPE)
+        t = sc.intersect_async(batches[1].ctypes.data, len(batches[1]), out.ctypes.data, A.TREE_MBVH)
+        sc.wait(t)
+        assert np.array_equal(out, want[1])
+        # more submissions than ticket slots without a single wait
+        small = W.random_rays(1000, *W.bounds(tris), seed=7)
+        hs = torch.from_numpy(small.view(np.float32).reshape(-1).copy()).pin_memory()
+        outs = [torch.zeros(2000, dtype=torch.float32).pin_memory() for _ in range(100)]
+        last = [sc.intersect_async(hs.data_ptr(), 1000, o.data_ptr(), A.TREE_MBVH) for o in outs]
+        sc.wait(last[0])  # recycled slot: already complete
+        sc.wait(0)
+        w_small = O.trace(m, tris, small)[0]
+        assert all(np.array_equal(o.numpy().view(A.HIT_DTYPE).reshape(-1), w_small) for o in outs)
+    finally:
+        sc.free()
+
+
+def test_gated_host_pipeline_in_a_subprocess(A):
+    """RTBVH_HOST_MODE=gated (launches that start before their input has arrived; read at library load, hence the
+    subprocess): the host-buffer calls return the same records as the device-resident launch."""
+    import subprocess
+    import sys
+    import os
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, '.')\n"
+        "from rtbvh_b200 import api, workloads as W\n"
+        "from oracle import oracle as O\n"
+        "tris = W.soup(50_000)\n"
+        "aabbs, centers = O.prims_from_triangles(tris)\n"
+        "rc, bvh = O.build(O.BINNED_SAH, aabbs, centers, 1); m = bvh.collapse()\n"
+        "sc = api.Scene(tris, bvh=None, mbvh=api.Mbvh.from_arrays(m.nodes, m.indices))\n"
+        "for n in (1, 100_000, 700_001):\n"
+        "    rays = W.random_rays(n, *W.bounds(tris), seed=n)\n"
+        "    want = O.trace(m, tris, rays, threads=8)[0]\n"
+        "    assert np.array_equal(sc.intersect(rays, api.TREE_MBVH), want), n\n"
+        "    assert np.array_equal(sc.occluded(rays, api.TREE_MBVH), O.trace(m, tris, rays, mode='any', threads=8)[0]), n\n"
+        "print('gated ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RTBVH_HOST_MODE="gated")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "gated ok" in r.stdout, r.stdout + r.stderr
