@@ -80,6 +80,19 @@ const char *rtbvh_gpu_last_error(void);           /* message of the last Error o
 ResultCode rtbvh_gpu_scene_create(const RTBvh *bvh, const RTMbvh *mbvh, const float *vertices, size_t vertex_stride,
                                   size_t triangle_count, RTGpuScene *scene);
 ResultCode rtbvh_gpu_scene_free(RTGpuScene scene);
+/* Dynamic scenes (the step after build for animated geometry; Bvh::refit src/bvh.rs:176-205, FFI refit
+ * rtbvh_ffi/src/lib.rs:519-538).  New vertex positions for the SAME triangles (same count and order): recomputes the
+ * per-triangle boxes (Triangle::aabb, un-padded), refits the scene's Bvh in place (leaf = union of its primitives'
+ * boxes, inner = union of its two children, each padded by 1e-4; topology fields kept), refreshes the slot boxes of the
+ * scene's Mbvh from the refitted binary nodes — the result equals Mbvh::construct of the refitted Bvh byte for byte
+ * (the reference never refreshes m_nodes) — and re-gathers the triangle records.  Nothing leaves the device; the host
+ * mirrors behind RTBvh / RTMbvh are not touched (rtbvh_gpu_scene_read_nodes reads the device copy).  The scene must hold
+ * the Bvh; an Mbvh in it must be the collapse of that Bvh.  The _device flavour takes device vertices and only
+ * enqueues work on `stream`: traversal calls enqueued behind it on that stream see the refitted trees. */
+ResultCode rtbvh_gpu_scene_refit(RTGpuScene scene, const float *vertices, size_t vertex_stride, size_t triangle_count);
+ResultCode rtbvh_gpu_scene_refit_device(RTGpuScene scene, const float *d_vertices, size_t vertex_stride,
+                                        size_t triangle_count, void *stream);
+ResultCode rtbvh_gpu_scene_read_nodes(RTGpuScene scene, RTTreeKind tree, void *out, size_t bytes);
 /* Incoherent batches (shadow / bounce rays): enable = 1 makes the single-ray calls trace every batch in Morton
  * order of (origin, direction) and scatter the results back.  Results are unchanged, bit for bit; only the
  * order in which the device works through the batch changes.  Default 0 (camera rays are coherent already). */

@@ -50,7 +50,7 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_peer_buffer_open", "rtbvh_gpu_peer_buffer_close", "rtbvh_gpu_peer_buffer_free",
                "rtbvh_gpu_intersect_device_scatter", "rtbvh_gpu_occluded_device_scatter", "rtbvh_gpu_peer_barrier",
                "rtbvh_gpu_intersect_async", "rtbvh_gpu_occluded_async", "rtbvh_gpu_wait", "rtbvh_gpu_host_alloc",
-               "rtbvh_gpu_host_free")
+               "rtbvh_gpu_host_free", "rtbvh_gpu_scene_refit", "rtbvh_gpu_scene_refit_device", "rtbvh_gpu_scene_read_nodes")
 
 
 class RTBvh(C.Structure):  # rtbvh_ffi/src/lib.rs:210-220
@@ -156,6 +156,12 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_host_alloc.argtypes = [sz, C.POINTER(vp)]
     L.rtbvh_gpu_host_free.restype = rc
     L.rtbvh_gpu_host_free.argtypes = [vp]
+    L.rtbvh_gpu_scene_refit.restype = rc
+    L.rtbvh_gpu_scene_refit.argtypes = [u64, vp, sz, sz]
+    L.rtbvh_gpu_scene_refit_device.restype = rc
+    L.rtbvh_gpu_scene_refit_device.argtypes = [u64, vp, sz, sz, vp]
+    L.rtbvh_gpu_scene_read_nodes.restype = rc
+    L.rtbvh_gpu_scene_read_nodes.argtypes = [u64, C.c_int, vp, sz]
     L.rtbvh_gpu_peer_barrier.restype = rc
     L.rtbvh_gpu_peer_barrier.argtypes = [C.POINTER(vp), C.c_int, C.c_int, u64, vp]
     L.rtbvh_gpu_intersect_device_scatter.restype = rc
@@ -349,6 +355,8 @@ class Scene:
         v = v.reshape(-1, stride // 4)
         assert v.shape[0] % 3 == 0
         self.handle = C.c_uint64(0)
+        self.n_nodes = int(bvh.rt.node_count) if bvh else 0
+        self.n_mnodes = int(mbvh.rt.node_count) if mbvh else 0
         _check(lib().rtbvh_gpu_scene_create(C.byref(bvh.rt) if bvh else None, C.byref(mbvh.rt) if mbvh else None,
                                             _p(v), stride, v.shape[0] // 3, C.byref(self.handle)))
 
@@ -389,6 +397,24 @@ class Scene:
     # ---- raw host pointers (pinned torch tensors etc.) ----------------------------------------
     def intersect_ptr(self, rays_ptr: int, n: int, hits_ptr: int, tree: int = TREE_MBVH):
         _check(lib().rtbvh_gpu_intersect(self.handle, tree, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr)))
+
+    # ---- dynamic scenes: refit in place from new vertex positions --------------------------------
+    def refit(self, verts: np.ndarray):
+        """rtbvh_gpu_scene_refit: verts float32 [n, 3, 3] (or [n, 3, 4]) of the same triangles, moved."""
+        v = np.ascontiguousarray(verts, dtype=np.float32)
+        stride = 16 if v.shape[-1] == 4 else 12
+        v = v.reshape(-1, stride // 4)
+        _check(lib().rtbvh_gpu_scene_refit(self.handle, v.ctypes.data_as(C.c_void_p), stride, v.shape[0] // 3))
+
+    def refit_device(self, d_verts, n_tris: int, vertex_stride: int = 12, stream: int = 0):
+        _check(lib().rtbvh_gpu_scene_refit_device(self.handle, _dev_ptr(d_verts), vertex_stride, n_tris, C.c_void_p(stream)))
+
+    def read_nodes(self, tree: int) -> np.ndarray:
+        """The device copy of the scene's nodes (after refits it differs from the host mirror)."""
+        dt, n = (MNODE_DTYPE, self.n_mnodes) if tree == TREE_MBVH else (NODE_DTYPE, self.n_nodes)
+        out = np.zeros(n, dtype=dt)
+        _check(lib().rtbvh_gpu_scene_read_nodes(self.handle, tree, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
 
     # ---- asynchronous host-buffer calls: submit -> ticket, wait(ticket) ------------------------
     def intersect_async(self, rays_ptr: int, n: int, hits_ptr: int, tree: int = TREE_MBVH) -> int:

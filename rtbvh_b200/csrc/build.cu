@@ -54,6 +54,15 @@ constexpr int kTaskBinWords = 3 * kBins * kBinWords;  // 336 words = 1344 B per 
 constexpr float kPad = 0.0001f;
 constexpr int kRadius = 14;          // locb.rs:27
 constexpr uint32_t kSmall = 32;      // subtrees with <= kSmall primitives are finished by one warp (sah_small_kernel)
+// Level tasks with <= kWarpTask primitives are binned AND split by one warp each (sah_warp_task_kernel: bins in shared
+// memory, no global atomics); larger tasks go through the span-based bin kernel + sah_split_kernel.  In pos_task a
+// warp-class task t is stored as -2 - t (the span kernel skips negative entries), -1 = position no longer active.
+#ifndef RTB_WARP_TASK
+#define RTB_WARP_TASK 512
+#endif
+constexpr uint32_t kWarpTask = RTB_WARP_TASK;
+__host__ __device__ inline int32_t pt_encode(uint32_t t, uint32_t n) { return n <= kWarpTask ? -2 - (int32_t)t : (int32_t)t; }
+__device__ __forceinline__ int32_t pt_task(int32_t pt) { return pt >= 0 ? pt : -2 - pt; }  // -1 -> -1
 
 // ---- order-preserving float <-> uint keys (so min/max can be integer atomics) --------------------
 __host__ __device__ inline uint32_t fkey(float f) {
@@ -144,6 +153,21 @@ __global__ void tri_prims_kernel(const float* __restrict__ verts, uint32_t strid
     cen[(size_t)i * 3] = c[0];
     cen[(size_t)i * 3 + 1] = c[1];
     cen[(size_t)i * 3 + 2] = c[2];
+}
+
+__global__ void tri_boxes_kernel(const float* __restrict__ verts, uint32_t stride, uint32_t n, float4* __restrict__ bb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* v = verts + (size_t)i * 3 * stride;
+    float mn[3], mx[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float a = v[k], b = v[stride + k], d = v[2 * stride + k];
+        mn[k] = fminf(fminf(fminf(1e34f, a), b), d);
+        mx[k] = fmaxf(fmaxf(fmaxf(-1e34f, a), b), d);
+    }
+    bb[(size_t)i * 2] = make_float4(mn[0], mn[1], mn[2], 0.f);
+    bb[(size_t)i * 2 + 1] = make_float4(mx[0], mx[1], mx[2], 0.f);
 }
 
 // Aabb::union_of_list without the pad (aabb.rs:125-129): block reduce + 6 key atomics
@@ -286,6 +310,7 @@ __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __re
     for (uint32_t c0 = begin; c0 < end; c0 += kBinBlock) {
         const uint32_t c1 = min(c0 + kBinBlock, end);
         const int32_t ta = pos_task[c0], tb = pos_task[c1 - 1];
+        if (ta == tb && ta < -1) continue;  // the whole chunk belongs to one warp-class task (block-uniform decision)
         const int uni = (ta == tb && ta >= 0) ? ta : -1;  // ranges are contiguous: equal ends => one task
         if (uni != cur) {
             if (cur >= 0) {
@@ -351,14 +376,9 @@ __device__ __forceinline__ Box warp_union(Box b) {
 
 // One warp per task: find_split on the three axes, axis choice, leaf / fallback rules, child boxes
 // (binned_sah.rs:80-114, :174-247).  Lane b < 16 owns bin b.
-__global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__ tasks, uint32_t A,
-                                                        const uint32_t* __restrict__ bins, const float4* __restrict__ nodes,
-                                                        uint32_t max_leaf, uint32_t depth, Decision* __restrict__ dec,
-                                                        uint4* __restrict__ counts) {
-    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (t >= A) return;
-    const Task task = tasks[t];
+__device__ __forceinline__ void sah_split_task(const Task task, uint32_t t, int lane, const uint32_t* taskbins,
+                                               const float4* __restrict__ nodes, uint32_t max_leaf, uint32_t depth,
+                                               Decision* __restrict__ dec, uint4* __restrict__ counts) {
     const uint32_t n = task.end - task.begin;
     Box bin[3];
     uint32_t cnt[3];
@@ -369,7 +389,7 @@ __global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__
         bin[ax] = box_empty();
         cnt[ax] = 0;
         if (lane < kBins) {
-            const uint32_t* g = bins + (size_t)t * kTaskBinWords + (ax * kBins + lane) * kBinWords;
+            const uint32_t* g = taskbins + (ax * kBins + lane) * kBinWords;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 bin[ax].mn[k] = fkey_inv(g[k]);
@@ -489,6 +509,54 @@ __global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__
         counts[t] = c;
     }
 }
+__global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__ tasks, uint32_t A,
+                                                        const uint32_t* __restrict__ bins, const float4* __restrict__ nodes,
+                                                        uint32_t max_leaf, uint32_t depth, Decision* __restrict__ dec,
+                                                        uint4* __restrict__ counts) {
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= A) return;
+    const Task task = tasks[t];
+    if (task.end - task.begin <= kWarpTask) return;  // sah_warp_task_kernel's
+    sah_split_task(task, t, lane, bins + (size_t)t * kTaskBinWords, nodes, max_leaf, depth, dec, counts);
+}
+
+// Warp-class tasks (<= kWarpTask primitives): one warp fills the 3 x 16 bins of its task in shared memory (no global
+// atomics, no bins in HBM) and evaluates the split right away.  On the deep levels of the level loop every task is of
+// this class: the pass then reads each primitive once (index, box, centroid) and writes one Decision per task.
+constexpr int kWarpTaskWarps = 4;
+__global__ void __launch_bounds__(kWarpTaskWarps * 32) sah_warp_task_kernel(const Task* __restrict__ tasks, uint32_t A,
+                                                                            const uint32_t* __restrict__ idx,
+                                                                            const TaskAux* __restrict__ aux,
+                                                                            const float4* __restrict__ bb,
+                                                                            const float* __restrict__ cen, uint32_t cstride,
+                                                                            const float4* __restrict__ nodes, uint32_t max_leaf,
+                                                                            uint32_t depth, Decision* __restrict__ dec,
+                                                                            uint4* __restrict__ counts) {
+    __shared__ uint32_t sb[kWarpTaskWarps][kTaskBinWords];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * kWarpTaskWarps + w;
+    if (t >= A) return;
+    const Task task = tasks[t];
+    if (task.end - task.begin > kWarpTask) return;
+    for (int k = lane; k < kTaskBinWords; k += 32) {
+        const int f = k % kBinWords;
+        sb[w][k] = f < 3 ? fkey(1e34f) : (f < 6 ? fkey(-1e34f) : 0u);
+    }
+    __syncwarp();
+    const TaskAux a = aux[t];
+    for (uint32_t i = task.begin + lane; i < task.end; i += 32) {
+        const uint32_t p = idx[i];
+        const Box box = load_box(bb, p);
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+            const int b = bin_index(cen[(size_t)p * cstride + ax], a.k[ax], a.off[ax]);
+            bin_accumulate(&sb[w][(ax * kBins + b) * kBinWords], box);
+        }
+    }
+    __syncwarp();
+    sah_split_task(task, t, lane, sb[w], nodes, max_leaf, depth, dec, counts);
+}
 
 // make_leaf (binned_sah.rs:134-138): second pad, left_first = begin, count = n
 __device__ __forceinline__ void make_leaf(float4* nodes, uint32_t node, Box b, uint32_t begin, uint32_t n) {
@@ -548,7 +616,7 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A, cons
         } else {
             store_node(nodes, left + k, cb[k], 0, 0);
             next_tasks[next] = Task{left + k, cbeg[k], cend[k]};
-            child_task[2 * t + k] = (int32_t)next++;
+            child_task[2 * t + k] = pt_encode(next++, nc);
         }
     }
 }
@@ -795,7 +863,7 @@ __global__ void sah_flag_kernel(const uint32_t* __restrict__ idx, const int32_t*
                                 const float* __restrict__ cen, uint32_t cstride, uint32_t* __restrict__ flag) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int32_t t = pos_task[i];
+    const int32_t t = pt_task(pos_task[i]);
     uint32_t f = 0;
     if (t >= 0) {
         const Decision& d = dec[t];
@@ -814,7 +882,7 @@ __global__ void sah_scatter_kernel(const uint32_t* __restrict__ idx, const int32
                                    int32_t* __restrict__ pos_task_out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int32_t t = pos_task[i];
+    const int32_t t = pt_task(pos_task[i]);
     if (t < 0 || !dec[t].split) {
         idx_out[i] = idx[i];
         pos_task_out[i] = -1;
@@ -1211,7 +1279,7 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         RTB_CUDA(ensure_tasks(1024));
         const Task root{0, 0, n};
         RTB_CUDA(cudaMemcpy(tasksA.p, &root, sizeof(Task), cudaMemcpyHostToDevice));
-        RTB_CUDA(cudaMemsetAsync(ptA.p, 0, (size_t)n * 4, 0));  // every position belongs to task 0
+        fill_i32_kernel<<<blocks(n, 256), 256>>>(ptA.as<int32_t>(), n, pt_encode(0, n));  // every position belongs to task 0
         A = 1;
     }
     uint32_t* idx_cur = idxA.as<uint32_t>();
@@ -1236,6 +1304,9 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
                                                 bins.as<uint32_t>());
         sah_split_kernel<<<blocks((size_t)A * 32, 128), 128>>>(t_cur, A, bins.as<uint32_t>(), nodes, max_leaf, depth,
                                                                dec.as<Decision>(), counts.as<uint4>());
+        sah_warp_task_kernel<<<blocks(A, kWarpTaskWarps), kWarpTaskWarps * 32>>>(t_cur, A, idx_cur, aux.as<TaskAux>(), d_bb, d_cen,
+                                                                                 cstride, nodes, max_leaf, depth,
+                                                                                 dec.as<Decision>(), counts.as<uint4>());
         size_t tbytes = temp.bytes;
         RTB_CUDA(cub::DeviceScan::ExclusiveScan(temp.p, tbytes, counts.as<uint4>(), ranks4.as<uint4>(), Uint4Add(),
                                                 make_uint4(0, 0, 0, 0), (int)A));
@@ -1574,6 +1645,70 @@ ResultCode gpu_refit(HostBvh* bvh, const RTAabb* aabbs) {
     g_build_stats.device_ms = dev.stop();
     RTB_CUDA(cudaMemcpy(bvh->nodes.data(), nodes.p, (size_t)n_nodes * 32, cudaMemcpyDeviceToHost));
     g_build_stats.total_ms = total.stop();
+    return Ok;
+}
+
+// ---- dynamic scenes: refit of device-resident trees ---------------------------------------------
+ResidentRefit::~ResidentRefit() {
+    cudaFree(parent);
+    cudaFree(arrived);
+    cudaFree(is_mroot);
+    cudaFree(mindex);
+    cudaFree(bb);
+}
+
+// One-off analysis of the topology (it does not change under refit): parent links and, if the scene holds the
+// 4-wide collapse of this tree, which binary nodes are 4-wide roots and where their MbvhNode lives.
+static ResultCode resident_refit_prepare(ResidentRefit* c, const float4* d_nodes, uint32_t n_nodes, uint32_t n_prims,
+                                         uint32_t m_count, bool want_mbvh, cudaStream_t st) {
+    if (c->n_nodes == n_nodes && c->parent && (!want_mbvh || c->is_mroot)) return Ok;
+    RTB_CUDA(cudaMalloc(&c->parent, (size_t)n_nodes * 4));
+    RTB_CUDA(cudaMalloc(&c->arrived, (size_t)n_nodes * 4));
+    RTB_CUDA(cudaMalloc(&c->bb, (size_t)(n_prims ? n_prims : 1) * 32));
+    c->n_nodes = n_nodes;
+    RTB_CUDA(cudaMemsetAsync(c->parent, 0xFF, (size_t)n_nodes * 4, st));
+    parents_kernel<<<blocks(n_nodes, 256), 256, 0, st>>>(d_nodes, n_nodes, c->parent);
+    if (want_mbvh) {
+        uint32_t* sub = nullptr;
+        RTB_CUDA(cudaMalloc(&c->is_mroot, n_nodes));
+        RTB_CUDA(cudaMalloc(&c->mindex, (size_t)n_nodes * 4));
+        RTB_CUDA(cudaMalloc(&sub, (size_t)n_nodes * 4));
+        RTB_CUDA(cudaMemsetAsync(sub, 0, (size_t)n_nodes * 4, st));
+        RTB_CUDA(cudaMemsetAsync(c->arrived, 0, (size_t)n_nodes * 4, st));
+        mroot_flag_kernel<<<blocks(n_nodes, 256), 256, 0, st>>>(d_nodes, n_nodes, c->parent, c->is_mroot);
+        mroot_sub_kernel<<<blocks(n_nodes, 256), 256, 0, st>>>(d_nodes, n_nodes, c->parent, c->is_mroot, sub, c->arrived);
+        mroot_index_kernel<<<blocks(n_nodes, 256), 256, 0, st>>>(d_nodes, n_nodes, c->parent, c->is_mroot, sub, c->mindex);
+        uint32_t total = 0;
+        RTB_CUDA(cudaMemcpyAsync(&total, sub, 4, cudaMemcpyDeviceToHost, st));
+        RTB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(sub);
+        if (total != m_count) return fail("scene refit: the scene's Mbvh is not the 4-wide collapse of its Bvh");
+    }
+    RTB_CUDA(cudaGetLastError());
+    return Ok;
+}
+
+ResultCode gpu_refit_resident(ResidentRefit* c, float4* d_nodes, uint32_t n_nodes, const uint32_t* d_indices, uint32_t n_prims,
+                              const float* d_vertices, uint32_t vstride, uint32_t tri_count, float4* d_mnodes, uint32_t m_count,
+                              cudaStream_t st) {
+    if (n_nodes == 0) return Ok;
+    float4 root[2];
+    RTB_CUDA(cudaMemcpyAsync(root, d_nodes, 32, cudaMemcpyDeviceToHost, st));
+    RTB_CUDA(cudaStreamSynchronize(st));
+    int rc, rl;
+    memcpy(&rc, &root[0].w, 4);
+    memcpy(&rl, &root[1].w, 4);
+    const bool root_is_leaf = rc >= 0 || rl < 0;
+    const bool want_mbvh = d_mnodes != nullptr && !root_is_leaf;
+    if (d_mnodes != nullptr && root_is_leaf) return fail("scene refit: single-leaf trees have no 4-wide structure to refresh; recreate the scene");
+    if (resident_refit_prepare(c, d_nodes, n_nodes, tri_count, m_count, want_mbvh, st) != Ok) return Error;
+    // Primitive::aabb of the bench Triangle (un-padded), then Bvh::refit bottom-up, then merge_nodes' box rules again
+    tri_boxes_kernel<<<blocks(tri_count, 256), 256, 0, st>>>(d_vertices, vstride, tri_count, c->bb);
+    RTB_CUDA(cudaMemsetAsync(c->arrived, 0, (size_t)n_nodes * 4, st));
+    refit_kernel<<<blocks(n_nodes, 256), 256, 0, st>>>(d_nodes, n_nodes, c->parent, d_indices, c->bb, c->arrived);
+    if (want_mbvh)
+        collapse_emit_kernel<<<blocks(n_nodes, 256), 256, 0, st>>>(d_nodes, n_nodes, c->is_mroot, c->mindex, d_mnodes);
+    RTB_CUDA(cudaGetLastError());
     return Ok;
 }
 

@@ -41,4 +41,20 @@ ResultCode gpu_collapse(const HostBvh& bvh, HostMbvh* out);
 // Bvh::refit (src/bvh.rs:176-205) on the GPU.
 ResultCode gpu_refit(HostBvh* bvh, const RTAabb* aabbs);
 
+// Dynamic scenes: refit of a device-resident Bvh (+ refresh of its Mbvh) from new vertex positions,
+// everything on `stream`.  The cache holds what does not change under refit (parent links, the binary node behind every
+// MbvhNode) plus scratch; it belongs to one tree pair.
+struct ResidentRefit {
+    uint32_t n_nodes = 0;
+    int32_t* parent = nullptr;
+    uint32_t* arrived = nullptr;
+    uint8_t* is_mroot = nullptr;
+    uint32_t* mindex = nullptr;
+    float4* bb = nullptr;
+    ~ResidentRefit();
+};
+ResultCode gpu_refit_resident(ResidentRefit* cache, float4* d_nodes, uint32_t n_nodes, const uint32_t* d_indices, uint32_t n_prims,
+                              const float* d_vertices, uint32_t vstride, uint32_t tri_count, float4* d_mnodes, uint32_t m_count,
+                              cudaStream_t stream);
+
 }  // namespace rtb

@@ -72,6 +72,13 @@ struct Scene {
     void* d_mbvh_nodes = nullptr;
     TriRec* d_tris_bvh = nullptr;   // leaf order of the Bvh's indices
     TriRec* d_tris_mbvh = nullptr;  // leaf order of the Mbvh's indices (may alias d_tris_bvh)
+    uint32_t* d_idx_bvh = nullptr;   // prim_indices of the trees (kept for refit: re-gathering the triangle records)
+    uint32_t* d_idx_mbvh = nullptr;  // may alias d_idx_bvh
+    uint32_t tri_count = 0;
+    ResidentRefit refit_cache;       // topology analysis + scratch of rtbvh_gpu_scene_refit*
+    float* d_refit_verts = nullptr;  // staging of the host-buffer refit call
+    size_t refit_verts_bytes = 0;
+    std::mutex refit_mutex;
     uint32_t* d_overflow = nullptr;
     float bounds[6] = {0, 0, 0, 1, 1, 1};  // root box (keys of the optional ray sort)
     std::atomic<int> sort_rays{0};
@@ -118,6 +125,9 @@ struct Scene {
         cudaFree(d_mbvh_nodes);
         if (d_tris_mbvh != d_tris_bvh) cudaFree(d_tris_mbvh);
         cudaFree(d_tris_bvh);
+        if (d_idx_mbvh != d_idx_bvh) cudaFree(d_idx_mbvh);
+        cudaFree(d_idx_bvh);
+        cudaFree(d_refit_verts);
         cudaFree(d_overflow);
         cudaFree(d_counters);
     }
@@ -438,20 +448,21 @@ ResultCode rtbvh_gpu_scene_create(const RTBvh* bvh, const RTMbvh* mbvh, const fl
     float* d_verts = nullptr;
     const size_t vbytes = triangle_count * 3 * vertex_stride;
     if (upload((void**)&d_verts, vertices, vbytes) != Ok) return Error;
-    auto gather = [&](const uint32_t* indices, uint32_t index_count, TriRec** out) -> ResultCode {
+    s->tri_count = (uint32_t)triangle_count;
+    auto gather = [&](const uint32_t* indices, uint32_t index_count, TriRec** out, uint32_t** d_idx_out) -> ResultCode {
         uint32_t* d_idx = nullptr;
         if (upload((void**)&d_idx, indices, (size_t)index_count * 4) != Ok) return Error;
+        *d_idx_out = d_idx;
         RTB_CUDA(cudaMalloc((void**)out, (size_t)(index_count ? index_count : 1) * sizeof(TriRec)));
         RTB_CUDA(launch_gather_tris(d_verts, (uint32_t)(vertex_stride / 4), d_idx, index_count, (uint32_t)triangle_count,
                                     *out, 0));
         RTB_CUDA(cudaDeviceSynchronize());
-        cudaFree(d_idx);
         return Ok;
     };
     ResultCode rc = Ok;
     if (bvh) {
         rc = upload(&s->d_bvh_nodes, bvh->nodes, (size_t)bvh->node_count * sizeof(RTBvhNode));
-        if (rc == Ok) rc = gather(bvh->indices, bvh->index_count, &s->d_tris_bvh);
+        if (rc == Ok) rc = gather(bvh->indices, bvh->index_count, &s->d_tris_bvh, &s->d_idx_bvh);
         s->bvh = DeviceTree{(const float4*)s->d_bvh_nodes, bvh->node_count, s->d_tris_bvh, bvh->index_count};
     }
     if (rc == Ok && mbvh) {
@@ -460,10 +471,12 @@ ResultCode rtbvh_gpu_scene_create(const RTBvh* bvh, const RTMbvh* mbvh, const fl
                           (bvh->indices == mbvh->indices ||
                            std::memcmp(bvh->indices, mbvh->indices, (size_t)bvh->index_count * 4) == 0);
         if (rc == Ok) {
-            if (same)
+            if (same) {
                 s->d_tris_mbvh = s->d_tris_bvh;  // Mbvh keeps a clone of the Bvh's prim_indices (src/bvh.rs:399-403)
-            else
-                rc = gather(mbvh->indices, mbvh->index_count, &s->d_tris_mbvh);
+                s->d_idx_mbvh = s->d_idx_bvh;
+            } else {
+                rc = gather(mbvh->indices, mbvh->index_count, &s->d_tris_mbvh, &s->d_idx_mbvh);
+            }
         }
         s->mbvh = DeviceTree{(const float4*)s->d_mbvh_nodes, mbvh->node_count, s->d_tris_mbvh, mbvh->index_count};
     }
@@ -487,6 +500,62 @@ ResultCode rtbvh_gpu_scene_create(const RTBvh* bvh, const RTMbvh* mbvh, const fl
     std::unique_lock<std::shared_mutex> lk(g_scenes.mu);
     g_scenes.scenes.push_back(s);
     *scene = (RTGpuScene)g_scenes.scenes.size();
+    return Ok;
+}
+
+// ---- dynamic scenes ------------------------------------------------------------------------------
+static ResultCode scene_refit_on(Scene& s, const float* d_vertices, size_t vertex_stride, size_t triangle_count, cudaStream_t st) {
+    if (vertex_stride != 12 && vertex_stride != 16) return fail("vertex_stride must be 12 or 16 bytes");
+    if (triangle_count != s.tri_count) return fail("scene refit: the triangle count must not change (rebuild instead)");
+    if (!s.d_bvh_nodes) return fail("scene refit needs the binary Bvh in the scene (an Mbvh alone has no refit in the reference either)");
+    if (s.d_mbvh_nodes && s.d_idx_mbvh != s.d_idx_bvh) return fail("scene refit: the scene's Mbvh is not the 4-wide collapse of its Bvh");
+    const uint32_t vs = (uint32_t)(vertex_stride / 4);
+    if (gpu_refit_resident(&s.refit_cache, (float4*)s.d_bvh_nodes, (uint32_t)s.bvh.node_count, s.d_idx_bvh, (uint32_t)s.bvh.index_count,
+                           d_vertices, vs, s.tri_count, (float4*)s.d_mbvh_nodes, (uint32_t)s.mbvh.node_count, st) != Ok)
+        return Error;
+    RTB_CUDA(launch_gather_tris(d_vertices, vs, s.d_idx_bvh, (uint32_t)s.bvh.index_count, s.tri_count, s.d_tris_bvh, st));
+    return Ok;
+}
+ResultCode rtbvh_gpu_scene_refit_device(RTGpuScene h, const float* d_vertices, size_t vertex_stride, size_t triangle_count,
+                                        void* stream) {
+    auto s = get_scene(h);
+    if (!s || !d_vertices) return fail("unknown scene / null vertices");
+    std::lock_guard<std::mutex> lk(s->refit_mutex);
+    RTB_CUDA(cudaSetDevice(s->device));
+    return scene_refit_on(*s, d_vertices, vertex_stride, triangle_count, (cudaStream_t)stream);
+}
+ResultCode rtbvh_gpu_scene_refit(RTGpuScene h, const float* vertices, size_t vertex_stride, size_t triangle_count) {
+    auto s = get_scene(h);
+    if (!s || !vertices) return fail("unknown scene / null vertices");
+    std::lock_guard<std::mutex> lk(s->refit_mutex);
+    RTB_CUDA(cudaSetDevice(s->device));
+    const size_t bytes = triangle_count * 3 * vertex_stride;
+    if (bytes > s->refit_verts_bytes) {
+        cudaFree(s->d_refit_verts);
+        s->d_refit_verts = nullptr;
+        s->refit_verts_bytes = 0;
+        RTB_CUDA(cudaMalloc(&s->d_refit_verts, bytes ? bytes : 16));
+        s->refit_verts_bytes = bytes;
+    }
+    RTB_CUDA(cudaMemcpy(s->d_refit_verts, vertices, bytes, cudaMemcpyHostToDevice));
+    if (scene_refit_on(*s, s->d_refit_verts, vertex_stride, triangle_count, 0) != Ok) return Error;
+    RTB_CUDA(cudaDeviceSynchronize());
+    float4 root[2];  // the keys of the optional ray sort follow the new root box
+    RTB_CUDA(cudaMemcpy(root, s->d_bvh_nodes, 32, cudaMemcpyDeviceToHost));
+    s->bounds[0] = root[0].x; s->bounds[1] = root[0].y; s->bounds[2] = root[0].z;
+    s->bounds[3] = root[1].x; s->bounds[4] = root[1].y; s->bounds[5] = root[1].z;
+    return Ok;
+}
+ResultCode rtbvh_gpu_scene_read_nodes(RTGpuScene h, RTTreeKind tree, void* out, size_t bytes) {
+    auto s = get_scene(h);
+    if (!s || !out) return fail("unknown scene / null buffer");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    const size_t have = (size_t)t->node_count * (tree == RT_TREE_MBVH ? sizeof(RTMbvhNode) : sizeof(RTBvhNode));
+    if (bytes != have) return fail("rtbvh_gpu_scene_read_nodes: buffer size must be node_count * sizeof(node)");
+    RTB_CUDA(cudaSetDevice(s->device));
+    RTB_CUDA(cudaDeviceSynchronize());
+    RTB_CUDA(cudaMemcpy(out, t->nodes, bytes, cudaMemcpyDeviceToHost));
     return Ok;
 }
 
