@@ -237,14 +237,18 @@ struct Decision {
     float lmn[3], lmx[3], rmn[3], rmx[3];
 };
 
-// Entry of BinnedSahBuildTask::run for every task of the level (binned_sah.rs:133-147): pad the node
-// box, compute the binning transform.  Every task here has >= 2 primitives and depth < 64 (children
-// that are leaves on entry are finalised by emit_kernel).
-__global__ void sah_prepare_kernel(const Task* __restrict__ tasks, uint32_t A, float4* nodes, TaskAux* __restrict__ aux) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= A) return;
-    const uint32_t node = tasks[t].node;
-    Box b = load_box(nodes, node);
+// What the level loop knows about level d (input of its kernels), kept on the device: the host enqueues levels without
+// waiting for their results.  state[d + 1] is written by level d's emit kernel.
+struct LevelState {
+    uint32_t A;            // tasks of this level
+    uint32_t node_count;   // level nodes allocated so far
+    uint32_t S;            // small subtrees collected so far
+    uint32_t small_slots;  // node slots reserved for them
+};
+
+// Entry of BinnedSahBuildTask::run (binned_sah.rs:133-147): pad the node box, compute the binning transform.  Every
+// task has >= 2 primitives and depth < 64 (children that are leaves on entry are finalised by emit_kernel).
+__device__ __forceinline__ Box task_enter(float4* nodes, uint32_t node, Box b, TaskAux* aux_slot) {
     box_pad(b, kPad);
     store_node(nodes, node, b, 0, 0);
     TaskAux a;
@@ -253,7 +257,14 @@ __global__ void sah_prepare_kernel(const Task* __restrict__ tasks, uint32_t A, f
         a.k[k] = fmul(fdiv(1.0f, fsub(b.mx[k], b.mn[k])), (float)kBins);
         a.off[k] = fmul(-b.mn[k], a.k[k]);
     }
-    aux[t] = a;
+    *aux_slot = a;
+    return b;
+}
+// Level 0: the root task (node 0 already holds union_of_list of the primitives).
+__global__ void sah_root_task_kernel(float4* nodes, uint32_t n, Task* tasks, TaskAux* aux, LevelState* state) {
+    tasks[0] = Task{0u, 0u, n};
+    task_enter(nodes, 0, load_box(nodes, 0), &aux[0]);
+    state[0] = LevelState{1u, 1u, 0u, 0u};
 }
 
 __global__ void sah_bins_init_kernel(uint32_t* __restrict__ bins, size_t words) {
@@ -300,10 +311,12 @@ __device__ __forceinline__ void bins_smem_flush(const uint32_t* sb, uint32_t* g)
 __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __restrict__ idx, const int32_t* __restrict__ pos_task,
                                                             uint32_t n, uint32_t span, const TaskAux* __restrict__ aux,
                                                             const float4* __restrict__ bb, const float* __restrict__ cen,
-                                                            uint32_t cstride, uint32_t* __restrict__ bins) {
+                                                            uint32_t cstride, uint32_t* __restrict__ bins,
+                                                            uint16_t* __restrict__ binidx /* 3 x 4-bit bin per position */,
+                                                            const LevelState* __restrict__ state) {
     __shared__ uint32_t sb[kTaskBinWords];
     const uint64_t begin64 = (uint64_t)blockIdx.x * span;
-    if (begin64 >= n) return;
+    if (begin64 >= n || state->A == 0) return;
     const uint32_t begin = (uint32_t)begin64;
     const uint32_t end = (uint32_t)min((uint64_t)n, begin64 + span);
     int cur = -1;  // task whose bins live in shared memory (block-uniform)
@@ -330,11 +343,14 @@ __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __re
                 const TaskAux a = aux[t];
                 const Box box = load_box(bb, p);
                 uint32_t* dst = uni >= 0 ? sb : bins + (size_t)t * kTaskBinWords;
+                uint32_t packed = 0;
 #pragma unroll
                 for (int ax = 0; ax < 3; ax++) {
                     const int b = bin_index(cen[(size_t)p * cstride + ax], a.k[ax], a.off[ax]);
                     bin_accumulate(&dst[(ax * kBins + b) * kBinWords], box);
+                    packed |= (uint32_t)b << (4 * ax);
                 }
+                binidx[i] = (uint16_t)packed;  // the partition pass reads this instead of gathering the centroid again
             }
         }
     }
@@ -509,34 +525,48 @@ __device__ __forceinline__ void sah_split_task(const Task task, uint32_t t, int 
         counts[t] = c;
     }
 }
-__global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__ tasks, uint32_t A,
-                                                        const uint32_t* __restrict__ bins, const float4* __restrict__ nodes,
+// Launched for A_ub >= A warps (the host only knows an upper bound of the level's task count): warps beyond A zero
+// their counts entry so that the fixed-size scan that follows is exact.
+__global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__ tasks, uint32_t A_ub,
+                                                        uint32_t* __restrict__ bins, const float4* __restrict__ nodes,
                                                         uint32_t max_leaf, uint32_t depth, Decision* __restrict__ dec,
-                                                        uint4* __restrict__ counts) {
+                                                        uint4* __restrict__ counts, const LevelState* __restrict__ state) {
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (t >= A) return;
+    if (t >= A_ub) return;
+    if (t >= state->A) {
+        if (lane == 0) counts[t] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
     const Task task = tasks[t];
     if (task.end - task.begin <= kWarpTask) return;  // sah_warp_task_kernel's
-    sah_split_task(task, t, lane, bins + (size_t)t * kTaskBinWords, nodes, max_leaf, depth, dec, counts);
+    uint32_t* tb = bins + (size_t)t * kTaskBinWords;
+    sah_split_task(task, t, lane, tb, nodes, max_leaf, depth, dec, counts);
+    // leave the bins of slot t clean for whichever task gets this index on a later level
+    __syncwarp();
+    for (int k = lane; k < kTaskBinWords; k += 32) {
+        const int f = k % kBinWords;
+        tb[k] = f < 3 ? fkey(1e34f) : (f < 6 ? fkey(-1e34f) : 0u);
+    }
 }
 
 // Warp-class tasks (<= kWarpTask primitives): one warp fills the 3 x 16 bins of its task in shared memory (no global
 // atomics, no bins in HBM) and evaluates the split right away.  On the deep levels of the level loop every task is of
 // this class: the pass then reads each primitive once (index, box, centroid) and writes one Decision per task.
 constexpr int kWarpTaskWarps = 4;
-__global__ void __launch_bounds__(kWarpTaskWarps * 32) sah_warp_task_kernel(const Task* __restrict__ tasks, uint32_t A,
+__global__ void __launch_bounds__(kWarpTaskWarps * 32) sah_warp_task_kernel(const Task* __restrict__ tasks,
                                                                             const uint32_t* __restrict__ idx,
                                                                             const TaskAux* __restrict__ aux,
                                                                             const float4* __restrict__ bb,
                                                                             const float* __restrict__ cen, uint32_t cstride,
                                                                             const float4* __restrict__ nodes, uint32_t max_leaf,
                                                                             uint32_t depth, Decision* __restrict__ dec,
-                                                                            uint4* __restrict__ counts) {
+                                                                            uint4* __restrict__ counts, uint16_t* __restrict__ binidx,
+                                                                            const LevelState* __restrict__ state) {
     __shared__ uint32_t sb[kWarpTaskWarps][kTaskBinWords];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x * kWarpTaskWarps + w;
-    if (t >= A) return;
+    if (t >= state->A) return;
     const Task task = tasks[t];
     if (task.end - task.begin > kWarpTask) return;
     for (int k = lane; k < kTaskBinWords; k += 32) {
@@ -548,11 +578,14 @@ __global__ void __launch_bounds__(kWarpTaskWarps * 32) sah_warp_task_kernel(cons
     for (uint32_t i = task.begin + lane; i < task.end; i += 32) {
         const uint32_t p = idx[i];
         const Box box = load_box(bb, p);
+        uint32_t packed = 0;
 #pragma unroll
         for (int ax = 0; ax < 3; ax++) {
             const int b = bin_index(cen[(size_t)p * cstride + ax], a.k[ax], a.off[ax]);
             bin_accumulate(&sb[w][(ax * kBins + b) * kBinWords], box);
+            packed |= (uint32_t)b << (4 * ax);
         }
+        binidx[i] = (uint16_t)packed;
     }
     __syncwarp();
     sah_split_task(task, t, lane, sb[w], nodes, max_leaf, depth, dec, counts);
@@ -574,15 +607,28 @@ struct SmallTask {
     uint32_t node, begin, end, depth, node_base;
 };
 
-// Allocate the child pairs (level order), write inner nodes / leaves, emit next-level tasks and small subtrees.
+// Allocate the child pairs (level order), write inner nodes / leaves, emit next-level tasks (entered right here: box
+// pad + binning transform, so the next level starts with its bin pass) and small subtrees.
 // rank[t] = exclusive scan of counts: x pairs, y next-level tasks, z small subtrees, w node slots of small subtrees.
-__global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A, const Decision* __restrict__ dec,
-                                const uint4* __restrict__ rank, uint32_t node_base, uint32_t small_base,
-                                uint32_t small_node_base, uint32_t depth, float4* nodes, Task* __restrict__ next_tasks,
+// The thread of the last task publishes the next level's state.
+__global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, const Decision* __restrict__ dec,
+                                const uint4* __restrict__ rank, const uint4* __restrict__ counts, uint32_t depth, float4* nodes,
+                                Task* __restrict__ next_tasks, TaskAux* __restrict__ next_aux,
                                 SmallTask* __restrict__ small_tasks,
-                                int32_t* __restrict__ child_task /* 2 per task: next-level task index or -1 */) {
+                                int32_t* __restrict__ child_task /* 2 per task: encoded next-level task or -1 */,
+                                LevelState* __restrict__ state /* [depth] in, [depth + 1] out */) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= A) return;
+    const LevelState cur = state[depth];
+    if (cur.A == 0) {
+        if (t == 0) state[depth + 1] = cur;
+        return;
+    }
+    if (t >= cur.A) return;
+    if (t == cur.A - 1) {
+        const uint4 r = rank[t], c = counts[t];
+        state[depth + 1] = LevelState{r.y + c.y, cur.node_count + 2u * (r.x + c.x), cur.S + r.z + c.z, cur.small_slots + r.w + c.w};
+    }
+    const uint32_t node_base = cur.node_count, small_base = cur.S, small_node_base = cur.small_slots;
     const Task task = tasks[t];
     const Decision d = dec[t];
     const uint32_t n = task.end - task.begin;
@@ -614,17 +660,11 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A, cons
             small++;
             small_nodes += 2u * nc - 2u;
         } else {
-            store_node(nodes, left + k, cb[k], 0, 0);
+            task_enter(nodes, left + k, cb[k], &next_aux[next]);
             next_tasks[next] = Task{left + k, cbeg[k], cend[k]};
             child_task[2 * t + k] = pt_encode(next++, nc);
         }
     }
-}
-
-// totals of the level = last exclusive rank + last value
-__global__ void sah_totals_kernel(const uint4* rank, const uint4* counts, uint32_t A, uint4* out) {
-    const uint4 r = rank[A - 1], c = counts[A - 1];
-    *out = make_uint4(r.x + c.x, r.y + c.y, r.z + c.z, r.w + c.w);
 }
 
 // ---- small subtrees: one warp runs BinnedSahBuildTask::run for every node below a <= 32-primitive task -----
@@ -857,43 +897,75 @@ __global__ void compact_nodes_kernel(const float4* __restrict__ in, float4* __re
     out[(size_t)dst * 2 + 1] = b;
 }
 
-// partition predicate (binned_sah.rs:213-219) for every index position
-__global__ void sah_flag_kernel(const uint32_t* __restrict__ idx, const int32_t* __restrict__ pos_task, uint32_t n,
-                                const TaskAux* __restrict__ aux, const Decision* __restrict__ dec,
-                                const float* __restrict__ cen, uint32_t cstride, uint32_t* __restrict__ flag) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t t = pt_task(pos_task[i]);
-    uint32_t f = 0;
-    if (t >= 0) {
-        const Decision& d = dec[t];
-        if (d.split) {
-            const uint32_t ax = d.axis;
-            f = (uint32_t)bin_index(cen[(size_t)idx[i] * cstride + ax], aux[t].k[ax], aux[t].off[ax]) < d.split_index ? 1u : 0u;
+// ---- stable partition of every task's index range: ONE segmented scan (cub::DeviceScan::InclusiveScanByKey over the
+// task keys) whose input iterator evaluates the partition predicate on the fly (binned_sah.rs:213-219) and whose output
+// iterator scatters the index to its place in the ping-pong buffer: no flag array, no rank array, no extra kernels.
+struct FlagSum {
+    uint32_t sum, flag;  // inclusive count of left-going positions of the segment; this position's own predicate
+};
+struct FlagSumOp {
+    __host__ __device__ FlagSum operator()(const FlagSum& a, const FlagSum& b) const { return FlagSum{a.sum + b.sum, b.flag}; }
+};
+struct PartitionParams {
+    const uint32_t* idx;
+    const int32_t* pos_task;
+    const Task* tasks;
+    const TaskAux* aux;
+    const Decision* dec;
+    const int32_t* child_task;
+    const uint16_t* binidx;
+    uint32_t* idx_out;
+    int32_t* pos_task_out;
+};
+struct PartitionFlagIn {
+    const PartitionParams* p;
+    __device__ FlagSum operator()(uint32_t i) const {
+        const int32_t t = pt_task(p->pos_task[i]);
+        uint32_t f = 0;
+        if (t >= 0) {
+            const Decision& d = p->dec[t];
+            if (d.split) {
+                f = (((uint32_t)p->binidx[i] >> (4u * d.axis)) & 15u) < d.split_index ? 1u : 0u;
+            }
         }
+        return FlagSum{f, f};
     }
-    flag[i] = f;
-}
-
-__global__ void sah_scatter_kernel(const uint32_t* __restrict__ idx, const int32_t* __restrict__ pos_task, uint32_t n,
-                                   const Task* __restrict__ tasks, const Decision* __restrict__ dec,
-                                   const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank_left,
-                                   const int32_t* __restrict__ child_task, uint32_t* __restrict__ idx_out,
-                                   int32_t* __restrict__ pos_task_out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t t = pt_task(pos_task[i]);
-    if (t < 0 || !dec[t].split) {
-        idx_out[i] = idx[i];
-        pos_task_out[i] = -1;
-        return;
+};
+struct PartitionScatterOut {
+    const PartitionParams* p;
+    uint32_t base;
+    struct Ref {
+        const PartitionParams* p;
+        uint32_t i;
+        __device__ const Ref& operator=(const FlagSum& v) const {
+            const int32_t t = pt_task(p->pos_task[i]);
+            if (t < 0 || !p->dec[t].split) {
+                p->idx_out[i] = p->idx[i];
+                p->pos_task_out[i] = -1;
+            } else {
+                const uint32_t begin = p->tasks[t].begin, nleft = p->dec[t].nleft, r = v.sum - v.flag;
+                const bool left = v.flag != 0;
+                const uint32_t dest = left ? begin + r : begin + nleft + (i - begin - r);
+                p->idx_out[dest] = p->idx[i];
+                p->pos_task_out[dest] = p->child_task[2 * t + (left ? 0 : 1)];
+            }
+            return *this;
+        }
+    };
+    using iterator_category = std::random_access_iterator_tag;
+    using value_type = FlagSum;
+    using difference_type = ptrdiff_t;
+    using pointer = void;
+    using reference = Ref;
+    __host__ __device__ PartitionScatterOut operator+(difference_type k) const { return PartitionScatterOut{p, base + (uint32_t)k}; }
+    __host__ __device__ PartitionScatterOut& operator+=(difference_type k) {
+        base += (uint32_t)k;
+        return *this;
     }
-    const uint32_t begin = tasks[t].begin, nleft = dec[t].nleft, r = rank_left[i];
-    const bool left = flag[i] != 0;
-    const uint32_t dest = left ? begin + r : begin + nleft + (i - begin - r);
-    idx_out[dest] = idx[i];
-    pos_task_out[dest] = child_task[2 * t + (left ? 0 : 1)];
-}
+    __host__ __device__ Ref operator[](difference_type k) const { return Ref{p, base + (uint32_t)k}; }
+    __host__ __device__ Ref operator*() const { return Ref{p, base}; }
+};
+using PartitionFlagIter = cub::TransformInputIterator<FlagSum, PartitionFlagIn, cub::CountingInputIterator<uint32_t>>;
 
 // =================================================================================================
 // LOCB
@@ -1221,16 +1293,13 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
     DevBuf nodesA;
     RTB_CUDA(nodesA.alloc((size_t)max_nodes * 32));
     float4* nodes = nodesA.as<float4>();
-    DevBuf idxA, idxB, ptA, ptB, tasksA, tasksB, aux, dec, bins, flag, rank, counts, ranks4, child_task, world, temp, totals,
-        small_tasks, used, waste, waste_prefix;
-    RTB_CUDA(idxA.alloc((size_t)n * 4));
-    RTB_CUDA(idxB.alloc((size_t)n * 4));
-    RTB_CUDA(ptA.alloc((size_t)n * 4));
-    RTB_CUDA(ptB.alloc((size_t)n * 4));
-    RTB_CUDA(flag.alloc((size_t)n * 4));
-    RTB_CUDA(rank.alloc((size_t)n * 4));
+    DevBuf idxB[2], ptB[2], tasksB[2], auxB[2], binidx, dec, bins, counts, ranks4, child_task, world, temp, state, params, small_tasks, used,
+        waste, waste_prefix;
+    for (int k = 0; k < 2; k++) {
+        RTB_CUDA(idxB[k].alloc((size_t)n * 4));
+        RTB_CUDA(ptB[k].alloc((size_t)n * 4));
+    }
     RTB_CUDA(world.alloc(6 * 4));
-    RTB_CUDA(totals.alloc(16));
     // every small subtree holds >= 2 primitives, so there are at most n / 2 of them
     const uint32_t small_cap = n / 2 + 1;
     RTB_CUDA(small_tasks.alloc((size_t)small_cap * sizeof(SmallTask)));
@@ -1238,110 +1307,112 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
     world_init_kernel<<<1, 32>>>(world.as<uint32_t>());
     world_reduce_kernel<<<std::min(blocks(n, 256), 148u * 8u), 256>>>(d_bb, n, world.as<uint32_t>());
     world_to_node_kernel<<<1, 1>>>(world.as<uint32_t>(), nodes, 0, 0, 0, nullptr);
-    iota_kernel<<<blocks(n, 256), 256>>>(idxA.as<uint32_t>(), n);
-    uint32_t node_count = 1;
-    uint32_t A = 0;
-    size_t task_cap = 0;
-    auto ensure_tasks = [&](size_t cap) -> cudaError_t {
-        if (cap <= task_cap) return cudaSuccess;
-        cap = std::max(cap, task_cap * 2);
-        cudaError_t e;
-        // tasksA holds the current level and must survive growth
-        DevBuf grown;
-        if ((e = grown.alloc(cap * sizeof(Task))) != cudaSuccess) return e;
-        if (tasksA.p && A) cudaMemcpyAsync(grown.p, tasksA.p, (size_t)A * sizeof(Task), cudaMemcpyDeviceToDevice, 0);
-        std::swap(grown.p, tasksA.p);
-        std::swap(grown.bytes, tasksA.bytes);
-        if ((e = tasksB.alloc(cap * 2 * sizeof(Task))) != cudaSuccess) return e;
-        if ((e = aux.alloc(cap * sizeof(TaskAux))) != cudaSuccess) return e;
-        if ((e = dec.alloc(cap * sizeof(Decision))) != cudaSuccess) return e;
-        if ((e = bins.alloc(cap * kTaskBinWords * 4)) != cudaSuccess) return e;
-        if ((e = counts.alloc(cap * sizeof(uint4))) != cudaSuccess) return e;
-        if ((e = ranks4.alloc(cap * sizeof(uint4))) != cudaSuccess) return e;
-        if ((e = child_task.alloc(cap * 8)) != cudaSuccess) return e;
-        task_cap = cap;
-        return cudaSuccess;
-    };
-    // CUB temp storage: sized for the largest scans we run
-    size_t temp_bytes = 0, tb = 0;
-    cub::DeviceScan::ExclusiveSumByKey(nullptr, tb, ptA.as<int32_t>(), flag.as<uint32_t>(), rank.as<uint32_t>(), (int)n);
-    temp_bytes = tb;
-    cub::DeviceScan::ExclusiveScan(nullptr, tb, (uint4*)nullptr, (uint4*)nullptr, Uint4Add(), make_uint4(0, 0, 0, 0), (int)(n / 2 + 1));
-    temp_bytes = std::max(temp_bytes, tb);
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)small_cap);
-    temp_bytes = std::max(temp_bytes, tb);
-    RTB_CUDA(temp.alloc(temp_bytes));
-
+    iota_kernel<<<blocks(n, 256), 256>>>(idxB[0].as<uint32_t>(), n);
+    LevelState fin{0u, 1u, 0u, 0u};
+    int parity = 0;  // idxB[parity] holds the current index order
     if (n <= 1) {  // the root is a leaf on entry: pad (run) + pad (make_leaf)
         // world_to_node wrote union_of_list's own pad; apply run's and make_leaf's pads
         root_leaf_kernel<<<1, 1>>>(nodes, n);
     } else {
-        RTB_CUDA(ensure_tasks(1024));
-        const Task root{0, 0, n};
-        RTB_CUDA(cudaMemcpy(tasksA.p, &root, sizeof(Task), cudaMemcpyHostToDevice));
-        fill_i32_kernel<<<blocks(n, 256), 256>>>(ptA.as<int32_t>(), n, pt_encode(0, n));  // every position belongs to task 0
-        A = 1;
-    }
-    uint32_t* idx_cur = idxA.as<uint32_t>();
-    uint32_t* idx_nxt = idxB.as<uint32_t>();
-    int32_t* pt_cur = ptA.as<int32_t>();
-    int32_t* pt_nxt = ptB.as<int32_t>();
-    uint32_t S = 0, small_slots = 0;  // small subtrees collected so far and the node slots reserved for them
-    // bin kernel: a machine-sized grid, every block owns a contiguous span (multiple of the chunk size)
-    const uint32_t bin_chunks = blocks(n, kBinBlock);
-    const uint32_t bin_grid = std::min(bin_chunks, 148u * 8u);
-    const uint32_t bin_span = ((bin_chunks + bin_grid - 1) / bin_grid) * kBinBlock;
-    // Node slots of small subtrees are numbered after all level nodes; until the level loop ends the final
-    // number of level nodes is unknown, so small node_base values are stored relative and rebased below.
-    for (uint32_t depth = 0; A > 0; depth++) {
-        RTB_CUDA(ensure_tasks(A));
-        Task* t_cur = tasksA.as<Task>();
-        Task* t_nxt = tasksB.as<Task>();
-        sah_prepare_kernel<<<blocks(A, 128), 128>>>(t_cur, A, nodes, aux.as<TaskAux>());
-        const size_t words = (size_t)A * kTaskBinWords;
+        // A level task holds > kSmall primitives (smaller children go to the small-subtree list), so no level has more
+        // than n / (kSmall + 1) tasks: every per-task array is sized once, nothing grows inside the loop.
+        const uint32_t task_cap = n / (kSmall + 1) + 2;
+        for (int k = 0; k < 2; k++) {
+            RTB_CUDA(tasksB[k].alloc((size_t)task_cap * sizeof(Task)));
+            RTB_CUDA(auxB[k].alloc((size_t)task_cap * sizeof(TaskAux)));
+        }
+        RTB_CUDA(dec.alloc((size_t)task_cap * sizeof(Decision)));
+        RTB_CUDA(bins.alloc((size_t)task_cap * kTaskBinWords * 4));
+        RTB_CUDA(counts.alloc((size_t)task_cap * sizeof(uint4)));
+        RTB_CUDA(ranks4.alloc((size_t)task_cap * sizeof(uint4)));
+        RTB_CUDA(child_task.alloc((size_t)task_cap * 8));
+        RTB_CUDA(binidx.alloc((size_t)n * 2));
+        RTB_CUDA(state.alloc((size_t)(kMaxDepth + 3) * sizeof(LevelState)));
+        RTB_CUDA(params.alloc(2 * sizeof(PartitionParams)));
+        PartitionParams hp[2];
+        for (int k = 0; k < 2; k++)
+            hp[k] = PartitionParams{idxB[k].as<uint32_t>(), ptB[k].as<int32_t>(), tasksB[k].as<Task>(), auxB[k].as<TaskAux>(),
+                                    dec.as<Decision>(), child_task.as<int32_t>(), binidx.as<uint16_t>(), idxB[k ^ 1].as<uint32_t>(),
+                                    ptB[k ^ 1].as<int32_t>()};
+        RTB_CUDA(cudaMemcpyAsync(params.p, hp, sizeof(hp), cudaMemcpyHostToDevice, 0));
+        // CUB temp storage: sized for the largest scans we run
+        size_t temp_bytes = 0, tb = 0;
+        const PartitionParams* dp = params.as<PartitionParams>();
+        cub::DeviceScan::InclusiveScanByKey(nullptr, tb, ptB[0].as<int32_t>(),
+                                            PartitionFlagIter(cub::CountingInputIterator<uint32_t>(0), PartitionFlagIn{dp}),
+                                            PartitionScatterOut{dp, 0}, FlagSumOp(), n);
+        temp_bytes = tb;
+        cub::DeviceScan::ExclusiveScan(nullptr, tb, (uint4*)nullptr, (uint4*)nullptr, Uint4Add(), make_uint4(0, 0, 0, 0), (int)task_cap);
+        temp_bytes = std::max(temp_bytes, tb);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)small_cap);
+        temp_bytes = std::max(temp_bytes, tb);
+        RTB_CUDA(temp.alloc(temp_bytes));
+        // bins start clean and are left clean by every split (sah_split_kernel re-initialises what it has read)
+        const size_t words = (size_t)task_cap * kTaskBinWords;
         sah_bins_init_kernel<<<blocks(words, 256), 256>>>(bins.as<uint32_t>(), words);
-        sah_bin_kernel<<<bin_grid, kBinBlock>>>(idx_cur, pt_cur, n, bin_span, aux.as<TaskAux>(), d_bb, d_cen, cstride,
-                                                bins.as<uint32_t>());
-        sah_split_kernel<<<blocks((size_t)A * 32, 128), 128>>>(t_cur, A, bins.as<uint32_t>(), nodes, max_leaf, depth,
-                                                               dec.as<Decision>(), counts.as<uint4>());
-        sah_warp_task_kernel<<<blocks(A, kWarpTaskWarps), kWarpTaskWarps * 32>>>(t_cur, A, idx_cur, aux.as<TaskAux>(), d_bb, d_cen,
-                                                                                 cstride, nodes, max_leaf, depth,
-                                                                                 dec.as<Decision>(), counts.as<uint4>());
-        size_t tbytes = temp.bytes;
-        RTB_CUDA(cub::DeviceScan::ExclusiveScan(temp.p, tbytes, counts.as<uint4>(), ranks4.as<uint4>(), Uint4Add(),
-                                                make_uint4(0, 0, 0, 0), (int)A));
-        // one small D2H per level: the host needs the next level's task count to size its launches
-        sah_totals_kernel<<<1, 1>>>(ranks4.as<uint4>(), counts.as<uint4>(), A, totals.as<uint4>());
-        uint32_t h[4];
-        RTB_CUDA(cudaMemcpy(h, totals.p, 16, cudaMemcpyDeviceToHost));
-        const uint32_t pairs = h[0], next_A = h[1], new_small = h[2], new_slots = h[3];
-        if ((size_t)next_A * 2 * sizeof(Task) > tasksB.bytes) {
-            RTB_CUDA(tasksB.alloc((size_t)next_A * 2 * sizeof(Task)));
-            t_nxt = tasksB.as<Task>();
-        }
-        if (S + new_small > small_cap) return fail("binned SAH: small-subtree list overflow");
-        sah_emit_kernel<<<blocks(A, 128), 128>>>(t_cur, A, dec.as<Decision>(), ranks4.as<uint4>(), node_count, S, small_slots,
-                                                 depth, nodes, t_nxt, small_tasks.as<SmallTask>(), child_task.as<int32_t>());
-        if (pairs > 0) {
-            sah_flag_kernel<<<blocks(n, 256), 256>>>(idx_cur, pt_cur, n, aux.as<TaskAux>(), dec.as<Decision>(), d_cen, cstride,
-                                                     flag.as<uint32_t>());
+        fill_i32_kernel<<<blocks(n, 256), 256>>>(ptB[0].as<int32_t>(), n, pt_encode(0, n));  // every position belongs to task 0
+        LevelState* d_state = state.as<LevelState>();
+        sah_root_task_kernel<<<1, 1>>>(nodes, n, tasksB[0].as<Task>(), auxB[0].as<TaskAux>(), d_state);
+        // bin kernel: a machine-sized grid, every block owns a contiguous span (multiple of the chunk size)
+        const uint32_t bin_chunks = blocks(n, kBinBlock);
+        const uint32_t bin_grid = std::min(bin_chunks, 148u * 8u);
+        const uint32_t bin_span = ((bin_chunks + bin_grid - 1) / bin_grid) * kBinBlock;
+        // The level loop runs on the device's own bookkeeping (LevelState): the host enqueues level after level with
+        // launch sizes from an upper bound of the task count and only looks at the state — one level behind, through a
+        // pinned copy — once the tree could be finished (a task can only vanish after log2(n / kSmall) halvings unless the
+        // input is degenerate; a level enqueued after the last one is a no-op that passes the index order through).
+        static thread_local LevelState* h_state = nullptr;
+        if (!h_state) RTB_CUDA(cudaHostAlloc(&h_state, (size_t)(kMaxDepth + 3) * sizeof(LevelState), cudaHostAllocDefault));
+        cudaEvent_t ev[2];
+        RTB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        RTB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+        uint32_t first_check = 0;
+        while ((uint64_t(kSmall) << (first_check + 1)) < n) first_check++;
+        uint32_t depth = 0;
+        bool done = false;
+        for (; !done && depth <= (uint32_t)kMaxDepth; depth++) {
+            const int par = (int)(depth & 1u);
+            const uint32_t A_ub = depth >= 31 ? task_cap : std::min(task_cap, 1u << depth);
+            const Task* t_cur = tasksB[par].as<Task>();
+            const TaskAux* aux_cur = auxB[par].as<TaskAux>();
+            const LevelState* st = d_state + depth;
+            sah_bin_kernel<<<bin_grid, kBinBlock>>>(idxB[par].as<uint32_t>(), ptB[par].as<int32_t>(), n, bin_span, aux_cur, d_bb, d_cen,
+                                                    cstride, bins.as<uint32_t>(), binidx.as<uint16_t>(), st);
+            sah_split_kernel<<<blocks((size_t)A_ub * 32, 128), 128>>>(t_cur, A_ub, bins.as<uint32_t>(), nodes, max_leaf, depth,
+                                                                      dec.as<Decision>(), counts.as<uint4>(), st);
+            sah_warp_task_kernel<<<blocks(A_ub, kWarpTaskWarps), kWarpTaskWarps * 32>>>(t_cur, idxB[par].as<uint32_t>(), aux_cur, d_bb,
+                                                                                        d_cen, cstride, nodes, max_leaf, depth,
+                                                                                        dec.as<Decision>(), counts.as<uint4>(),
+                                                                                        binidx.as<uint16_t>(), st);
+            size_t tbytes = temp.bytes;
+            RTB_CUDA(cub::DeviceScan::ExclusiveScan(temp.p, tbytes, counts.as<uint4>(), ranks4.as<uint4>(), Uint4Add(),
+                                                    make_uint4(0, 0, 0, 0), (int)A_ub));
+            sah_emit_kernel<<<blocks(A_ub, 128), 128>>>(t_cur, A_ub, dec.as<Decision>(), ranks4.as<uint4>(), counts.as<uint4>(), depth,
+                                                        nodes, tasksB[par ^ 1].as<Task>(), auxB[par ^ 1].as<TaskAux>(),
+                                                        small_tasks.as<SmallTask>(), child_task.as<int32_t>(), d_state);
             tbytes = temp.bytes;
-            RTB_CUDA(cub::DeviceScan::ExclusiveSumByKey(temp.p, tbytes, pt_cur, flag.as<uint32_t>(), rank.as<uint32_t>(), (int)n));
-            sah_scatter_kernel<<<blocks(n, 256), 256>>>(idx_cur, pt_cur, n, t_cur, dec.as<Decision>(), flag.as<uint32_t>(),
-                                                        rank.as<uint32_t>(), child_task.as<int32_t>(), idx_nxt, pt_nxt);
-            std::swap(idx_cur, idx_nxt);
-            std::swap(pt_cur, pt_nxt);
+            RTB_CUDA(cub::DeviceScan::InclusiveScanByKey(temp.p, tbytes, ptB[par].as<int32_t>(),
+                                                         PartitionFlagIter(cub::CountingInputIterator<uint32_t>(0), PartitionFlagIn{dp + par}),
+                                                         PartitionScatterOut{dp + par, 0}, FlagSumOp(), n));
+            RTB_CUDA(cudaMemcpyAsync(&h_state[depth + 1], d_state + depth + 1, sizeof(LevelState), cudaMemcpyDeviceToHost, 0));
+            RTB_CUDA(cudaEventRecord(ev[par], 0));
+            if (depth >= 1 && depth - 1 >= first_check) {
+                RTB_CUDA(cudaEventSynchronize(ev[par ^ 1]));  // level depth - 1 has finished: h_state[depth] is valid
+                if (h_state[depth].A == 0) done = true;      // the level just enqueued is a no-op; nothing follows it
+            }
         }
-        node_count += 2 * pairs;
-        S += new_small;
-        small_slots += new_slots;
-        // next level's tasks become current
-        std::swap(tasksA.p, tasksB.p);
-        std::swap(tasksA.bytes, tasksB.bytes);
-        A = next_A;
+        RTB_CUDA(cudaEventSynchronize(ev[(depth - 1) & 1u]));
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
         RTB_CUDA(cudaGetLastError());
+        fin = h_state[depth];
+        if (fin.A != 0) return fail("binned SAH: level loop did not terminate");
+        parity = (int)(depth & 1u);  // one ping-pong step per enqueued level
+        if (fin.S > small_cap) return fail("binned SAH: small-subtree list overflow");
     }
-    const uint32_t level_nodes = node_count;
+    uint32_t* idx_cur = idxB[parity].as<uint32_t>();
+    const uint32_t S = fin.S, small_slots = fin.small_slots;
+    const uint32_t level_nodes = fin.node_count;
     uint32_t total_nodes = level_nodes;
     if (S > 0) {
         // rebase the reserved ranges behind the level nodes, then let one warp finish each subtree
@@ -1372,8 +1443,9 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         std::swap(out->nodes.p, nodesA.p);
         std::swap(out->nodes.bytes, nodesA.bytes);
     }
-    RTB_CUDA(out->indices.alloc((size_t)n * 4));
-    RTB_CUDA(cudaMemcpyAsync(out->indices.p, idx_cur, (size_t)n * 4, cudaMemcpyDeviceToDevice, 0));
+    // hand the index buffer over as well
+    std::swap(out->indices.p, idxB[parity].p);
+    std::swap(out->indices.bytes, idxB[parity].bytes);
     out->node_count = total_nodes;
     out->index_count = n;
     RTB_CUDA(cudaDeviceSynchronize());
