@@ -80,6 +80,18 @@ const char *rtbvh_gpu_last_error(void);           /* message of the last Error o
 ResultCode rtbvh_gpu_scene_create(const RTBvh *bvh, const RTMbvh *mbvh, const float *vertices, size_t vertex_stride,
                                   size_t triangle_count, RTGpuScene *scene);
 ResultCode rtbvh_gpu_scene_free(RTGpuScene scene);
+/* Build straight into a scene: Builder{aabbs: None, primitives: &[Triangle]}.construct_binned_sah /
+ * construct_locally_ordered_clustered (src/bvh.rs:87-137) and, if want_mbvh, Mbvh::construct (src/bvh.rs:381-404), with
+ * nodes, prim_indices and triangle records LEFT ON THE DEVICE: no host mirror is produced (no D2H of the tree, no second
+ * upload), which is what a renderer that only traces on the GPU needs and what makes per-frame rebuilds affordable.
+ * The trees are the same, byte for byte, as create_bvh / rtbvh_gpu_create_bvh_triangles + create_mbvh produce;
+ * rtbvh_gpu_scene_tree_size / _read_nodes / _read_indices copy them out on demand.  _device takes device vertices. */
+ResultCode rtbvh_gpu_scene_build(const float *vertices, size_t vertex_stride, size_t triangle_count, size_t prims_per_leaf,
+                                 BvhType type, int want_mbvh, RTGpuScene *scene);
+ResultCode rtbvh_gpu_scene_build_device(const float *d_vertices, size_t vertex_stride, size_t triangle_count,
+                                        size_t prims_per_leaf, BvhType type, int want_mbvh, RTGpuScene *scene);
+ResultCode rtbvh_gpu_scene_tree_size(RTGpuScene scene, RTTreeKind tree, uint32_t *node_count, uint32_t *index_count);
+ResultCode rtbvh_gpu_scene_read_indices(RTGpuScene scene, RTTreeKind tree, uint32_t *out, size_t count);
 /* Dynamic scenes (the step after build for animated geometry; Bvh::refit src/bvh.rs:176-205, FFI refit
  * rtbvh_ffi/src/lib.rs:519-538).  New vertex positions for the SAME triangles (same count and order): recomputes the
  * per-triangle boxes (Triangle::aabb, un-padded), refits the scene's Bvh in place (leaf = union of its primitives'

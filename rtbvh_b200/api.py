@@ -50,7 +50,8 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_peer_buffer_open", "rtbvh_gpu_peer_buffer_close", "rtbvh_gpu_peer_buffer_free",
                "rtbvh_gpu_intersect_device_scatter", "rtbvh_gpu_occluded_device_scatter", "rtbvh_gpu_peer_barrier",
                "rtbvh_gpu_intersect_async", "rtbvh_gpu_occluded_async", "rtbvh_gpu_wait", "rtbvh_gpu_host_alloc",
-               "rtbvh_gpu_host_free", "rtbvh_gpu_scene_refit", "rtbvh_gpu_scene_refit_device", "rtbvh_gpu_scene_read_nodes")
+               "rtbvh_gpu_host_free", "rtbvh_gpu_scene_refit", "rtbvh_gpu_scene_refit_device", "rtbvh_gpu_scene_read_nodes",
+               "rtbvh_gpu_scene_build", "rtbvh_gpu_scene_build_device", "rtbvh_gpu_scene_tree_size", "rtbvh_gpu_scene_read_indices")
 
 
 class RTBvh(C.Structure):  # rtbvh_ffi/src/lib.rs:210-220
@@ -156,6 +157,14 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_host_alloc.argtypes = [sz, C.POINTER(vp)]
     L.rtbvh_gpu_host_free.restype = rc
     L.rtbvh_gpu_host_free.argtypes = [vp]
+    L.rtbvh_gpu_scene_build.restype = rc
+    L.rtbvh_gpu_scene_build.argtypes = [vp, sz, sz, sz, u32, C.c_int, C.POINTER(u64)]
+    L.rtbvh_gpu_scene_build_device.restype = rc
+    L.rtbvh_gpu_scene_build_device.argtypes = [vp, sz, sz, sz, u32, C.c_int, C.POINTER(u64)]
+    L.rtbvh_gpu_scene_tree_size.restype = rc
+    L.rtbvh_gpu_scene_tree_size.argtypes = [u64, C.c_int, C.POINTER(u32), C.POINTER(u32)]
+    L.rtbvh_gpu_scene_read_indices.restype = rc
+    L.rtbvh_gpu_scene_read_indices.argtypes = [u64, C.c_int, vp, sz]
     L.rtbvh_gpu_scene_refit.restype = rc
     L.rtbvh_gpu_scene_refit.argtypes = [u64, vp, sz, sz]
     L.rtbvh_gpu_scene_refit_device.restype = rc
@@ -359,6 +368,37 @@ class Scene:
         self.n_mnodes = int(mbvh.rt.node_count) if mbvh else 0
         _check(lib().rtbvh_gpu_scene_create(C.byref(bvh.rt) if bvh else None, C.byref(mbvh.rt) if mbvh else None,
                                             _p(v), stride, v.shape[0] // 3, C.byref(self.handle)))
+
+    @classmethod
+    def build(cls, vertices, bvh_type: int = 1, prims_per_leaf: int = 1, mbvh: bool = True, n_tris: int | None = None,
+              vertex_stride: int = 12) -> "Scene":
+        """rtbvh_gpu_scene_build(_device): trees built and kept on the device.  `vertices`: numpy [n, 3, 3|4] (host) or a
+        torch CUDA tensor / raw device pointer (then pass n_tris and vertex_stride)."""
+        self = cls.__new__(cls)
+        self.handle = C.c_uint64(0)
+        if isinstance(vertices, np.ndarray):
+            v = np.ascontiguousarray(vertices, dtype=np.float32)
+            stride = 16 if v.shape[-1] == 4 else 12
+            v = v.reshape(-1, stride // 4)
+            _check(lib().rtbvh_gpu_scene_build(_p(v), stride, v.shape[0] // 3, prims_per_leaf, bvh_type, int(mbvh),
+                                               C.byref(self.handle)))
+        else:
+            _check(lib().rtbvh_gpu_scene_build_device(_dev_ptr(vertices), vertex_stride, n_tris, prims_per_leaf, bvh_type,
+                                                      int(mbvh), C.byref(self.handle)))
+        nn, ni = C.c_uint32(0), C.c_uint32(0)
+        _check(lib().rtbvh_gpu_scene_tree_size(self.handle, TREE_BVH, C.byref(nn), C.byref(ni)))
+        self.n_nodes, self.n_indices, self.n_mnodes = nn.value, ni.value, 0
+        if mbvh:
+            _check(lib().rtbvh_gpu_scene_tree_size(self.handle, TREE_MBVH, C.byref(nn), None))
+            self.n_mnodes = nn.value
+        return self
+
+    def read_indices(self, tree: int = TREE_BVH) -> np.ndarray:
+        ni = C.c_uint32(0)
+        _check(lib().rtbvh_gpu_scene_tree_size(self.handle, tree, None, C.byref(ni)))
+        out = np.zeros(ni.value, dtype=np.uint32)
+        _check(lib().rtbvh_gpu_scene_read_indices(self.handle, tree, out.ctypes.data_as(C.c_void_p), ni.value))
+        return out
 
     def set_ray_sorting(self, enable: bool = True):
         """Trace every single-ray batch in Morton order of (origin, direction); results are unchanged."""

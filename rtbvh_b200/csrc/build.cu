@@ -1247,6 +1247,12 @@ struct DevBuf {
     }
     template <class T>
     T* as() { return (T*)p; }
+    void* release() {  // hands the allocation to the caller (cudaFree accepts pool allocations)
+        void* q = p;
+        p = nullptr;
+        bytes = 0;
+        return q;
+    }
 };
 inline unsigned blocks(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
@@ -1716,6 +1722,50 @@ ResultCode gpu_refit(HostBvh* bvh, const RTAabb* aabbs) {
     RTB_CUDA(cudaGetLastError());
     g_build_stats.device_ms = dev.stop();
     RTB_CUDA(cudaMemcpy(bvh->nodes.data(), nodes.p, (size_t)n_nodes * 32, cudaMemcpyDeviceToHost));
+    g_build_stats.total_ms = total.stop();
+    return Ok;
+}
+
+// ---- build straight into device-resident trees (no host mirror): the scene path of rtbvh_gpu_scene_build ----------
+ResultCode gpu_build_resident(const float* vertices, bool vertices_on_device, size_t vertex_stride, size_t tri_count,
+                              size_t prims_per_leaf, uint32_t bvh_type, bool want_mbvh, ResidentTrees* out) {
+    if (need_device() != Ok) return Error;
+    if (tri_count >= (size_t(1) << 31)) return fail("more than 2^31 primitives");
+    const uint32_t n = (uint32_t)tri_count;
+    Timer total, dev;
+    total.start();
+    DevBuf verts, bb, cen;
+    const float* d_verts = vertices;
+    if (!vertices_on_device) {
+        RTB_CUDA(verts.alloc((size_t)n * 3 * vertex_stride));
+        RTB_CUDA(cudaMemcpyAsync(verts.p, vertices, (size_t)n * 3 * vertex_stride, cudaMemcpyHostToDevice, 0));
+        d_verts = verts.as<float>();
+    }
+    RTB_CUDA(bb.alloc((size_t)n * 32));
+    RTB_CUDA(cen.alloc((size_t)n * 12));
+    dev.start();
+    tri_prims_kernel<<<blocks(n, 256), 256>>>(d_verts, (uint32_t)(vertex_stride / 4), n, bb.as<float4>(), cen.as<float>());
+    DeviceBvh d;
+    uint32_t iters = 0;
+    ResultCode rc;
+    if (bvh_type == LocallyOrderedClustered)
+        rc = build_locb_device(bb.as<float4>(), cen.as<float>(), 3, n, &d, &iters);
+    else
+        rc = build_binned_sah_device(bb.as<float4>(), cen.as<float>(), 3, n, (uint32_t)(prims_per_leaf ? prims_per_leaf : 1), &d);
+    if (rc != Ok) return rc;
+    DevBuf mnodes;
+    uint32_t m_count = 0;
+    if (want_mbvh && collapse_device(d.nodes.as<float4>(), d.node_count, &mnodes, &m_count) != Ok) return Error;
+    g_build_stats.device_ms = dev.stop();
+    g_build_stats.iterations = iters;
+    g_build_stats.node_count = d.node_count;
+    out->node_count = d.node_count;
+    out->index_count = d.index_count;
+    out->m_count = m_count;
+    out->d_nodes = d.nodes.release();
+    out->d_indices = (uint32_t*)d.indices.release();
+    out->d_mnodes = want_mbvh ? mnodes.release() : nullptr;
+    out->d_vertices = vertices_on_device ? nullptr : (float*)verts.release();
     g_build_stats.total_ms = total.stop();
     return Ok;
 }

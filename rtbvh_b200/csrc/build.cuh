@@ -41,6 +41,18 @@ ResultCode gpu_collapse(const HostBvh& bvh, HostMbvh* out);
 // Bvh::refit (src/bvh.rs:176-205) on the GPU.
 ResultCode gpu_refit(HostBvh* bvh, const RTAabb* aabbs);
 
+// Builder::construct_* + Mbvh::construct with the results LEFT ON THE DEVICE (cudaFree-able allocations): what
+// rtbvh_gpu_scene_build hands to a scene.  d_vertices is the uploaded copy of host vertices (null if they were resident).
+struct ResidentTrees {
+    void* d_nodes = nullptr;
+    uint32_t* d_indices = nullptr;
+    void* d_mnodes = nullptr;
+    float* d_vertices = nullptr;
+    uint32_t node_count = 0, index_count = 0, m_count = 0;
+};
+ResultCode gpu_build_resident(const float* vertices, bool vertices_on_device, size_t vertex_stride, size_t tri_count,
+                              size_t prims_per_leaf, uint32_t bvh_type, bool want_mbvh, ResidentTrees* out);
+
 // Dynamic scenes: refit of a device-resident Bvh (+ refresh of its Mbvh) from new vertex positions,
 // everything on `stream`.  The cache holds what does not change under refit (parent links, the binary node behind every
 // MbvhNode) plus scratch; it belongs to one tree pair.

@@ -503,6 +503,76 @@ ResultCode rtbvh_gpu_scene_create(const RTBvh* bvh, const RTMbvh* mbvh, const fl
     return Ok;
 }
 
+// ---- build into a scene without host mirrors ----------------------------------------------------------------------
+static ResultCode scene_build_common(const float* vertices, bool on_device, size_t vertex_stride, size_t triangle_count,
+                                     size_t prims_per_leaf, BvhType type, int want_mbvh, RTGpuScene* scene) {
+    if (!scene || !vertices) return fail("rtbvh_gpu_scene_build: null argument");
+    if (vertex_stride != 12 && vertex_stride != 16) return fail("vertex_stride must be 12 or 16 bytes");
+    if (triangle_count == 0) return NoPrimitives;
+    if (rtbvh_gpu_device_count() == 0) return fail("no CUDA device: the builders run on the GPU only (no CPU fallback)");
+    auto s = std::make_shared<Scene>();
+    RTB_CUDA(cudaGetDevice(&s->device));
+    RTB_CUDA(cudaMalloc(&s->d_overflow, sizeof(uint32_t)));
+    RTB_CUDA(cudaMemset(s->d_overflow, 0, sizeof(uint32_t)));
+    RTB_CUDA(cudaMalloc(&s->d_counters, kCounterSlots * sizeof(unsigned long long)));
+    ResidentTrees rt;
+    const ResultCode rc = gpu_build_resident(vertices, on_device, vertex_stride, triangle_count, prims_per_leaf, (uint32_t)type,
+                                             want_mbvh != 0, &rt);
+    s->d_bvh_nodes = rt.d_nodes;  // owned by the scene from here on (freed by ~Scene also on the error paths below)
+    s->d_idx_bvh = rt.d_indices;
+    s->d_mbvh_nodes = rt.d_mnodes;
+    s->d_idx_mbvh = rt.d_mnodes ? rt.d_indices : nullptr;
+    s->d_refit_verts = rt.d_vertices;
+    s->refit_verts_bytes = rt.d_vertices ? triangle_count * 3 * vertex_stride : 0;
+    if (rc != Ok) return rc;
+    s->tri_count = (uint32_t)triangle_count;
+    const float* d_verts = on_device ? vertices : rt.d_vertices;
+    RTB_CUDA(cudaMalloc((void**)&s->d_tris_bvh, (size_t)rt.index_count * sizeof(TriRec)));
+    RTB_CUDA(launch_gather_tris(d_verts, (uint32_t)(vertex_stride / 4), rt.d_indices, rt.index_count, (uint32_t)triangle_count,
+                                s->d_tris_bvh, 0));
+    s->bvh = DeviceTree{(const float4*)s->d_bvh_nodes, rt.node_count, s->d_tris_bvh, rt.index_count};
+    if (rt.d_mnodes) {
+        s->d_tris_mbvh = s->d_tris_bvh;
+        s->mbvh = DeviceTree{(const float4*)s->d_mbvh_nodes, rt.m_count, s->d_tris_mbvh, rt.index_count};
+    }
+    float4 root[2];
+    RTB_CUDA(cudaMemcpy(root, s->d_bvh_nodes, 32, cudaMemcpyDeviceToHost));  // also drains the gather
+    s->bounds[0] = root[0].x; s->bounds[1] = root[0].y; s->bounds[2] = root[0].z;
+    s->bounds[3] = root[1].x; s->bounds[4] = root[1].y; s->bounds[5] = root[1].z;
+    std::unique_lock<std::shared_mutex> lk(g_scenes.mu);
+    g_scenes.scenes.push_back(s);
+    *scene = (RTGpuScene)g_scenes.scenes.size();
+    return Ok;
+}
+ResultCode rtbvh_gpu_scene_build(const float* vertices, size_t vertex_stride, size_t triangle_count, size_t prims_per_leaf,
+                                 BvhType type, int want_mbvh, RTGpuScene* scene) {
+    return scene_build_common(vertices, false, vertex_stride, triangle_count, prims_per_leaf, type, want_mbvh, scene);
+}
+ResultCode rtbvh_gpu_scene_build_device(const float* d_vertices, size_t vertex_stride, size_t triangle_count,
+                                        size_t prims_per_leaf, BvhType type, int want_mbvh, RTGpuScene* scene) {
+    return scene_build_common(d_vertices, true, vertex_stride, triangle_count, prims_per_leaf, type, want_mbvh, scene);
+}
+ResultCode rtbvh_gpu_scene_tree_size(RTGpuScene h, RTTreeKind tree, uint32_t* node_count, uint32_t* index_count) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    if (node_count) *node_count = t->node_count;
+    if (index_count) *index_count = t->index_count;
+    return Ok;
+}
+ResultCode rtbvh_gpu_scene_read_indices(RTGpuScene h, RTTreeKind tree, uint32_t* out, size_t count) {
+    auto s = get_scene(h);
+    if (!s || !out) return fail("unknown scene / null buffer");
+    const DeviceTree* t = pick_tree(*s, tree);
+    const uint32_t* d = tree == RT_TREE_MBVH ? s->d_idx_mbvh : s->d_idx_bvh;
+    if (!t || !d) return fail("scene has no such tree");
+    if (count != t->index_count) return fail("rtbvh_gpu_scene_read_indices: count must equal the tree's index_count");
+    RTB_CUDA(cudaSetDevice(s->device));
+    RTB_CUDA(cudaMemcpy(out, d, count * 4, cudaMemcpyDeviceToHost));
+    return Ok;
+}
+
 // ---- dynamic scenes ------------------------------------------------------------------------------
 static ResultCode scene_refit_on(Scene& s, const float* d_vertices, size_t vertex_stride, size_t triangle_count, cudaStream_t st) {
     if (vertex_stride != 12 && vertex_stride != 16) return fail("vertex_stride must be 12 or 16 bytes");

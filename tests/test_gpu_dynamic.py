@@ -86,3 +86,39 @@ def test_scene_refit_rejects_what_it_cannot_do(A, O, W):
     rays = W.random_rays(5_000, *W.bounds(moved))
     assert np.array_equal(sb.intersect(rays, A.TREE_BVH), O.trace(want, moved, rays)[0])
     sb.free()
+
+
+@pytest.mark.parametrize("kind", ["sah", "locb"])
+def test_scene_build_resident_equals_host_mirrored_build(A, O, W, kind):
+    """rtbvh_gpu_scene_build: the trees never leave the device, yet they are the trees create_bvh + create_mbvh produce,
+    and tracing them gives what the oracle gets on the oracle-built tree."""
+    import torch
+    tris = W.soup(40_000, seed=W.SEED_SOUP + 21)
+    btype = A.BINNED_SAH if kind == "sah" else A.LOCALLY_ORDERED_CLUSTERED
+    host_bvh = A.build_triangles(tris, btype, 2)
+    host_m = A.Mbvh.construct(host_bvh)
+    sc = A.Scene.build(tris, btype, 2, mbvh=True)
+    d_verts = torch.from_numpy(tris.reshape(-1).copy()).cuda()
+    sd = A.Scene.build(d_verts, btype, 2, mbvh=True, n_tris=len(tris))
+    try:
+        for s in (sc, sd):
+            assert s.n_nodes == host_bvh.rt.node_count and s.n_mnodes == host_m.rt.node_count
+            assert s.read_nodes(A.TREE_BVH).tobytes() == host_bvh.nodes.tobytes()
+            assert s.read_nodes(A.TREE_MBVH).tobytes() == host_m.nodes.tobytes()
+            assert np.array_equal(s.read_indices(A.TREE_BVH), host_bvh.indices)
+        aabbs, centers = O.prims_from_triangles(tris)
+        rc, obvh = O.build(O.BINNED_SAH if kind == "sah" else O.LOCB, aabbs, centers, 2)
+        om = obvh.collapse()
+        rays = np.concatenate([W.camera_rays(W.soup_camera(200, 200)), W.random_rays(30_000, *W.bounds(tris))])
+        for tree, otree in ((A.TREE_BVH, obvh), (A.TREE_MBVH, om)):
+            assert np.array_equal(sc.intersect(rays, tree), O.trace(otree, tris, rays)[0])
+            assert np.array_equal(sd.occluded(rays, tree), O.trace(otree, tris, rays, mode="any")[0])
+        # a resident scene refits like any other
+        moved = _wobble(tris, 2)
+        sc.refit(moved)
+        want = obvh.refit(O.prims_from_triangles(moved)[0])
+        assert np.array_equal(sc.intersect(rays, A.TREE_MBVH), O.trace(want.collapse(), moved, rays)[0])
+    finally:
+        sc.free(); sd.free(); host_m.free(); host_bvh.free()
+    with pytest.raises(A.RtbvhError):
+        A.Scene.build(np.zeros((0, 3, 3), np.float32))
