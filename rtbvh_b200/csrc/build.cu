@@ -676,16 +676,68 @@ struct SmallEntry {
     Box box;
 };
 constexpr int kSmallWarps = 4;
-__global__ void __launch_bounds__(kSmallWarps * 32) sah_small_kernel(const SmallTask* __restrict__ tasks, uint32_t S,
+#ifndef RTB_SMALL_MINBLOCKS
+#define RTB_SMALL_MINBLOCKS 8  // 64 registers: the kernel is latency-bound, resident warps matter more than registers
+#endif
+__device__ __forceinline__ Box shfl_box(const Box& b, int src) {
+    Box r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        r.mn[k] = __shfl_sync(0xFFFFFFFFu, b.mn[k], src);
+        r.mx[k] = __shfl_sync(0xFFFFFFFFu, b.mx[k], src);
+    }
+    return r;
+}
+// One candidate split (axis ax, bins < sidx go left) over the primitives [b, e) of the warp's shared-memory tile:
+// lo = {min xyz, packed bin ids}, hi = {max xyz, primitive id}.
+__device__ __forceinline__ float small_candidate(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t b,
+                                                 uint32_t e, int ax, uint32_t sidx, Box& L, Box& R) {
+    L = box_empty();
+    R = box_empty();
+    uint32_t cl = 0, cr = 0;
+    for (uint32_t j = b; j < e; j++) {
+        const float4 l4 = lo[j], h4 = hi[j];
+        const Box pb{{l4.x, l4.y, l4.z}, {h4.x, h4.y, h4.z}};
+        const uint32_t bj = (__float_as_uint(l4.w) >> (8 * ax)) & 0xFFu;
+        if (bj < sidx) {
+            L = box_union(L, pb);
+            cl++;
+        } else {
+            R = box_union(R, pb);
+            cr++;
+        }
+    }
+    return fadd(fmul(box_half_area(L), (float)cl), fmul(box_half_area(R), (float)cr));
+}
+// find_split over the 15 candidates held by one aligned 16-lane group (lane & 15 = split - 1; lane 15 of the group holds
+// no candidate): first strict minimum below f32::MAX in order s = 1..15 (binned_sah.rs:95-111).  All lanes of the group
+// return the group's (cost, count).
+__device__ __forceinline__ void small_argmin16(float cost, int lane, float& best_cost, uint32_t& best_count) {
+    uint32_t cnt = (uint32_t)(lane & 15) + 1u;
+    if ((lane & 15) == 15 || !(cost < FLT_MAX)) {
+        cost = FLT_MAX;
+        cnt = (uint32_t)kBins;
+    }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) {
+        const float oc = __shfl_xor_sync(0xFFFFFFFFu, cost, off);
+        const uint32_t oi = __shfl_xor_sync(0xFFFFFFFFu, cnt, off);
+        if (oc < cost || (oc == cost && oi < cnt)) {
+            cost = oc;
+            cnt = oi;
+        }
+    }
+    best_cost = cost;
+    best_count = cnt;
+}
+__global__ void __launch_bounds__(kSmallWarps * 32, RTB_SMALL_MINBLOCKS) sah_small_kernel(const SmallTask* __restrict__ tasks, uint32_t S,
                                                                       uint32_t* __restrict__ idx, const float4* __restrict__ bb,
                                                                       const float* __restrict__ cen, uint32_t cstride,
                                                                       float4* nodes, uint32_t max_leaf,
                                                                       uint32_t* __restrict__ used_nodes) {
-    __shared__ Box s_box[kSmallWarps][32];
+    __shared__ float4 s_lo[kSmallWarps][32];  // min xyz | packed bin ids of the node being split
+    __shared__ float4 s_hi[kSmallWarps][32];  // max xyz | primitive id
     __shared__ float s_cen[kSmallWarps][32][3];
-    __shared__ uint32_t s_idx[kSmallWarps][32];
-    __shared__ uint32_t s_bin[kSmallWarps][32];  // 3 x 8-bit bin ids
-    __shared__ float s_cost[kSmallWarps][48];
     __shared__ SmallEntry s_stack[kSmallWarps][34];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x * kSmallWarps + w;
@@ -694,8 +746,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32) sah_small_kernel(const Small
     const uint32_t n = task.end - task.begin;
     if ((uint32_t)lane < n) {
         const uint32_t p = idx[task.begin + lane];
-        s_idx[w][lane] = p;
-        s_box[w][lane] = load_box(bb, p);
+        const float4 l4 = bb[(size_t)p * 2], h4 = bb[(size_t)p * 2 + 1];
+        s_lo[w][lane] = make_float4(l4.x, l4.y, l4.z, 0.f);
+        s_hi[w][lane] = make_float4(h4.x, h4.y, h4.z, __uint_as_float(p));
         for (int k = 0; k < 3; k++) s_cen[w][lane][k] = cen[(size_t)p * cstride + k];
     }
     int sp = 0;
@@ -724,61 +777,44 @@ __global__ void __launch_bounds__(kSmallWarps * 32) sah_small_kernel(const Small
         if (in) {
 #pragma unroll
             for (int k = 0; k < 3; k++) mybins |= (uint32_t)bin_index(s_cen[w][lane][k], k3[k], off3[k]) << (8 * k);
-            s_bin[w][lane] = mybins;
+            s_lo[w][lane].w = __uint_as_float(mybins);
         }
         __syncwarp();
-        // 45 candidates (3 axes x split positions 1..15): lane c and lane c + 32
-        for (int cid = lane; cid < 45; cid += 32) {
-            const int ax = cid / 15;
-            const uint32_t sidx = (uint32_t)(cid % 15) + 1u;
-            Box L = box_empty(), R = box_empty();
-            uint32_t cl = 0, cr = 0;
-            for (uint32_t j = e.b; j < e.e; j++) {
-                const uint32_t bj = (s_bin[w][j] >> (8 * ax)) & 0xFFu;
-                if (bj < sidx) {
-                    L = box_union(L, s_box[w][j]);
-                    cl++;
-                } else {
-                    R = box_union(R, s_box[w][j]);
-                    cr++;
-                }
-            }
-            s_cost[w][cid] = fadd(fmul(box_half_area(L), (float)cl), fmul(box_half_area(R), (float)cr));
-        }
-        __syncwarp();
-        // find_split per axis: first strict minimum below f32::MAX in order s = 1..15 (binned_sah.rs:95-111)
-        float bc = FLT_MAX;
-        uint32_t bcount = (uint32_t)kBins;
-        if (lane < 3) {
-            for (int i = 0; i < 15; i++) {
-                const float c = s_cost[w][lane * 15 + i];
-                if (c < bc) {
-                    bc = c;
-                    bcount = (uint32_t)i + 1u;
-                }
-            }
-        }
+        // 45 candidates (3 axes x split positions 1..15) in two rounds: lanes 0-15 / 16-31 hold axes 0 / 1, then lanes
+        // 0-15 hold axis 2; lane 15 of a group holds nothing.  Every lane keeps the child boxes of its candidates.
+        Box L1, R1, L2, R2;
+        float c1 = FLT_MAX, c2 = FLT_MAX;
+        L1 = R1 = L2 = R2 = box_empty();
+        if ((lane & 15) != 15) c1 = small_candidate(s_lo[w], s_hi[w], e.b, e.e, lane >> 4, (uint32_t)(lane & 15) + 1u, L1, R1);
+        if (lane < 15) c2 = small_candidate(s_lo[w], s_hi[w], e.b, e.e, 2, (uint32_t)lane + 1u, L2, R2);
+        float bc1, bc2;
+        uint32_t bn1, bn2;
+        small_argmin16(c1, lane, bc1, bn1);
+        small_argmin16(c2, lane, bc2, bn2);
         float best_cost[3];
         uint32_t best_count[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            best_cost[k] = __shfl_sync(0xFFFFFFFFu, bc, k);
-            best_count[k] = __shfl_sync(0xFFFFFFFFu, bcount, k);
-        }
+        best_cost[0] = __shfl_sync(0xFFFFFFFFu, bc1, 0);
+        best_count[0] = __shfl_sync(0xFFFFFFFFu, bn1, 0);
+        best_cost[1] = __shfl_sync(0xFFFFFFFFu, bc1, 16);
+        best_count[1] = __shfl_sync(0xFFFFFFFFu, bn1, 16);
+        best_cost[2] = __shfl_sync(0xFFFFFFFFu, bc2, 0);
+        best_count[2] = __shfl_sync(0xFFFFFFFFu, bn2, 0);
         int best_axis = 0;
         if (best_cost[0] > best_cost[1]) best_axis = 1;
         if ((best_axis == 0 ? best_cost[0] : best_cost[1]) > best_cost[2]) best_axis = 2;
         uint32_t split_index = best_axis == 0 ? best_count[0] : (best_axis == 1 ? best_count[1] : best_count[2]);
         const float axis_cost = best_axis == 0 ? best_cost[0] : (best_axis == 1 ? best_cost[1] : best_cost[2]);
         const float max_split_cost = fmul(box_half_area(nb), fsub((float)nn, 1.0f));
-        bool do_split = true;
+        bool do_split = true, fallback = false;
         if (split_index == (uint32_t)kBins || axis_cost >= max_split_cost) {
             if (nn > max_leaf) {  // fallback (binned_sah.rs:189-205)
+                fallback = true;
                 best_axis = box_longest_axis(nb);
                 // per-bin counts on that axis: lane b < 16 counts the primitives of bin b
                 uint32_t cnt = 0;
                 if (lane < kBins)
-                    for (uint32_t j = e.b; j < e.e; j++) cnt += (((s_bin[w][j] >> (8 * best_axis)) & 0xFFu) == (uint32_t)lane) ? 1u : 0u;
+                    for (uint32_t j = e.b; j < e.e; j++)
+                        cnt += (((__float_as_uint(s_lo[w][j].w) >> (8 * best_axis)) & 0xFFu) == (uint32_t)lane) ? 1u : 0u;
                 uint32_t cum = cnt;
 #pragma unroll
                 for (int o = 1; o < kBins; o <<= 1) {
@@ -802,24 +838,35 @@ __global__ void __launch_bounds__(kSmallWarps * 32) sah_small_kernel(const Small
             if (lane == 0) make_leaf(nodes, e.node, nb, task.begin + e.b, nn);
             continue;
         }
-        // child boxes; quirk Q3: the left box uses the SAH split count of the final axis
-        const uint32_t q3 = best_axis == 0 ? best_count[0] : (best_axis == 1 ? best_count[1] : best_count[2]);
-        const Box mine = in ? s_box[w][lane] : box_empty();
-        const Box lb = warp_union((in && mybin < q3) ? mine : box_empty());
-        const Box rb = warp_union((in && mybin >= split_index) ? mine : box_empty());
+        // child boxes.  Regular split: the lane that evaluated the winning candidate already holds them.  Fallback:
+        // quirk Q3 — the left box uses the SAH split count of the final axis, the right box the fallback index.
+        Box lb, rb;
+        if (!fallback) {
+            const int src = best_axis < 2 ? 16 * best_axis + (int)split_index - 1 : (int)split_index - 1;
+            lb = shfl_box(best_axis < 2 ? L1 : L2, src);
+            rb = shfl_box(best_axis < 2 ? R1 : R2, src);
+        } else {
+            const uint32_t q3 = best_axis == 0 ? best_count[0] : (best_axis == 1 ? best_count[1] : best_count[2]);
+            const float4 l4 = s_lo[w][lane], h4 = s_hi[w][lane];
+            const Box mine = in ? Box{{l4.x, l4.y, l4.z}, {h4.x, h4.y, h4.z}} : box_empty();
+            lb = warp_union((in && mybin < q3) ? mine : box_empty());
+            rb = warp_union((in && mybin >= split_index) ? mine : box_empty());
+        }
         // stable partition of [b, e) inside the warp
         const uint32_t lt = (1u << lane) - 1u;
         uint32_t dest = (uint32_t)lane;
         if (in) dest = goes_left ? e.b + (uint32_t)__popc(lmask & lt) : e.b + nleft + (uint32_t)__popc((inmask & ~lmask) & lt);
-        const Box mybox = mine;
-        const uint32_t myidx = in ? s_idx[w][lane] : 0u;
+        float4 mylo = make_float4(0.f, 0.f, 0.f, 0.f), myhi = mylo;
         float myc[3] = {0.f, 0.f, 0.f};
-        if (in)
+        if (in) {
+            mylo = s_lo[w][lane];
+            myhi = s_hi[w][lane];
             for (int k = 0; k < 3; k++) myc[k] = s_cen[w][lane][k];
+        }
         __syncwarp();
         if (in) {
-            s_box[w][dest] = mybox;
-            s_idx[w][dest] = myidx;
+            s_lo[w][dest] = mylo;
+            s_hi[w][dest] = myhi;
             for (int k = 0; k < 3; k++) s_cen[w][dest][k] = myc[k];
         }
         const uint32_t left = next_free;
@@ -849,7 +896,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) sah_small_kernel(const Small
         sp += (r_leaf ? 0 : 1) + (l_leaf ? 0 : 1);
         __syncwarp();
     }
-    if ((uint32_t)lane < n) idx[task.begin + lane] = s_idx[w][lane];
+    if ((uint32_t)lane < n) idx[task.begin + lane] = __float_as_uint(s_hi[w][lane].w);
     if (lane == 0) used_nodes[t] = next_free - task.node_base;
 }
 
