@@ -92,6 +92,9 @@ ResultCode rtbvh_gpu_scene_build_device(const float *d_vertices, size_t vertex_s
                                         size_t prims_per_leaf, BvhType type, int want_mbvh, RTGpuScene *scene);
 ResultCode rtbvh_gpu_scene_tree_size(RTGpuScene scene, RTTreeKind tree, uint32_t *node_count, uint32_t *index_count);
 ResultCode rtbvh_gpu_scene_read_indices(RTGpuScene scene, RTTreeKind tree, uint32_t *out, size_t count);
+/* The builders keep one device workspace per host thread between calls (it only grows: a 30 M-triangle build leaves
+ * ~7 GB reserved) so that repeated builds never wait for the allocator; this gives it back. */
+ResultCode rtbvh_gpu_trim_workspace(void);
 /* Dynamic scenes (the step after build for animated geometry; Bvh::refit src/bvh.rs:176-205, FFI refit
  * rtbvh_ffi/src/lib.rs:519-538).  New vertex positions for the SAME triangles (same count and order): recomputes the
  * per-triangle boxes (Triangle::aabb, un-padded), refits the scene's Bvh in place (leaf = union of its primitives'

@@ -51,7 +51,7 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_intersect_device_scatter", "rtbvh_gpu_occluded_device_scatter", "rtbvh_gpu_peer_barrier",
                "rtbvh_gpu_intersect_async", "rtbvh_gpu_occluded_async", "rtbvh_gpu_wait", "rtbvh_gpu_host_alloc",
                "rtbvh_gpu_host_free", "rtbvh_gpu_scene_refit", "rtbvh_gpu_scene_refit_device", "rtbvh_gpu_scene_read_nodes",
-               "rtbvh_gpu_scene_build", "rtbvh_gpu_scene_build_device", "rtbvh_gpu_scene_tree_size", "rtbvh_gpu_scene_read_indices")
+               "rtbvh_gpu_trim_workspace", "rtbvh_gpu_scene_build", "rtbvh_gpu_scene_build_device", "rtbvh_gpu_scene_tree_size", "rtbvh_gpu_scene_read_indices")
 
 
 class RTBvh(C.Structure):  # rtbvh_ffi/src/lib.rs:210-220
@@ -545,6 +545,12 @@ def device_view(ptr: int, nbytes: int):
     """A torch uint8 tensor aliasing raw device memory (e.g. a gather buffer), for stream-ordered consumers."""
     import torch
     return torch.as_tensor(_DevView(ptr, nbytes), device="cuda")
+
+
+def trim_workspace():
+    """Frees this thread's builder workspace (rtbvh_gpu_trim_workspace)."""
+    lib().rtbvh_gpu_trim_workspace.restype = C.c_int
+    _check(lib().rtbvh_gpu_trim_workspace())
 
 
 def peer_barrier(flag_arrays: list[int], rank: int, value: int, stream: int = 0):

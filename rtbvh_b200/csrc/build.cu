@@ -30,6 +30,9 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -228,6 +231,8 @@ struct Task {
 };
 struct TaskAux {
     float k[3], off[3];  // center_to_bin, bin_offset (binned_sah.rs:146-147)
+    uint32_t slot;       // span-class tasks (> kWarpTask primitives): which 3 x 16 bin block in HBM is theirs this level
+    uint32_t pad;
 };
 struct Decision {
     uint32_t split;        // 1: node becomes inner
@@ -248,10 +253,12 @@ struct LevelState {
 
 // Entry of BinnedSahBuildTask::run (binned_sah.rs:133-147): pad the node box, compute the binning transform.  Every
 // task has >= 2 primitives and depth < 64 (children that are leaves on entry are finalised by emit_kernel).
-__device__ __forceinline__ Box task_enter(float4* nodes, uint32_t node, Box b, TaskAux* aux_slot) {
+__device__ __forceinline__ Box task_enter(float4* nodes, uint32_t node, Box b, TaskAux* aux_slot, uint32_t bin_slot) {
     box_pad(b, kPad);
     store_node(nodes, node, b, 0, 0);
     TaskAux a;
+    a.slot = bin_slot;
+    a.pad = 0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         a.k[k] = fmul(fdiv(1.0f, fsub(b.mx[k], b.mn[k])), (float)kBins);
@@ -263,7 +270,7 @@ __device__ __forceinline__ Box task_enter(float4* nodes, uint32_t node, Box b, T
 // Level 0: the root task (node 0 already holds union_of_list of the primitives).
 __global__ void sah_root_task_kernel(float4* nodes, uint32_t n, Task* tasks, TaskAux* aux, LevelState* state) {
     tasks[0] = Task{0u, 0u, n};
-    task_enter(nodes, 0, load_box(nodes, 0), &aux[0]);
+    task_enter(nodes, 0, load_box(nodes, 0), &aux[0], 0u);
     state[0] = LevelState{1u, 1u, 0u, 0u};
 }
 
@@ -328,7 +335,7 @@ __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __re
         if (uni != cur) {
             if (cur >= 0) {
                 __syncthreads();
-                bins_smem_flush(sb, bins + (size_t)cur * kTaskBinWords);
+                bins_smem_flush(sb, bins + (size_t)aux[cur].slot * kTaskBinWords);
             }
             __syncthreads();
             if (uni >= 0) bins_smem_init(sb);
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __re
                 const uint32_t p = idx[i];
                 const TaskAux a = aux[t];
                 const Box box = load_box(bb, p);
-                uint32_t* dst = uni >= 0 ? sb : bins + (size_t)t * kTaskBinWords;
+                uint32_t* dst = uni >= 0 ? sb : bins + (size_t)a.slot * kTaskBinWords;
                 uint32_t packed = 0;
 #pragma unroll
                 for (int ax = 0; ax < 3; ax++) {
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __re
     }
     if (cur >= 0) {
         __syncthreads();
-        bins_smem_flush(sb, bins + (size_t)cur * kTaskBinWords);
+        bins_smem_flush(sb, bins + (size_t)aux[cur].slot * kTaskBinWords);
     }
 }
 
@@ -528,7 +535,8 @@ __device__ __forceinline__ void sah_split_task(const Task task, uint32_t t, int 
 // Launched for A_ub >= A warps (the host only knows an upper bound of the level's task count): warps beyond A zero
 // their counts entry so that the fixed-size scan that follows is exact.
 __global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__ tasks, uint32_t A_ub,
-                                                        uint32_t* __restrict__ bins, const float4* __restrict__ nodes,
+                                                        const TaskAux* __restrict__ aux, uint32_t* __restrict__ bins,
+                                                        const float4* __restrict__ nodes,
                                                         uint32_t max_leaf, uint32_t depth, Decision* __restrict__ dec,
                                                         uint4* __restrict__ counts, const LevelState* __restrict__ state) {
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__
     }
     const Task task = tasks[t];
     if (task.end - task.begin <= kWarpTask) return;  // sah_warp_task_kernel's
-    uint32_t* tb = bins + (size_t)t * kTaskBinWords;
+    uint32_t* tb = bins + (size_t)aux[t].slot * kTaskBinWords;
     sah_split_task(task, t, lane, tb, nodes, max_leaf, depth, dec, counts);
     // leave the bins of slot t clean for whichever task gets this index on a later level
     __syncwarp();
@@ -616,6 +624,7 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, c
                                 Task* __restrict__ next_tasks, TaskAux* __restrict__ next_aux,
                                 SmallTask* __restrict__ small_tasks,
                                 int32_t* __restrict__ child_task /* 2 per task: encoded next-level task or -1 */,
+                                uint32_t* __restrict__ span_tasks /* [depth + 1]: bin blocks handed out for the next level */,
                                 LevelState* __restrict__ state /* [depth] in, [depth + 1] out */) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const LevelState cur = state[depth];
@@ -660,7 +669,9 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, c
             small++;
             small_nodes += 2u * nc - 2u;
         } else {
-            task_enter(nodes, left + k, cb[k], &next_aux[next]);
+            // which bin block a span-class task gets is irrelevant to the result (scratch), so a counter will do
+            const uint32_t slot = nc > kWarpTask ? atomicAdd(&span_tasks[depth + 1], 1u) : 0u;
+            task_enter(nodes, left + k, cb[k], &next_aux[next], slot);
             next_tasks[next] = Task{left + k, cbeg[k], cend[k]};
             child_task[2 * t + k] = pt_encode(next++, nc);
         }
@@ -1258,49 +1269,95 @@ __global__ void refit_kernel(float4* nodes, uint32_t n_nodes, const int32_t* __r
     }
 }
 
-// ---- small RAII helpers ----------------------------------------------------------------------------
-// Stream-ordered allocations from the device's default memory pool (release threshold raised once):
-// after the first build the builders' scratch buffers come out of the pool without touching the driver.
-static void tune_pool_once() {
-    static bool done = false;
-    if (done) return;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    done = true;
+// ---- builder workspace ------------------------------------------------------------------------------
+// Every scratch and result buffer of a build is carved out of one device arena per host thread (bump pointer, reset at
+// the start of each builder entry point, grown — never shrunk — when a build needs more).  Measured on B200: the same
+// buffers taken from the stream-ordered pool (cudaMallocAsync) cost 15-3500 ms of host time per 10-30 M triangle build
+// (profiles/r2t_build_trace.txt) against 20-90 ms of kernels; from the arena they cost nothing after the first build.
+// rtbvh_gpu_trim_workspace() gives the memory back.
+static thread_local double g_alloc_host_ms = 0;  // host time spent inside cudaMalloc for the arena (RTBVH_BUILD_TRACE)
+static bool build_trace() {
+    static const bool v = std::getenv("RTBVH_BUILD_TRACE") != nullptr;
+    return v;
 }
-struct DevBuf {
+struct Arena {
+    struct Chunk {
+        char* base;
+        size_t cap, used;
+    };
+    std::vector<Chunk> chunks;
+    int device = -1;
+    ~Arena() { release(); }
+    void release() {
+        for (auto& c : chunks) cudaFree(c.base);
+        chunks.clear();
+    }
+    // Start of a builder entry point: everything handed out before is dead.  Several chunks mean the last build had to
+    // grow: merge them into one allocation of the combined size so that the steady state is a single chunk.
+    cudaError_t reset() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev != device) {
+            release();
+            device = dev;
+        }
+        if (chunks.size() > 1) {
+            size_t total = 0;
+            for (auto& c : chunks) total += c.cap;
+            release();
+            const cudaError_t e = grow(total);
+            if (e != cudaSuccess) return e;
+        }
+        for (auto& c : chunks) c.used = 0;
+        return cudaSuccess;
+    }
+    cudaError_t grow(size_t cap) {
+        Chunk c{nullptr, cap, 0};
+        const auto t0 = std::chrono::steady_clock::now();
+        const cudaError_t e = cudaMalloc((void**)&c.base, cap);
+        g_alloc_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (e == cudaSuccess) chunks.push_back(c);
+        return e;
+    }
+    cudaError_t take(size_t bytes, void** out) {
+        bytes = (bytes + 255) & ~size_t(255);
+        if (chunks.empty() || chunks.back().cap - chunks.back().used < bytes) {
+            const size_t last = chunks.empty() ? 0 : chunks.back().cap;
+            const cudaError_t e = grow(std::max({bytes, last, size_t(64) << 20}));
+            if (e != cudaSuccess) return e;
+        }
+        Chunk& c = chunks.back();
+        *out = c.base + c.used;
+        c.used += bytes;
+        return cudaSuccess;
+    }
+};
+static Arena& arena() {
+    static thread_local Arena a;
+    return a;
+}
+struct DevBuf {  // a view into the arena: nothing to free
     void* p = nullptr;
     size_t bytes = 0;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() {
-        if (p) cudaFreeAsync(p, 0);
-    }
     cudaError_t alloc(size_t b) {
-        if (b <= bytes) return cudaSuccess;
-        tune_pool_once();
-        if (p) cudaFreeAsync(p, 0);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMallocAsync(&p, b ? b : 16, 0);
-        if (e == cudaSuccess) bytes = b;
+        if (b <= bytes && p) return cudaSuccess;
+        const cudaError_t e = arena().take(b ? b : 16, &p);
+        bytes = e == cudaSuccess ? b : 0;
         return e;
     }
     template <class T>
     T* as() { return (T*)p; }
-    void* release() {  // hands the allocation to the caller (cudaFree accepts pool allocations)
-        void* q = p;
-        p = nullptr;
-        bytes = 0;
-        return q;
-    }
 };
+// A cudaMalloc'ed copy of an arena buffer, owned by the caller (the resident scene path).
+static cudaError_t detach(const DevBuf& b, size_t bytes, void** out) {
+    *out = nullptr;
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    return bytes ? cudaMemcpyAsync(*out, b.p, bytes, cudaMemcpyDeviceToDevice, 0) : cudaSuccess;
+}
 inline unsigned blocks(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
 struct Timer {
@@ -1346,7 +1403,7 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
     DevBuf nodesA;
     RTB_CUDA(nodesA.alloc((size_t)max_nodes * 32));
     float4* nodes = nodesA.as<float4>();
-    DevBuf idxB[2], ptB[2], tasksB[2], auxB[2], binidx, dec, bins, counts, ranks4, child_task, world, temp, state, params, small_tasks, used,
+    DevBuf idxB[2], ptB[2], tasksB[2], auxB[2], binidx, span_tasks, dec, bins, counts, ranks4, child_task, world, temp, state, params, small_tasks, used,
         waste, waste_prefix;
     for (int k = 0; k < 2; k++) {
         RTB_CUDA(idxB[k].alloc((size_t)n * 4));
@@ -1375,7 +1432,11 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
             RTB_CUDA(auxB[k].alloc((size_t)task_cap * sizeof(TaskAux)));
         }
         RTB_CUDA(dec.alloc((size_t)task_cap * sizeof(Decision)));
-        RTB_CUDA(bins.alloc((size_t)task_cap * kTaskBinWords * 4));
+        // only span-class tasks (> kWarpTask primitives) own a bin block in HBM: at most n / (kWarpTask + 1) per level
+        const uint32_t span_cap = n / (kWarpTask + 1) + 2;
+        RTB_CUDA(bins.alloc((size_t)span_cap * kTaskBinWords * 4));
+        RTB_CUDA(span_tasks.alloc((size_t)(kMaxDepth + 3) * 4));
+        RTB_CUDA(cudaMemsetAsync(span_tasks.p, 0, (size_t)(kMaxDepth + 3) * 4, 0));
         RTB_CUDA(counts.alloc((size_t)task_cap * sizeof(uint4)));
         RTB_CUDA(ranks4.alloc((size_t)task_cap * sizeof(uint4)));
         RTB_CUDA(child_task.alloc((size_t)task_cap * 8));
@@ -1401,7 +1462,7 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         temp_bytes = std::max(temp_bytes, tb);
         RTB_CUDA(temp.alloc(temp_bytes));
         // bins start clean and are left clean by every split (sah_split_kernel re-initialises what it has read)
-        const size_t words = (size_t)task_cap * kTaskBinWords;
+        const size_t words = (size_t)span_cap * kTaskBinWords;
         sah_bins_init_kernel<<<blocks(words, 256), 256>>>(bins.as<uint32_t>(), words);
         fill_i32_kernel<<<blocks(n, 256), 256>>>(ptB[0].as<int32_t>(), n, pt_encode(0, n));  // every position belongs to task 0
         LevelState* d_state = state.as<LevelState>();
@@ -1431,7 +1492,7 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
             const LevelState* st = d_state + depth;
             sah_bin_kernel<<<bin_grid, kBinBlock>>>(idxB[par].as<uint32_t>(), ptB[par].as<int32_t>(), n, bin_span, aux_cur, d_bb, d_cen,
                                                     cstride, bins.as<uint32_t>(), binidx.as<uint16_t>(), st);
-            sah_split_kernel<<<blocks((size_t)A_ub * 32, 128), 128>>>(t_cur, A_ub, bins.as<uint32_t>(), nodes, max_leaf, depth,
+            sah_split_kernel<<<blocks((size_t)A_ub * 32, 128), 128>>>(t_cur, A_ub, aux_cur, bins.as<uint32_t>(), nodes, max_leaf, depth,
                                                                       dec.as<Decision>(), counts.as<uint4>(), st);
             sah_warp_task_kernel<<<blocks(A_ub, kWarpTaskWarps), kWarpTaskWarps * 32>>>(t_cur, idxB[par].as<uint32_t>(), aux_cur, d_bb,
                                                                                         d_cen, cstride, nodes, max_leaf, depth,
@@ -1442,7 +1503,8 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
                                                     make_uint4(0, 0, 0, 0), (int)A_ub));
             sah_emit_kernel<<<blocks(A_ub, 128), 128>>>(t_cur, A_ub, dec.as<Decision>(), ranks4.as<uint4>(), counts.as<uint4>(), depth,
                                                         nodes, tasksB[par ^ 1].as<Task>(), auxB[par ^ 1].as<TaskAux>(),
-                                                        small_tasks.as<SmallTask>(), child_task.as<int32_t>(), d_state);
+                                                        small_tasks.as<SmallTask>(), child_task.as<int32_t>(),
+                                                        span_tasks.as<uint32_t>(), d_state);
             tbytes = temp.bytes;
             RTB_CUDA(cub::DeviceScan::InclusiveScanByKey(temp.p, tbytes, ptB[par].as<int32_t>(),
                                                          PartitionFlagIter(cub::CountingInputIterator<uint32_t>(0), PartitionFlagIn{dp + par}),
@@ -1643,6 +1705,10 @@ static ResultCode need_device() {
         cudaGetLastError();
         return fail("no CUDA device: the builders run on the GPU only (no CPU fallback)");
     }
+    // every builder entry point starts with an empty workspace (what earlier builds of this thread left in it is dead:
+    // they synchronised before returning and copied their results out)
+    const cudaError_t e = arena().reset();
+    if (e != cudaSuccess) return fail("builder workspace", e);
     return Ok;
 }
 
@@ -1719,6 +1785,10 @@ ResultCode gpu_build_bvh_triangles(const float* vertices, size_t vertex_stride, 
     g_build_stats.total_ms = total.stop();
     g_build_stats.iterations = iters;
     g_build_stats.node_count = d.node_count;
+    if (build_trace())
+        std::fprintf(stderr, "[rtbvh build] n=%u type=%u device_ms=%.3f (host time inside cudaMalloc %.3f ms) total_ms=%.3f\n", n,
+                     bvh_type, g_build_stats.device_ms, g_alloc_host_ms, g_build_stats.total_ms);
+    g_alloc_host_ms = 0;
     return rc;
 }
 
@@ -1803,17 +1873,27 @@ ResultCode gpu_build_resident(const float* vertices, bool vertices_on_device, si
     DevBuf mnodes;
     uint32_t m_count = 0;
     if (want_mbvh && collapse_device(d.nodes.as<float4>(), d.node_count, &mnodes, &m_count) != Ok) return Error;
-    g_build_stats.device_ms = dev.stop();
     g_build_stats.iterations = iters;
     g_build_stats.node_count = d.node_count;
     out->node_count = d.node_count;
     out->index_count = d.index_count;
     out->m_count = m_count;
-    out->d_nodes = d.nodes.release();
-    out->d_indices = (uint32_t*)d.indices.release();
-    out->d_mnodes = want_mbvh ? mnodes.release() : nullptr;
-    out->d_vertices = vertices_on_device ? nullptr : (float*)verts.release();
+    // the trees leave the builder's workspace: exact-size allocations owned by the scene
+    RTB_CUDA(detach(d.nodes, (size_t)d.node_count * 32, &out->d_nodes));
+    RTB_CUDA(detach(d.indices, (size_t)d.index_count * 4, (void**)&out->d_indices));
+    if (want_mbvh) RTB_CUDA(detach(mnodes, (size_t)m_count * 128, &out->d_mnodes));
+    if (!vertices_on_device) RTB_CUDA(detach(verts, (size_t)n * 3 * vertex_stride, (void**)&out->d_vertices));
+    g_build_stats.device_ms = dev.stop();
     g_build_stats.total_ms = total.stop();
+    if (build_trace())
+        std::fprintf(stderr, "[rtbvh build] resident n=%u type=%u device_ms=%.3f (host time inside cudaMalloc %.3f ms) total_ms=%.3f\n",
+                     n, bvh_type, g_build_stats.device_ms, g_alloc_host_ms, g_build_stats.total_ms);
+    g_alloc_host_ms = 0;
+    return Ok;
+}
+
+ResultCode gpu_trim_workspace() {
+    arena().release();
     return Ok;
 }
 

@@ -53,6 +53,9 @@ struct ResidentTrees {
 ResultCode gpu_build_resident(const float* vertices, bool vertices_on_device, size_t vertex_stride, size_t tri_count,
                               size_t prims_per_leaf, uint32_t bvh_type, bool want_mbvh, ResidentTrees* out);
 
+// Frees the calling thread's builder workspace (it is otherwise kept between builds and only ever grows).
+ResultCode gpu_trim_workspace();
+
 // Dynamic scenes: refit of a device-resident Bvh (+ refresh of its Mbvh) from new vertex positions,
 // everything on `stream`.  The cache holds what does not change under refit (parent links, the binary node behind every
 // MbvhNode) plus scratch; it belongs to one tree pair.

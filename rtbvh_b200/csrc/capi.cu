@@ -573,6 +573,8 @@ ResultCode rtbvh_gpu_scene_read_indices(RTGpuScene h, RTTreeKind tree, uint32_t*
     return Ok;
 }
 
+ResultCode rtbvh_gpu_trim_workspace(void) { return gpu_trim_workspace(); }
+
 // ---- dynamic scenes ------------------------------------------------------------------------------
 static ResultCode scene_refit_on(Scene& s, const float* d_vertices, size_t vertex_stride, size_t triangle_count, cudaStream_t st) {
     if (vertex_stride != 12 && vertex_stride != 16) return fail("vertex_stride must be 12 or 16 bytes");
