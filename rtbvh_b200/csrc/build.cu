@@ -234,6 +234,12 @@ struct TaskAux {
     uint32_t slot;       // span-class tasks (> kWarpTask primitives): which 3 x 16 bin block in HBM is theirs this level
     uint32_t pad;
 };
+struct alignas(32) PartTask {  // everything the partition needs to know about a task, one 32-byte sector (written by emit)
+    uint32_t begin, nleft;         // nleft == 0: the task did not split (a split always has 0 < nleft < n)
+    int32_t child_left, child_right;  // encoded next-level task of each side, -1 if that child needs no further level pass
+    uint32_t shift, split_index;   // predicate: ((binidx >> shift) & 15) < split_index; split_index == 0: no split
+    uint32_t pad[2];
+};
 struct Decision {
     uint32_t split;        // 1: node becomes inner
     uint32_t axis;         // final best_axis
@@ -268,10 +274,12 @@ __device__ __forceinline__ Box task_enter(float4* nodes, uint32_t node, Box b, T
     return b;
 }
 // Level 0: the root task (node 0 already holds union_of_list of the primitives).
-__global__ void sah_root_task_kernel(float4* nodes, uint32_t n, Task* tasks, TaskAux* aux, LevelState* state) {
+__global__ void sah_root_task_kernel(float4* nodes, uint32_t n, Task* tasks, TaskAux* aux, LevelState* state,
+                                     uint32_t* span_tasks) {
     tasks[0] = Task{0u, 0u, n};
     task_enter(nodes, 0, load_box(nodes, 0), &aux[0], 0u);
     state[0] = LevelState{1u, 1u, 0u, 0u};
+    span_tasks[0] = n > kWarpTask ? 1u : 0u;
 }
 
 __global__ void sah_bins_init_kernel(uint32_t* __restrict__ bins, size_t words) {
@@ -296,16 +304,53 @@ __device__ __forceinline__ void bin_accumulate(uint32_t* b, const Box& box) {
 // atomics instead of (n / 256) x 336.  Chunks that straddle tasks fall back to direct global atomics (deep
 // levels: small tasks, low contention).
 constexpr int kBinBlock = 256;
-__device__ __forceinline__ void bins_smem_init(uint32_t* sb) {
-    for (int w = threadIdx.x; w < kTaskBinWords; w += kBinBlock) {
-        const int f = w % kBinWords;
+// Runs at least this long get lane-private bin copies (42 KB to init and fold per run; 384 measured slower than 1024).
+constexpr uint32_t kLanePrivateRun = 1024;
+// Fill bins with primitives (binned_sah.rs:157-172) for the span-class tasks (> kWarpTask primitives) of the level.
+// Every block owns a contiguous span of index positions and walks it RUN by run (a run = the part of one task's range
+// inside the span; the task table gives its end, so no search).  A run is accumulated in shared memory and folded into
+// the task's bin block in HBM with 336 atomics, so a primitive never costs a global atomic.  With ONE copy of the
+// 3 x 16 bins the 21 shared-memory atomics of a primitive collide inside the warp (32 lanes on 16 bins, ~5 replays each:
+// measured 77 ns per primitive and level at 10 M triangles); long runs therefore use a private copy per LANE — entry e
+// of lane l at sb[e * 32 + l]: one instruction touches 32 different banks and never the same address twice — which
+// brought the root level of a 10 M build from 776 to 122 us.  Short runs keep the single copy (cheap to init and fold).
+template <int COPIES>
+__device__ __forceinline__ void bin_run(uint32_t* sb, uint32_t pos, uint32_t run_end, const TaskAux& a,
+                                        const uint32_t* __restrict__ idx, const float4* __restrict__ bb,
+                                        const float* __restrict__ cen, uint32_t cstride, uint32_t* __restrict__ g,
+                                        uint16_t* __restrict__ binidx) {
+    const unsigned lane = COPIES == 32 ? (threadIdx.x & 31u) : 0u;
+    for (int w = threadIdx.x; w < kTaskBinWords * COPIES; w += kBinBlock) {
+        const int f = (w / COPIES) % kBinWords;
         sb[w] = f < 3 ? fkey(1e34f) : (f < 6 ? fkey(-1e34f) : 0u);
     }
-}
-__device__ __forceinline__ void bins_smem_flush(const uint32_t* sb, uint32_t* g) {
+    __syncthreads();
+    for (uint32_t i = pos + threadIdx.x; i < run_end; i += kBinBlock) {
+        const uint32_t p = idx[i];
+        const Box box = load_box(bb, p);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+            const int b = bin_index(cen[(size_t)p * cstride + ax], a.k[ax], a.off[ax]);
+            uint32_t* e = &sb[((ax * kBins + b) * kBinWords) * COPIES + lane];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                atomicMin(e + k * COPIES, fkey(box.mn[k]));
+                atomicMax(e + (3 + k) * COPIES, fkey(box.mx[k]));
+            }
+            atomicAdd(e + 6 * COPIES, 1u);
+            packed |= (uint32_t)b << (4 * ax);
+        }
+        binidx[i] = (uint16_t)packed;  // the partition pass reads this instead of gathering the centroid again
+    }
+    __syncthreads();
     for (int w = threadIdx.x; w < kTaskBinWords; w += kBinBlock) {
         const int f = w % kBinWords;
-        const uint32_t v = sb[w];
+        uint32_t v = f < 3 ? fkey(1e34f) : (f < 6 ? fkey(-1e34f) : 0u);
+        for (unsigned k = 0; k < (unsigned)COPIES; k++) {
+            const uint32_t c = sb[w * COPIES + ((threadIdx.x + k) & (COPIES - 1))];  // rotated: conflict-free across the warp
+            v = f < 3 ? min(v, c) : (f < 6 ? max(v, c) : v + c);
+        }
         if (f < 3) {
             if (v != fkey(1e34f)) atomicMin(&g[w], v);
         } else if (f < 6) {
@@ -314,56 +359,49 @@ __device__ __forceinline__ void bins_smem_flush(const uint32_t* sb, uint32_t* g)
             atomicAdd(&g[w], v);
         }
     }
+    __syncthreads();
 }
+// PRIV = false: the small-build variant without the lane-private path (1.3 KB instead of 42 KB of shared memory per block,
+// 8 instead of 5 blocks per SM): below a few M primitives a block sees too few primitives per run for the copies to pay
+// (measured at 1 Mi triangles: 0.55 ms per build for this variant, 0.71-0.77 ms with lane-private runs).
+template <bool PRIV>
 __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __restrict__ idx, const int32_t* __restrict__ pos_task,
-                                                            uint32_t n, uint32_t span, const TaskAux* __restrict__ aux,
-                                                            const float4* __restrict__ bb, const float* __restrict__ cen,
-                                                            uint32_t cstride, uint32_t* __restrict__ bins,
+                                                            uint32_t n, uint32_t span, const Task* __restrict__ tasks,
+                                                            const TaskAux* __restrict__ aux, const float4* __restrict__ bb,
+                                                            const float* __restrict__ cen, uint32_t cstride,
+                                                            uint32_t* __restrict__ bins,
                                                             uint16_t* __restrict__ binidx /* 3 x 4-bit bin per position */,
-                                                            const LevelState* __restrict__ state) {
-    __shared__ uint32_t sb[kTaskBinWords];
+                                                            const LevelState* __restrict__ state,
+                                                            const uint32_t* __restrict__ span_tasks /* of this level */) {
+    __shared__ uint32_t sb[kTaskBinWords * (PRIV ? 32 : 1)];
+    __shared__ uint32_t s_next;
     const uint64_t begin64 = (uint64_t)blockIdx.x * span;
-    if (begin64 >= n || state->A == 0) return;
-    const uint32_t begin = (uint32_t)begin64;
+    if (begin64 >= n || state->A == 0 || *span_tasks == 0) return;  // deep levels: only warp-class tasks are left
     const uint32_t end = (uint32_t)min((uint64_t)n, begin64 + span);
-    int cur = -1;  // task whose bins live in shared memory (block-uniform)
-    for (uint32_t c0 = begin; c0 < end; c0 += kBinBlock) {
-        const uint32_t c1 = min(c0 + kBinBlock, end);
-        const int32_t ta = pos_task[c0], tb = pos_task[c1 - 1];
-        if (ta == tb && ta < -1) continue;  // the whole chunk belongs to one warp-class task (block-uniform decision)
-        const int uni = (ta == tb && ta >= 0) ? ta : -1;  // ranges are contiguous: equal ends => one task
-        if (uni != cur) {
-            if (cur >= 0) {
-                __syncthreads();
-                bins_smem_flush(sb, bins + (size_t)aux[cur].slot * kTaskBinWords);
-            }
+    uint32_t pos = (uint32_t)begin64;
+    while (pos < end) {  // every decision below is block-uniform
+        const int32_t pt = pos_task[pos];
+        if (pt >= 0) {  // span-class task: bin the run
+            const uint32_t run_end = min(end, tasks[pt].end);
+            const TaskAux a = aux[pt];
+            uint32_t* g = bins + (size_t)a.slot * kTaskBinWords;
+            if (PRIV && run_end - pos >= kLanePrivateRun)
+                bin_run<PRIV ? 32 : 1>(sb, pos, run_end, a, idx, bb, cen, cstride, g, binidx);
+            else
+                bin_run<1>(sb, pos, run_end, a, idx, bb, cen, cstride, g, binidx);
+            pos = run_end;
+        } else if (pt < -1) {  // warp-class task (sah_warp_task_kernel's): skip its range
+            pos = min(end, tasks[-2 - pt].end);
+        } else {  // finished positions carry no range: find the next live one in this chunk
+            const uint32_t c1 = min(pos + kBinBlock, end);
+            if (threadIdx.x == 0) s_next = c1;
             __syncthreads();
-            if (uni >= 0) bins_smem_init(sb);
+            const uint32_t i = pos + threadIdx.x;
+            if (i < c1 && pos_task[i] != -1) atomicMin(&s_next, i);
             __syncthreads();
-            cur = uni;
+            pos = s_next;
+            __syncthreads();
         }
-        const uint32_t i = c0 + threadIdx.x;
-        if (i < c1) {
-            const int32_t t = uni >= 0 ? uni : pos_task[i];
-            if (t >= 0) {
-                const uint32_t p = idx[i];
-                const TaskAux a = aux[t];
-                const Box box = load_box(bb, p);
-                uint32_t* dst = uni >= 0 ? sb : bins + (size_t)a.slot * kTaskBinWords;
-                uint32_t packed = 0;
-#pragma unroll
-                for (int ax = 0; ax < 3; ax++) {
-                    const int b = bin_index(cen[(size_t)p * cstride + ax], a.k[ax], a.off[ax]);
-                    bin_accumulate(&dst[(ax * kBins + b) * kBinWords], box);
-                    packed |= (uint32_t)b << (4 * ax);
-                }
-                binidx[i] = (uint16_t)packed;  // the partition pass reads this instead of gathering the centroid again
-            }
-        }
-    }
-    if (cur >= 0) {
-        __syncthreads();
-        bins_smem_flush(sb, bins + (size_t)aux[cur].slot * kTaskBinWords);
     }
 }
 
@@ -583,6 +621,8 @@ __global__ void __launch_bounds__(kWarpTaskWarps * 32) sah_warp_task_kernel(cons
     }
     __syncwarp();
     const TaskAux a = aux[t];
+    // (measured: four bin copies per warp to thin out the atomic replays made this kernel 1.4x SLOWER at 1 Mi triangles —
+    // with ~150 primitives per task it is bound by the gather latency and the init/fold of the copies, not by replays)
     for (uint32_t i = task.begin + lane; i < task.end; i += 32) {
         const uint32_t p = idx[i];
         const Box box = load_box(bb, p);
@@ -623,7 +663,7 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, c
                                 const uint4* __restrict__ rank, const uint4* __restrict__ counts, uint32_t depth, float4* nodes,
                                 Task* __restrict__ next_tasks, TaskAux* __restrict__ next_aux,
                                 SmallTask* __restrict__ small_tasks,
-                                int32_t* __restrict__ child_task /* 2 per task: encoded next-level task or -1 */,
+                                PartTask* __restrict__ ptask /* per task: what the partition pass needs */,
                                 uint32_t* __restrict__ span_tasks /* [depth + 1]: bin blocks handed out for the next level */,
                                 LevelState* __restrict__ state /* [depth] in, [depth + 1] out */) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -644,8 +684,7 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, c
     Box nb = load_box(nodes, task.node);
     if (!d.split) {
         make_leaf(nodes, task.node, nb, task.begin, n);
-        child_task[2 * t] = -1;
-        child_task[2 * t + 1] = -1;
+        ptask[t] = PartTask{task.begin, 0u, -1, -1, 0u, 0u, {0u, 0u}};
         return;
     }
     const uint4 r = rank[t];
@@ -657,9 +696,9 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, c
     Box cb[2] = {Box{{d.lmn[0], d.lmn[1], d.lmn[2]}, {d.lmx[0], d.lmx[1], d.lmx[2]}},
                  Box{{d.rmn[0], d.rmn[1], d.rmn[2]}, {d.rmx[0], d.rmx[1], d.rmx[2]}}};
     const uint32_t cbeg[2] = {task.begin, mid}, cend[2] = {mid, task.end};
+    int32_t child[2] = {-1, -1};
     for (int k = 0; k < 2; k++) {
         const uint32_t nc = cend[k] - cbeg[k];
-        child_task[2 * t + k] = -1;
         if (nc <= 1 || cap) {  // leaf on entry: pad (run) + pad (make_leaf), binned_sah.rs:133-143
             box_pad(cb[k], kPad);
             make_leaf(nodes, left + k, cb[k], cbeg[k], nc);
@@ -673,9 +712,10 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, c
             const uint32_t slot = nc > kWarpTask ? atomicAdd(&span_tasks[depth + 1], 1u) : 0u;
             task_enter(nodes, left + k, cb[k], &next_aux[next], slot);
             next_tasks[next] = Task{left + k, cbeg[k], cend[k]};
-            child_task[2 * t + k] = pt_encode(next++, nc);
+            child[k] = pt_encode(next++, nc);
         }
     }
+    ptask[t] = PartTask{task.begin, d.nleft, child[0], child[1], 4u * d.axis, d.split_index, {0u, 0u}};
 }
 
 // ---- small subtrees: one warp runs BinnedSahBuildTask::run for every node below a <= 32-primitive task -----
@@ -967,10 +1007,7 @@ struct FlagSumOp {
 struct PartitionParams {
     const uint32_t* idx;
     const int32_t* pos_task;
-    const Task* tasks;
-    const TaskAux* aux;
-    const Decision* dec;
-    const int32_t* child_task;
+    const PartTask* ptask;
     const uint16_t* binidx;
     uint32_t* idx_out;
     int32_t* pos_task_out;
@@ -981,10 +1018,8 @@ struct PartitionFlagIn {
         const int32_t t = pt_task(p->pos_task[i]);
         uint32_t f = 0;
         if (t >= 0) {
-            const Decision& d = p->dec[t];
-            if (d.split) {
-                f = (((uint32_t)p->binidx[i] >> (4u * d.axis)) & 15u) < d.split_index ? 1u : 0u;
-            }
+            const uint2 k = *reinterpret_cast<const uint2*>(&p->ptask[t].shift);  // {shift, split_index}
+            if (k.y != 0u) f = (((uint32_t)p->binidx[i] >> k.x) & 15u) < k.y ? 1u : 0u;
         }
         return FlagSum{f, f};
     }
@@ -997,15 +1032,17 @@ struct PartitionScatterOut {
         uint32_t i;
         __device__ const Ref& operator=(const FlagSum& v) const {
             const int32_t t = pt_task(p->pos_task[i]);
-            if (t < 0 || !p->dec[t].split) {
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (t >= 0) q = *reinterpret_cast<const uint4*>(&p->ptask[t]);  // {begin, nleft, child_left, child_right}
+            if (t < 0 || q.y == 0u) {  // finished position, or a task that became a leaf this level
                 p->idx_out[i] = p->idx[i];
                 p->pos_task_out[i] = -1;
             } else {
-                const uint32_t begin = p->tasks[t].begin, nleft = p->dec[t].nleft, r = v.sum - v.flag;
+                const uint32_t r = v.sum - v.flag;
                 const bool left = v.flag != 0;
-                const uint32_t dest = left ? begin + r : begin + nleft + (i - begin - r);
+                const uint32_t dest = left ? q.x + r : q.x + q.y + (i - q.x - r);
                 p->idx_out[dest] = p->idx[i];
-                p->pos_task_out[dest] = p->child_task[2 * t + (left ? 0 : 1)];
+                p->pos_task_out[dest] = (int32_t)(left ? q.z : q.w);
             }
             return *this;
         }
@@ -1403,7 +1440,7 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
     DevBuf nodesA;
     RTB_CUDA(nodesA.alloc((size_t)max_nodes * 32));
     float4* nodes = nodesA.as<float4>();
-    DevBuf idxB[2], ptB[2], tasksB[2], auxB[2], binidx, span_tasks, dec, bins, counts, ranks4, child_task, world, temp, state, params, small_tasks, used,
+    DevBuf idxB[2], ptB[2], tasksB[2], auxB[2], binidx, span_tasks, dec, bins, counts, ranks4, ptask, world, temp, state, params, small_tasks, used,
         waste, waste_prefix;
     for (int k = 0; k < 2; k++) {
         RTB_CUDA(idxB[k].alloc((size_t)n * 4));
@@ -1439,15 +1476,14 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         RTB_CUDA(cudaMemsetAsync(span_tasks.p, 0, (size_t)(kMaxDepth + 3) * 4, 0));
         RTB_CUDA(counts.alloc((size_t)task_cap * sizeof(uint4)));
         RTB_CUDA(ranks4.alloc((size_t)task_cap * sizeof(uint4)));
-        RTB_CUDA(child_task.alloc((size_t)task_cap * 8));
+        RTB_CUDA(ptask.alloc((size_t)task_cap * sizeof(PartTask)));
         RTB_CUDA(binidx.alloc((size_t)n * 2));
         RTB_CUDA(state.alloc((size_t)(kMaxDepth + 3) * sizeof(LevelState)));
         RTB_CUDA(params.alloc(2 * sizeof(PartitionParams)));
         PartitionParams hp[2];
         for (int k = 0; k < 2; k++)
-            hp[k] = PartitionParams{idxB[k].as<uint32_t>(), ptB[k].as<int32_t>(), tasksB[k].as<Task>(), auxB[k].as<TaskAux>(),
-                                    dec.as<Decision>(), child_task.as<int32_t>(), binidx.as<uint16_t>(), idxB[k ^ 1].as<uint32_t>(),
-                                    ptB[k ^ 1].as<int32_t>()};
+            hp[k] = PartitionParams{idxB[k].as<uint32_t>(), ptB[k].as<int32_t>(), ptask.as<PartTask>(), binidx.as<uint16_t>(),
+                                    idxB[k ^ 1].as<uint32_t>(), ptB[k ^ 1].as<int32_t>()};
         RTB_CUDA(cudaMemcpyAsync(params.p, hp, sizeof(hp), cudaMemcpyHostToDevice, 0));
         // CUB temp storage: sized for the largest scans we run
         size_t temp_bytes = 0, tb = 0;
@@ -1466,10 +1502,11 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         sah_bins_init_kernel<<<blocks(words, 256), 256>>>(bins.as<uint32_t>(), words);
         fill_i32_kernel<<<blocks(n, 256), 256>>>(ptB[0].as<int32_t>(), n, pt_encode(0, n));  // every position belongs to task 0
         LevelState* d_state = state.as<LevelState>();
-        sah_root_task_kernel<<<1, 1>>>(nodes, n, tasksB[0].as<Task>(), auxB[0].as<TaskAux>(), d_state);
+        sah_root_task_kernel<<<1, 1>>>(nodes, n, tasksB[0].as<Task>(), auxB[0].as<TaskAux>(), d_state, span_tasks.as<uint32_t>());
         // bin kernel: a machine-sized grid, every block owns a contiguous span (multiple of the chunk size)
         const uint32_t bin_chunks = blocks(n, kBinBlock);
-        const uint32_t bin_grid = std::min(bin_chunks, 148u * 8u);
+        const bool bin_priv = n >= (4u << 20);
+        const uint32_t bin_grid = std::min(bin_chunks, 148u * (bin_priv ? 5u : 8u));  // one wave of resident blocks
         const uint32_t bin_span = ((bin_chunks + bin_grid - 1) / bin_grid) * kBinBlock;
         // The level loop runs on the device's own bookkeeping (LevelState): the host enqueues level after level with
         // launch sizes from an upper bound of the task count and only looks at the state — one level behind, through a
@@ -1490,8 +1527,14 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
             const Task* t_cur = tasksB[par].as<Task>();
             const TaskAux* aux_cur = auxB[par].as<TaskAux>();
             const LevelState* st = d_state + depth;
-            sah_bin_kernel<<<bin_grid, kBinBlock>>>(idxB[par].as<uint32_t>(), ptB[par].as<int32_t>(), n, bin_span, aux_cur, d_bb, d_cen,
-                                                    cstride, bins.as<uint32_t>(), binidx.as<uint16_t>(), st);
+            if (bin_priv)
+                sah_bin_kernel<true><<<bin_grid, kBinBlock>>>(idxB[par].as<uint32_t>(), ptB[par].as<int32_t>(), n, bin_span, t_cur, aux_cur,
+                                                              d_bb, d_cen, cstride, bins.as<uint32_t>(), binidx.as<uint16_t>(), st,
+                                                              span_tasks.as<uint32_t>() + depth);
+            else
+                sah_bin_kernel<false><<<bin_grid, kBinBlock>>>(idxB[par].as<uint32_t>(), ptB[par].as<int32_t>(), n, bin_span, t_cur, aux_cur,
+                                                               d_bb, d_cen, cstride, bins.as<uint32_t>(), binidx.as<uint16_t>(), st,
+                                                               span_tasks.as<uint32_t>() + depth);
             sah_split_kernel<<<blocks((size_t)A_ub * 32, 128), 128>>>(t_cur, A_ub, aux_cur, bins.as<uint32_t>(), nodes, max_leaf, depth,
                                                                       dec.as<Decision>(), counts.as<uint4>(), st);
             sah_warp_task_kernel<<<blocks(A_ub, kWarpTaskWarps), kWarpTaskWarps * 32>>>(t_cur, idxB[par].as<uint32_t>(), aux_cur, d_bb,
@@ -1503,7 +1546,7 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
                                                     make_uint4(0, 0, 0, 0), (int)A_ub));
             sah_emit_kernel<<<blocks(A_ub, 128), 128>>>(t_cur, A_ub, dec.as<Decision>(), ranks4.as<uint4>(), counts.as<uint4>(), depth,
                                                         nodes, tasksB[par ^ 1].as<Task>(), auxB[par ^ 1].as<TaskAux>(),
-                                                        small_tasks.as<SmallTask>(), child_task.as<int32_t>(),
+                                                        small_tasks.as<SmallTask>(), ptask.as<PartTask>(),
                                                         span_tasks.as<uint32_t>(), d_state);
             tbytes = temp.bytes;
             RTB_CUDA(cub::DeviceScan::InclusiveScanByKey(temp.p, tbytes, ptB[par].as<int32_t>(),
