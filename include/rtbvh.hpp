@@ -309,11 +309,41 @@ class Scene {
         if (rtbvh_gpu_scene_create(bvh ? &b : nullptr, mbvh ? &m : nullptr, vertices, vertex_stride, triangle_count, &h_) != Ok)
             throw std::runtime_error(rtbvh_gpu_last_error());
     }
+    // Builder{aabbs: None, primitives}.construct_* + Mbvh::from, built and kept on the device (no host mirror)
+    static Scene build(const float* vertices, size_t vertex_stride, size_t triangle_count, BvhType type = BinnedSAH,
+                       size_t primitives_per_leaf = 1, bool with_mbvh = true) {
+        Scene s;
+        if (rtbvh_gpu_scene_build(vertices, vertex_stride, triangle_count, primitives_per_leaf, type, with_mbvh ? 1 : 0, &s.h_) != Ok)
+            throw std::runtime_error(rtbvh_gpu_last_error());
+        return s;
+    }
     ~Scene() {
         if (h_) rtbvh_gpu_scene_free(h_);
     }
     Scene(const Scene&) = delete;
     Scene& operator=(const Scene&) = delete;
+    Scene(Scene&& o) noexcept : h_(o.h_) { o.h_ = 0; }
+    // Bvh::refit for a resident scene: same triangles, new positions; also refreshes the Mbvh and the triangle records
+    void refit(const float* vertices, size_t vertex_stride, size_t triangle_count) {
+        if (rtbvh_gpu_scene_refit(h_, vertices, vertex_stride, triangle_count) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
+    }
+    // submit / wait: the buffers must stay alive and untouched until wait(ticket) returns (page-locked ones make it asynchronous)
+    uint64_t intersect_async(const RTRay* rays, size_t n, RTHit* hits, RTTreeKind tree = RT_TREE_MBVH) {
+        uint64_t ticket = 0;
+        if (rtbvh_gpu_intersect_async(h_, tree, rays, n, hits, &ticket) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
+        return ticket;
+    }
+    void wait(uint64_t ticket = 0) {
+        if (rtbvh_gpu_wait(h_, ticket) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
+    }
+    std::vector<RTMbvhNode> read_mbvh_nodes() const {
+        uint32_t n = 0;
+        if (rtbvh_gpu_scene_tree_size(h_, RT_TREE_MBVH, &n, nullptr) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
+        std::vector<RTMbvhNode> out(n);
+        if (rtbvh_gpu_scene_read_nodes(h_, RT_TREE_MBVH, out.data(), out.size() * sizeof(RTMbvhNode)) != Ok)
+            throw std::runtime_error(rtbvh_gpu_last_error());
+        return out;
+    }
     std::vector<RTHit> intersect(const std::vector<RTRay>& rays, RTTreeKind tree = RT_TREE_MBVH) const {
         std::vector<RTHit> hits(rays.size());
         if (rtbvh_gpu_intersect(h_, tree, rays.data(), rays.size(), hits.data()) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
@@ -327,6 +357,7 @@ class Scene {
     void set_ray_sorting(bool on) { rtbvh_gpu_scene_set_ray_sorting(h_, on ? 1 : 0); }
 
   private:
+    Scene() = default;
     RTGpuScene h_ = 0;
 };
 

@@ -215,6 +215,55 @@ static void batch_equals_iterator_loop(const std::vector<Triangle>& prims) {
     }
 }
 
+// A resident scene (built on the device, no host mirror) answers like the host-mirrored trees, through the blocking and
+// the submit/wait calls, and follows moving vertices through refit like a rebuilt-and-collapsed reference tree would.
+static void resident_scene_async_and_refit(const std::vector<Triangle>& prims) {
+    Bvh bvh = builder(prims, nullptr, 1).construct_binned_sah().unwrap();
+    Mbvh mbvh(bvh);
+    Scene mirrored(&bvh, &mbvh, &prims[0].v0.x, 12, prims.size());
+    Scene resident = Scene::build(&prims[0].v0.x, 12, prims.size(), BinnedSAH, 1, true);
+    const std::vector<RTMbvhNode> rn = resident.read_mbvh_nodes();
+    CHECK(rn.size() == mbvh.raw().node_count);
+    CHECK(std::memcmp(rn.data(), mbvh.raw().nodes, rn.size() * sizeof(RTMbvhNode)) == 0);
+    std::vector<RTRay> rays;
+    uint64_t s = 777;
+    auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (float)((s >> 40) & 0xFFFFFF) / 16777216.0f; };
+    for (int i = 0; i < 50000; i++) {
+        const float ox = -8 + 16 * rnd(), oy = -4 + 12 * rnd(), oz = -8 + 16 * rnd();
+        const float tx = -3 + 6 * rnd(), ty = 3 * rnd(), tz = -2 + 4 * rnd();
+        float dx = tx - ox, dy = ty - oy, dz = tz - oz;
+        const float il = 1.0f / std::sqrt(dx * dx + dy * dy + dz * dz);
+        rays.push_back(RTRay{{ox, oy, oz}, 1e-4f, {dx * il, dy * il, dz * il}, 1e34f});
+    }
+    const std::vector<RTHit> want = mirrored.intersect(rays);
+    std::vector<RTHit> a(rays.size()), b(rays.size());
+    const uint64_t t0 = resident.intersect_async(rays.data(), rays.size(), a.data());
+    const uint64_t t1 = resident.intersect_async(rays.data(), rays.size(), b.data(), RT_TREE_BVH);
+    CHECK(t1 > t0);
+    resident.wait(t1);
+    resident.wait(t0);
+    CHECK(std::memcmp(a.data(), want.data(), want.size() * sizeof(RTHit)) == 0);
+    const std::vector<RTHit> want_bvh = mirrored.intersect(rays, RT_TREE_BVH);
+    CHECK(std::memcmp(b.data(), want_bvh.data(), want_bvh.size() * sizeof(RTHit)) == 0);
+    // move every triangle, refit both scenes' worth of state: FFI refit on the host-mirrored Bvh + a new collapse vs scene refit
+    std::vector<Triangle> moved = prims;
+    std::vector<Aabb> boxes;
+    for (size_t i = 0; i < moved.size(); i++) {
+        const float d = 0.05f * std::sin((float)i * 0.37f);
+        for (Vec3* v : {&moved[i].v0, &moved[i].v1, &moved[i].v2}) { v->x += d; v->y -= d * 0.5f; v->z += d * 0.25f; }
+        boxes.push_back(moved[i].aabb());  // Primitive::aabb of the tests' Triangle: un-padded, what the scene refit computes
+    }
+    resident.refit(&moved[0].v0.x, 12, moved.size());
+    bvh.refit(boxes.data());
+    Mbvh mbvh2(bvh);
+    Scene mirrored2(&bvh, &mbvh2, &moved[0].v0.x, 12, moved.size());
+    const std::vector<RTMbvhNode> rn2 = resident.read_mbvh_nodes();
+    CHECK(rn2.size() == mbvh2.raw().node_count);
+    CHECK(std::memcmp(rn2.data(), mbvh2.raw().nodes, rn2.size() * sizeof(RTMbvhNode)) == 0);
+    const std::vector<RTHit> h1 = resident.intersect(rays), h2 = mirrored2.intersect(rays);
+    CHECK(std::memcmp(h1.data(), h2.data(), h1.size() * sizeof(RTHit)) == 0);
+}
+
 int main(int argc, char** argv) {
     CHECK(argc >= 2);
     CHECK(rtbvh_gpu_device_count() > 0);
@@ -225,6 +274,7 @@ int main(int argc, char** argv) {
     teapot_builds(teapot);
     ffi_tests();
     batch_equals_iterator_loop(teapot);
+    resident_scene_async_and_refit(teapot);
     std::printf("ok: %d checks\n", g_checks);
     return 0;
 }

@@ -24,8 +24,10 @@ def test_cpp_mirror_compiles_and_links():
 
 @pytest.mark.gpu
 def test_reference_tests_through_cpp_mirror():
-    if not os.path.exists(EXE):
-        _compile()
+    srcs = [os.path.join(ROOT, "tests", "cpp", "test_reference_api.cpp"), os.path.join(ROOT, "include", "rtbvh.hpp"),
+            os.path.join(ROOT, "include", "rtbvh_iter.hpp"), os.path.join(ROOT, "include", "rtbvh_gpu.h")]
+    if not os.path.exists(EXE) or any(os.path.getmtime(f) > os.path.getmtime(EXE) for f in srcs):
+        _compile()  # a binary older than its sources would test yesterday's code
     r = subprocess.run([EXE, os.path.join(ROOT, "tests", "golden", "teapot_tris.npy")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("ok:")
