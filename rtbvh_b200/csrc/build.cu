@@ -760,6 +760,7 @@ __device__ __forceinline__ float small_candidate(const float4* __restrict__ lo, 
     }
     return fadd(fmul(box_half_area(L), (float)cl), fmul(box_half_area(R), (float)cr));
 }
+__device__ __forceinline__ unsigned inmask2(uint32_t b) { return 3u << b; }  // the two lanes of a 2-primitive node
 // find_split over the 15 candidates held by one aligned 16-lane group (lane & 15 = split - 1; lane 15 of the group holds
 // no candidate): first strict minimum below f32::MAX in order s = 1..15 (binned_sah.rs:95-111).  All lanes of the group
 // return the group's (cost, count).
@@ -831,6 +832,51 @@ __global__ void __launch_bounds__(kSmallWarps * 32, RTB_SMALL_MINBLOCKS) sah_sma
             s_lo[w][lane].w = __uint_as_float(mybins);
         }
         __syncwarp();
+        if (nn == 2) {
+            // Two primitives (about a third of all nodes): the 45 candidates collapse to one.  On an axis where the two
+            // bins differ every split position between them has the same cost half_area(A) + half_area(B) (first one:
+            // min bin + 1); where they are equal one side is always empty and the cost is NaN (never chosen).  The cost is the
+            // same on every usable axis, so find_split's strict comparisons keep the first usable axis.  Anything else
+            // (no usable axis, cost not below the leaf cost -> fallback / leaf rules) takes the general path below.
+            const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, mybins, (int)e.b), b1 = __shfl_sync(0xFFFFFFFFu, mybins, (int)e.b + 1);
+            int ax = -1;
+#pragma unroll
+            for (int k = 2; k >= 0; k--)
+                if (((b0 >> (8 * k)) & 0xFFu) != ((b1 >> (8 * k)) & 0xFFu)) ax = k;
+            if (ax >= 0) {
+                const float4 l0 = s_lo[w][e.b], h0 = s_hi[w][e.b], l1 = s_lo[w][e.b + 1], h1 = s_hi[w][e.b + 1];
+                const Box A = box_union(box_empty(), Box{{l0.x, l0.y, l0.z}, {h0.x, h0.y, h0.z}});
+                const Box B = box_union(box_empty(), Box{{l1.x, l1.y, l1.z}, {h1.x, h1.y, h1.z}});
+                const float cost = fadd(fmul(box_half_area(A), 1.0f), fmul(box_half_area(B), 1.0f));
+                const float max_cost2 = fmul(box_half_area(nb), fsub(2.0f, 1.0f));
+                if (cost < FLT_MAX && cost < max_cost2) {
+                    const bool first_left = ((b0 >> (8 * ax)) & 0xFFu) < ((b1 >> (8 * ax)) & 0xFFu);
+                    __syncwarp();
+                    if (!first_left && in) {  // stable partition of two: the right-going primitive sits first -> swap
+                        const uint32_t other = (uint32_t)lane == e.b ? e.b + 1 : e.b;
+                        const float4 olo = s_lo[w][other], ohi = s_hi[w][other];
+                        float oc[3];
+                        for (int k = 0; k < 3; k++) oc[k] = s_cen[w][other][k];
+                        __syncwarp(inmask2(e.b));
+                        s_lo[w][lane] = olo;
+                        s_hi[w][lane] = ohi;
+                        for (int k = 0; k < 3; k++) s_cen[w][lane][k] = oc[k];
+                    }
+                    const uint32_t left = next_free;
+                    next_free += 2;
+                    if (lane == 0) {
+                        store_node(nodes, e.node, nb, -1, (int)left);
+                        Box bl = first_left ? A : B, br = first_left ? B : A;
+                        box_pad(bl, kPad);  // leaf on entry: entry pad + make_leaf pad (binned_sah.rs:133-143)
+                        box_pad(br, kPad);
+                        make_leaf(nodes, left, bl, task.begin + e.b, 1u);
+                        make_leaf(nodes, left + 1, br, task.begin + e.b + 1, 1u);
+                    }
+                    __syncwarp();
+                    continue;
+                }
+            }
+        }
         // 45 candidates (3 axes x split positions 1..15) in two rounds: lanes 0-15 / 16-31 hold axes 0 / 1, then lanes
         // 0-15 hold axis 2; lane 15 of a group holds nothing.  Every lane keeps the child boxes of its candidates.
         Box L1, R1, L2, R2;
