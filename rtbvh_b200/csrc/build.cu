@@ -57,15 +57,16 @@ constexpr int kTaskBinWords = 3 * kBins * kBinWords;  // 336 words = 1344 B per 
 constexpr float kPad = 0.0001f;
 constexpr int kRadius = 14;          // locb.rs:27
 constexpr uint32_t kSmall = 32;      // subtrees with <= kSmall primitives are finished by one warp (sah_small_kernel)
-// Level tasks with <= kWarpTask primitives are binned AND split by one warp each (sah_warp_task_kernel: bins in shared
-// memory, no global atomics); larger tasks go through the span-based bin kernel + sah_split_kernel.  In pos_task a
-// warp-class task t is stored as -2 - t (the span kernel skips negative entries), -1 = position no longer active.
+// Level tasks with <= kWarpTask primitives are binned, split AND partitioned by one warp each (sah_warp_task_kernel: bins
+// and the task's index range in shared memory, no global atomics, no global partition pass); larger ("span-class") tasks go
+// through the span-based bin kernel + sah_split_kernel + the segmented-scan partition.  pos_task holds, per index
+// position, the span-class task it belongs to or -1 (finished, or inside a warp-class task: nothing for the span passes).
 #ifndef RTB_WARP_TASK
 #define RTB_WARP_TASK 512
 #endif
 constexpr uint32_t kWarpTask = RTB_WARP_TASK;
-__host__ __device__ inline int32_t pt_encode(uint32_t t, uint32_t n) { return n <= kWarpTask ? -2 - (int32_t)t : (int32_t)t; }
-__device__ __forceinline__ int32_t pt_task(int32_t pt) { return pt >= 0 ? pt : -2 - pt; }  // -1 -> -1
+__host__ __device__ inline int32_t pt_encode(uint32_t t, uint32_t n) { return n <= kWarpTask ? -1 : (int32_t)t; }
+__device__ __forceinline__ int32_t pt_task(int32_t pt) { return pt; }
 
 // ---- order-preserving float <-> uint keys (so min/max can be integer atomics) --------------------
 __host__ __device__ inline uint32_t fkey(float f) {
@@ -390,14 +391,12 @@ __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __re
             else
                 bin_run<1>(sb, pos, run_end, a, idx, bb, cen, cstride, g, binidx);
             pos = run_end;
-        } else if (pt < -1) {  // warp-class task (sah_warp_task_kernel's): skip its range
-            pos = min(end, tasks[-2 - pt].end);
-        } else {  // finished positions carry no range: find the next live one in this chunk
+        } else {  // finished / warp-class positions carry no range: find the next span-class one in this chunk
             const uint32_t c1 = min(pos + kBinBlock, end);
             if (threadIdx.x == 0) s_next = c1;
             __syncthreads();
             const uint32_t i = pos + threadIdx.x;
-            if (i < c1 && pos_task[i] != -1) atomicMin(&s_next, i);
+            if (i < c1 && pos_task[i] >= 0) atomicMin(&s_next, i);
             __syncthreads();
             pos = s_next;
             __syncthreads();
@@ -437,9 +436,13 @@ __device__ __forceinline__ Box warp_union(Box b) {
 
 // One warp per task: find_split on the three axes, axis choice, leaf / fallback rules, child boxes
 // (binned_sah.rs:80-114, :174-247).  Lane b < 16 owns bin b.
-__device__ __forceinline__ void sah_split_task(const Task task, uint32_t t, int lane, const uint32_t* taskbins,
-                                               const float4* __restrict__ nodes, uint32_t max_leaf, uint32_t depth,
-                                               Decision* __restrict__ dec, uint4* __restrict__ counts) {
+struct SplitOut {  // warp-uniform result of sah_split_task
+    bool split;
+    uint32_t axis, split_index, nleft;
+};
+__device__ __forceinline__ SplitOut sah_split_task(const Task task, uint32_t t, int lane, const uint32_t* taskbins,
+                                                   const float4* __restrict__ nodes, uint32_t max_leaf, uint32_t depth,
+                                                   Decision* __restrict__ dec, uint4* __restrict__ counts) {
     const uint32_t n = task.end - task.begin;
     Box bin[3];
     uint32_t cnt[3];
@@ -569,6 +572,7 @@ __device__ __forceinline__ void sah_split_task(const Task task, uint32_t t, int 
         }
         counts[t] = c;
     }
+    return SplitOut{do_split, (uint32_t)best_axis, split_index, nleft};
 }
 // Launched for A_ub >= A warps (the host only knows an upper bound of the level's task count): warps beyond A zero
 // their counts entry so that the fixed-size scan that follows is exact.
@@ -596,25 +600,36 @@ __global__ void __launch_bounds__(128) sah_split_kernel(const Task* __restrict__
     }
 }
 
-// Warp-class tasks (<= kWarpTask primitives): one warp fills the 3 x 16 bins of its task in shared memory (no global
-// atomics, no bins in HBM) and evaluates the split right away.  On the deep levels of the level loop every task is of
-// this class: the pass then reads each primitive once (index, box, centroid) and writes one Decision per task.
+// Levels without span-class tasks skip sah_split_kernel, which also zeroes the counts of the slots beyond A.
+__global__ void zero_counts_tail_kernel(uint4* __restrict__ counts, uint32_t A_ub, const LevelState* __restrict__ state) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < A_ub && t >= state->A) counts[t] = make_uint4(0u, 0u, 0u, 0u);
+}
+// Warp-class tasks (<= kWarpTask primitives): one warp does the whole node step of its task — it stages the task's index
+// range in shared memory, fills the 3 x 16 bins there (no global atomics, no bins in HBM), evaluates the split and, if
+// the node splits, writes the range back stably partitioned IN PLACE (it owns the range; ballot prefix sums give the
+// destinations).  Such a task never shows up in the global partition pass, and once a level holds no span-class task
+// any more the level loop consists of this kernel, the scan of the per-task counts and the emit kernel only.
 constexpr int kWarpTaskWarps = 4;
 __global__ void __launch_bounds__(kWarpTaskWarps * 32) sah_warp_task_kernel(const Task* __restrict__ tasks,
-                                                                            const uint32_t* __restrict__ idx,
+                                                                            uint32_t* __restrict__ idx,
                                                                             const TaskAux* __restrict__ aux,
                                                                             const float4* __restrict__ bb,
                                                                             const float* __restrict__ cen, uint32_t cstride,
                                                                             const float4* __restrict__ nodes, uint32_t max_leaf,
                                                                             uint32_t depth, Decision* __restrict__ dec,
-                                                                            uint4* __restrict__ counts, uint16_t* __restrict__ binidx,
+                                                                            uint4* __restrict__ counts,
                                                                             const LevelState* __restrict__ state) {
     __shared__ uint32_t sb[kWarpTaskWarps][kTaskBinWords];
+    __shared__ uint32_t s_idx[kWarpTaskWarps][kWarpTask];   // the task's index range as read
+    __shared__ uint32_t s_out[kWarpTaskWarps][kWarpTask];   // ... and partitioned
+    __shared__ uint16_t s_pk[kWarpTaskWarps][kWarpTask];    // 3 x 4-bit bin per primitive
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x * kWarpTaskWarps + w;
     if (t >= state->A) return;
     const Task task = tasks[t];
-    if (task.end - task.begin > kWarpTask) return;
+    const uint32_t n = task.end - task.begin;
+    if (n > kWarpTask) return;
     for (int k = lane; k < kTaskBinWords; k += 32) {
         const int f = k % kBinWords;
         sb[w][k] = f < 3 ? fkey(1e34f) : (f < 6 ? fkey(-1e34f) : 0u);
@@ -623,8 +638,8 @@ __global__ void __launch_bounds__(kWarpTaskWarps * 32) sah_warp_task_kernel(cons
     const TaskAux a = aux[t];
     // (measured: four bin copies per warp to thin out the atomic replays made this kernel 1.4x SLOWER at 1 Mi triangles —
     // with ~150 primitives per task it is bound by the gather latency and the init/fold of the copies, not by replays)
-    for (uint32_t i = task.begin + lane; i < task.end; i += 32) {
-        const uint32_t p = idx[i];
+    for (uint32_t j = lane; j < n; j += 32) {
+        const uint32_t p = idx[task.begin + j];
         const Box box = load_box(bb, p);
         uint32_t packed = 0;
 #pragma unroll
@@ -633,10 +648,27 @@ __global__ void __launch_bounds__(kWarpTaskWarps * 32) sah_warp_task_kernel(cons
             bin_accumulate(&sb[w][(ax * kBins + b) * kBinWords], box);
             packed |= (uint32_t)b << (4 * ax);
         }
-        binidx[i] = (uint16_t)packed;
+        s_idx[w][j] = p;
+        s_pk[w][j] = (uint16_t)packed;
     }
     __syncwarp();
-    sah_split_task(task, t, lane, sb[w], nodes, max_leaf, depth, dec, counts);
+    const SplitOut so = sah_split_task(task, t, lane, sb[w], nodes, max_leaf, depth, dec, counts);
+    if (!so.split) return;
+    // stable partition (binned_sah.rs:213-219 predicate): lefts to [0, nleft), rights behind them, original order kept
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t lbase = 0, rbase = so.nleft;
+    for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool valid = j < n;
+        const bool left = valid && (((uint32_t)s_pk[w][valid ? j : 0] >> (4u * so.axis)) & 15u) < so.split_index;
+        const uint32_t lm = __ballot_sync(0xFFFFFFFFu, left), vm = __ballot_sync(0xFFFFFFFFu, valid);
+        const uint32_t rm = vm & ~lm;
+        if (valid) s_out[w][left ? lbase + (uint32_t)__popc(lm & lt) : rbase + (uint32_t)__popc(rm & lt)] = s_idx[w][j];
+        lbase += (uint32_t)__popc(lm);
+        rbase += (uint32_t)__popc(rm);
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < n; j += 32) idx[task.begin + j] = s_out[w][j];
 }
 
 // make_leaf (binned_sah.rs:134-138): second pad, left_first = begin, count = n
@@ -1563,30 +1595,40 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         cudaEvent_t ev[2];
         RTB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
         RTB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+        // From the first level that could be free of span-class tasks (all tasks <= kWarpTask needs log2(n / kWarpTask)
+        // halvings) the host reads the state one level behind; the GPU still has a full level queued, so this costs no
+        // bubble.  Once a level has no span-class task none will follow (children only get smaller): from then on the
+        // span bin, the span split and the global partition pass — and with it the ping-pong of the index buffers — are
+        // left out.  The loop ends when a level had no task at all.
+        static thread_local uint32_t* h_span = nullptr;
+        if (!h_span) RTB_CUDA(cudaHostAlloc(&h_span, (size_t)(kMaxDepth + 3) * 4, cudaHostAllocDefault));
         uint32_t first_check = 0;
-        while ((uint64_t(kSmall) << (first_check + 1)) < n) first_check++;
+        while ((uint64_t(kWarpTask) << (first_check + 1)) < n) first_check++;
         uint32_t depth = 0;
-        bool done = false;
+        bool done = false, span_left = true;
         for (; !done && depth <= (uint32_t)kMaxDepth; depth++) {
-            const int par = (int)(depth & 1u);
+            const int par = (int)(depth & 1u);  // tasks / aux ping-pong every level
             const uint32_t A_ub = depth >= 31 ? task_cap : std::min(task_cap, 1u << depth);
             const Task* t_cur = tasksB[par].as<Task>();
             const TaskAux* aux_cur = auxB[par].as<TaskAux>();
             const LevelState* st = d_state + depth;
-            if (bin_priv)
-                sah_bin_kernel<true><<<bin_grid, kBinBlock>>>(idxB[par].as<uint32_t>(), ptB[par].as<int32_t>(), n, bin_span, t_cur, aux_cur,
-                                                              d_bb, d_cen, cstride, bins.as<uint32_t>(), binidx.as<uint16_t>(), st,
-                                                              span_tasks.as<uint32_t>() + depth);
-            else
-                sah_bin_kernel<false><<<bin_grid, kBinBlock>>>(idxB[par].as<uint32_t>(), ptB[par].as<int32_t>(), n, bin_span, t_cur, aux_cur,
-                                                               d_bb, d_cen, cstride, bins.as<uint32_t>(), binidx.as<uint16_t>(), st,
-                                                               span_tasks.as<uint32_t>() + depth);
-            sah_split_kernel<<<blocks((size_t)A_ub * 32, 128), 128>>>(t_cur, A_ub, aux_cur, bins.as<uint32_t>(), nodes, max_leaf, depth,
-                                                                      dec.as<Decision>(), counts.as<uint4>(), st);
-            sah_warp_task_kernel<<<blocks(A_ub, kWarpTaskWarps), kWarpTaskWarps * 32>>>(t_cur, idxB[par].as<uint32_t>(), aux_cur, d_bb,
+            if (span_left) {
+                if (bin_priv)
+                    sah_bin_kernel<true><<<bin_grid, kBinBlock>>>(idxB[parity].as<uint32_t>(), ptB[parity].as<int32_t>(), n, bin_span, t_cur,
+                                                                  aux_cur, d_bb, d_cen, cstride, bins.as<uint32_t>(), binidx.as<uint16_t>(),
+                                                                  st, span_tasks.as<uint32_t>() + depth);
+                else
+                    sah_bin_kernel<false><<<bin_grid, kBinBlock>>>(idxB[parity].as<uint32_t>(), ptB[parity].as<int32_t>(), n, bin_span, t_cur,
+                                                                   aux_cur, d_bb, d_cen, cstride, bins.as<uint32_t>(), binidx.as<uint16_t>(),
+                                                                   st, span_tasks.as<uint32_t>() + depth);
+                sah_split_kernel<<<blocks((size_t)A_ub * 32, 128), 128>>>(t_cur, A_ub, aux_cur, bins.as<uint32_t>(), nodes, max_leaf, depth,
+                                                                          dec.as<Decision>(), counts.as<uint4>(), st);
+            } else {
+                zero_counts_tail_kernel<<<blocks(A_ub, 256), 256>>>(counts.as<uint4>(), A_ub, st);
+            }
+            sah_warp_task_kernel<<<blocks(A_ub, kWarpTaskWarps), kWarpTaskWarps * 32>>>(t_cur, idxB[parity].as<uint32_t>(), aux_cur, d_bb,
                                                                                         d_cen, cstride, nodes, max_leaf, depth,
-                                                                                        dec.as<Decision>(), counts.as<uint4>(),
-                                                                                        binidx.as<uint16_t>(), st);
+                                                                                        dec.as<Decision>(), counts.as<uint4>(), st);
             size_t tbytes = temp.bytes;
             RTB_CUDA(cub::DeviceScan::ExclusiveScan(temp.p, tbytes, counts.as<uint4>(), ranks4.as<uint4>(), Uint4Add(),
                                                     make_uint4(0, 0, 0, 0), (int)A_ub));
@@ -1594,15 +1636,20 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
                                                         nodes, tasksB[par ^ 1].as<Task>(), auxB[par ^ 1].as<TaskAux>(),
                                                         small_tasks.as<SmallTask>(), ptask.as<PartTask>(),
                                                         span_tasks.as<uint32_t>(), d_state);
-            tbytes = temp.bytes;
-            RTB_CUDA(cub::DeviceScan::InclusiveScanByKey(temp.p, tbytes, ptB[par].as<int32_t>(),
-                                                         PartitionFlagIter(cub::CountingInputIterator<uint32_t>(0), PartitionFlagIn{dp + par}),
-                                                         PartitionScatterOut{dp + par, 0}, FlagSumOp(), n));
+            if (span_left) {
+                tbytes = temp.bytes;
+                RTB_CUDA(cub::DeviceScan::InclusiveScanByKey(temp.p, tbytes, ptB[parity].as<int32_t>(),
+                                                             PartitionFlagIter(cub::CountingInputIterator<uint32_t>(0), PartitionFlagIn{dp + parity}),
+                                                             PartitionScatterOut{dp + parity, 0}, FlagSumOp(), n));
+                parity ^= 1;
+            }
             RTB_CUDA(cudaMemcpyAsync(&h_state[depth + 1], d_state + depth + 1, sizeof(LevelState), cudaMemcpyDeviceToHost, 0));
+            RTB_CUDA(cudaMemcpyAsync(&h_span[depth + 1], span_tasks.as<uint32_t>() + depth + 1, 4, cudaMemcpyDeviceToHost, 0));
             RTB_CUDA(cudaEventRecord(ev[par], 0));
             if (depth >= 1 && depth - 1 >= first_check) {
-                RTB_CUDA(cudaEventSynchronize(ev[par ^ 1]));  // level depth - 1 has finished: h_state[depth] is valid
+                RTB_CUDA(cudaEventSynchronize(ev[par ^ 1]));  // level depth - 1 has finished: h_state / h_span [depth] are valid
                 if (h_state[depth].A == 0) done = true;      // the level just enqueued is a no-op; nothing follows it
+                if (h_span[depth] == 0) span_left = false;   // level `depth` had no span-class task: none from depth + 1 on
             }
         }
         RTB_CUDA(cudaEventSynchronize(ev[(depth - 1) & 1u]));
@@ -1611,7 +1658,6 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         RTB_CUDA(cudaGetLastError());
         fin = h_state[depth];
         if (fin.A != 0) return fail("binned SAH: level loop did not terminate");
-        parity = (int)(depth & 1u);  // one ping-pong step per enqueued level
         if (fin.S > small_cap) return fail("binned SAH: small-subtree list overflow");
     }
     uint32_t* idx_cur = idxB[parity].as<uint32_t>();
