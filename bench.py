@@ -264,7 +264,20 @@ def run_gpu(args):
         # the gather is part of the traversal kernel: every record is stored into all ranks' gather buffers (P2P over
         # NVLink) as its ray finishes; a one-block device barrier closes each step (rtbvh_b200/multigpu.py FusedGather)
         from rtbvh_b200 import multigpu as MG
-        fused = MG.FusedGather(rays_per_step, 8)
+        try:
+            fused = MG.FusedGather(rays_per_step, 8)
+            ok = 1
+        except Exception as e:  # no cudaIpc / peer access between these ranks: the NCCL gather is the other GPU path
+            log(f"[bench] fused gather unavailable on rank {rank}: {e}")
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag[0]) == 0:
+            if fused is not None:
+                fused.close()
+            fused, gather = None, "nccl"
+            g_out = [torch.empty(world * rays_per_step * 2, dtype=torch.float32, device="cuda") for _ in range(2)]
+            info["gather_note"] = "cudaIpc peer mapping failed on this box: fell back from the fused gather to NCCL all_gather"
 
     def step(k):
         b = k % ring

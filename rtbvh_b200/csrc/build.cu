@@ -1236,6 +1236,108 @@ __global__ void locb_write_kernel(const float4* __restrict__ in, float4* __restr
     }
 }
 
+// The tail of the clustering: once a range holds <= kLocbTail clusters an iteration is a handful of microseconds of work
+// behind five launches and a host round trip (58 iterations at 1 Mi triangles, ~35 of them this small).  One block runs all
+// remaining iterations back to back — the same four phases, separated by block barriers, on the same global arrays — and
+// reports how many it ran (the parity tells the host which node buffer holds the tree).
+constexpr uint32_t kLocbTail = 2048;
+constexpr int kLocbTailThreads = 1024;
+// (everything the block re-reads after one of its own barriers goes through L2: __ldcg)
+__device__ __forceinline__ Box tail_box(const float4* nodes, size_t i) {
+    const float4 lo = __ldcg(&nodes[i * 2]), hi = __ldcg(&nodes[i * 2 + 1]);
+    return Box{{lo.x, lo.y, lo.z}, {hi.x, hi.y, hi.z}};
+}
+__global__ void __launch_bounds__(kLocbTailThreads) locb_tail_kernel(float4* bufA, float4* bufB, uint32_t* nb, uint32_t* P,
+                                                                     uint32_t begin, uint32_t end, uint32_t previous_end,
+                                                                     uint32_t* out_state /* [0] iterations, [1] error */) {
+    typedef cub::BlockScan<uint32_t, kLocbTailThreads> BlockScan;
+    __shared__ typename BlockScan::TempStorage scan_tmp;
+    float4* cur = bufA;
+    float4* other = bufB;
+    uint32_t iters = 0, err = 0;
+    const uint32_t tid = threadIdx.x;
+    while (end - begin > 1) {
+        // nearest neighbour within the search window (locb.rs:93-142): ascending j, strict <
+        for (uint32_t i = begin + tid; i < end; i += kLocbTailThreads) {
+            const uint32_t sb = (i > begin + kRadius) ? i - kRadius : begin;
+            const uint32_t se = min(i + kRadius + 1, end);
+            const Box me = tail_box(cur, i);
+            float best = FLT_MAX;
+            uint32_t best_j = 0xFFFFFFFFu;
+            for (uint32_t j = sb; j < se; j++) {
+                if (j == i) continue;
+                const float d = box_half_area(box_union(me, tail_box(cur, j)));
+                if (d < best) {
+                    best = d;
+                    best_j = j;
+                }
+            }
+            nb[i] = best_j;
+        }
+        __syncthreads();
+        // mutual pairs (locb.rs:158-167) and their inclusive scan
+        uint32_t carry = 0;
+        for (uint32_t base = begin; base < end; base += kLocbTailThreads) {
+            const uint32_t i = base + tid;
+            uint32_t f = 0;
+            if (i < end) {
+                const uint32_t j = __ldcg(&nb[i]);
+                f = (j < end && j >= begin && i < j && __ldcg(&nb[j]) == i) ? 1u : 0u;
+            }
+            uint32_t incl, agg;
+            BlockScan(scan_tmp).InclusiveSum(f, incl, agg);
+            if (i < end) P[i] = carry + incl;
+            carry += agg;
+            __syncthreads();
+        }
+        const uint32_t merged_count = carry;
+        if (merged_count == 0) {  // no mutual pair (degenerate input): the multi-kernel loop reports the same
+            err = 1;
+            break;
+        }
+        // layout math + merge / copy (locb.rs:178-242)
+        const uint32_t children_begin = end - 2u * merged_count;
+        const uint32_t unmerged_begin = children_begin - (end - begin - merged_count);
+        for (uint32_t i = begin + tid; i < previous_end; i += kLocbTailThreads) {
+            if (i < end) {
+                const uint32_t j = __ldcg(&nb[i]);
+                const bool mutual = j >= begin && j < end && __ldcg(&nb[j]) == i;
+                if (mutual) {
+                    if (i < j) {
+                        const uint32_t parent = unmerged_begin + (j - begin) - __ldcg(&P[j]);
+                        const uint32_t first_child = children_begin + (__ldcg(&P[i]) - 1u) * 2u;
+                        const Box u = box_union(tail_box(cur, j), tail_box(cur, i));
+                        store_node(other, parent, u, -1, (int)first_child);
+                        other[(size_t)first_child * 2] = __ldcg(&cur[(size_t)i * 2]);
+                        other[(size_t)first_child * 2 + 1] = __ldcg(&cur[(size_t)i * 2 + 1]);
+                        other[(size_t)first_child * 2 + 2] = __ldcg(&cur[(size_t)j * 2]);
+                        other[(size_t)first_child * 2 + 3] = __ldcg(&cur[(size_t)j * 2 + 1]);
+                    }
+                } else {
+                    const uint32_t dst = unmerged_begin + (i - begin) - __ldcg(&P[i]);
+                    other[(size_t)dst * 2] = __ldcg(&cur[(size_t)i * 2]);
+                    other[(size_t)dst * 2 + 1] = __ldcg(&cur[(size_t)i * 2 + 1]);
+                }
+            } else {  // carry the pairs placed by the previous iteration (locb.rs:242)
+                other[(size_t)i * 2] = __ldcg(&cur[(size_t)i * 2]);
+                other[(size_t)i * 2 + 1] = __ldcg(&cur[(size_t)i * 2 + 1]);
+            }
+        }
+        __syncthreads();
+        float4* t = cur;
+        cur = other;
+        other = t;
+        previous_end = end;
+        begin = unmerged_begin;
+        end = children_begin;
+        iters++;
+    }
+    if (tid == 0) {
+        out_state[0] = iters;
+        out_state[1] = err;
+    }
+}
+
 // =================================================================================================
 // Collapse (merge_nodes) and refit
 // =================================================================================================
@@ -1747,7 +1849,7 @@ static ResultCode build_locb_device(const float4* d_bb, const float* d_cen, uint
     uint32_t begin = node_count - n, end = node_count, previous_end = end;
     locb_leaves_kernel<<<blocks(n, 256), 256>>>((const float4*)d_bb, out->indices.as<uint32_t>(), n, cur, begin);
     uint32_t iters = 0;
-    while (end - begin > 1) {
+    while (end - begin > kLocbTail) {
         const uint32_t c = end - begin;
         locb_nn_kernel<<<blocks(c, 128), 128>>>(cur, begin, end, nb.as<uint32_t>());
         locb_flag_kernel<<<blocks(c, 256), 256>>>(nb.as<uint32_t>(), begin, end, merged.as<uint32_t>());
@@ -1765,6 +1867,17 @@ static ResultCode build_locb_device(const float4* d_bb, const float* d_cen, uint
         begin = unmerged_begin;
         end = children_begin;
         iters++;
+    }
+    if (end - begin > 1) {  // the small iterations: one block, no host round trips
+        DevBuf tail_state;
+        RTB_CUDA(tail_state.alloc(8));
+        locb_tail_kernel<<<1, kLocbTailThreads>>>(cur, other, nb.as<uint32_t>(), P.as<uint32_t>(), begin, end, previous_end,
+                                                  tail_state.as<uint32_t>());
+        uint32_t ts[2] = {0, 0};
+        RTB_CUDA(cudaMemcpy(ts, tail_state.p, 8, cudaMemcpyDeviceToHost));
+        if (ts[1]) return fail("LOCB: no mutual pair found (degenerate input)");
+        if (ts[0] & 1u) std::swap(cur, other);
+        iters += ts[0];
     }
     if (cur != out->nodes.as<float4>()) {  // keep the result in out->nodes
         std::swap(out->nodes.p, nodesB.p);
