@@ -10,8 +10,9 @@ fov, hashed sub-pixel jitter per (frame, pixel).  One STEP = `--frames-per-step`
   value  : Mrays/s, rays already resident in HBM, one traversal kernel launch per step, CUDA events on the
            launching stream, max over ranks.
   e2e    : Mrays/s through the host-buffer C-ABI calls: pinned host rays -> H2D -> kernel -> D2H hit records inside
-           the timed region every step.  value = submit/wait flavour (rtbvh_gpu_intersect_async + rtbvh_gpu_wait,
-           two steps in flight); sync_call_value = the blocking rtbvh_gpu_intersect.
+           the timed region every step.  value = submit/wait flavour with split origin / direction arrays
+           (rtbvh_gpu_intersect_od_async + rtbvh_gpu_wait, two steps in flight, 24 B per ray);
+           rtray_async_value = the same with 32-byte RTRay records; sync_call_value = the blocking rtbvh_gpu_intersect.
   roofline.achieved : algorithmic bytes per ray (32 + 8 + 128*n_m + 40*n_p; n_m, n_p = node visits / triangle
            tests per ray counted by the instrumented CPU oracle on a sample of the same rays, SURVEY.md
            section 8d) x rays per launch / mean launch duration; peak = MEASURED_PEAKS.json hbm_gbs.
@@ -347,13 +348,38 @@ def run_gpu(args):
     e2e_ms = (time.perf_counter() - t0) * 1e3
     same_async = bool(torch.equal(h_hits[(e2e_steps - 1) % n_host].view(torch.int32),
                                   d_hits[(e2e_steps - 1) % n_host].cpu().view(torch.int32)))
+    e2e_rtray_ms = e2e_ms
+    # the same steps with the rays in the reference FFI's argument shape: origins[3n] + directions[3n] (24 B per ray across
+    # PCIe instead of 32; t_min = 1e-4 and t = 1e34 are the constants Ray::new sets, src/ray.rs:166-182)
+    h_o = [torch.empty(rays_per_step * 3, dtype=torch.float32).pin_memory() for _ in range(n_host)]
+    h_d = [torch.empty(rays_per_step * 3, dtype=torch.float32).pin_memory() for _ in range(n_host)]
+    for b in range(n_host):
+        r8 = h_rays[b].view(rays_per_step, 8)
+        h_o[b].view(rays_per_step, 3).copy_(r8[:, 0:3])
+        h_d[b].view(rays_per_step, 3).copy_(r8[:, 4:7])
+        h_hits[b].zero_()
+    for k in range(min(2, args.warmup)):
+        scene.intersect_od_ptr(h_o[k % n_host].data_ptr(), h_d[k % n_host].data_ptr(), rays_per_step, h_hits[k % n_host].data_ptr(),
+                               api.TREE_MBVH, 1e-4, 1e34)
+    barrier()
+    tickets = []
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        if k >= 2:
+            scene.wait(tickets[k - 2])
+        tickets.append(scene.intersect_od_async(h_o[k % n_host].data_ptr(), h_d[k % n_host].data_ptr(), rays_per_step,
+                                                h_hits[k % n_host].data_ptr(), api.TREE_MBVH, 1e-4, 1e34))
+    scene.wait(0)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    same_od = bool(torch.equal(h_hits[(e2e_steps - 1) % n_host].view(torch.int32),
+                               d_hits[(e2e_steps - 1) % n_host].cpu().view(torch.int32)))
     # the host-buffer path must agree with the resident path on the same rays
     same = bool(torch.equal(h_hits[0].view(torch.int32), d_hits[0].cpu().view(torch.int32)))
 
-    t = torch.tensor([ms, e2e_ms, e2e_sync_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_ms, e2e_sync_ms, e2e_rtray_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, e2e_sync_ms = float(t[0]), float(t[1]), float(t[2])
+    ms, e2e_ms, e2e_sync_ms, e2e_rtray_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         total_rays = world * args.steps * rays_per_step
@@ -403,13 +429,16 @@ def run_gpu(args):
                                     "GPU) + one-block device barrier per step, no NCCL on the data path" if gather == "fused"
                                     else "single GPU" if world == 1 else "rays sharded, tree replicated, no gather"), **info},
             "clocks": clocks, "gpu_launches": args.steps,
-            "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": rays_per_step * 32,
+            "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": rays_per_step * 24,
                     "d2h_bytes_per_step": rays_per_step * 8, "steps": e2e_steps,
-                    "host_equals_resident": same and same_async,
-                    "call": "rtbvh_gpu_intersect_async + rtbvh_gpu_wait, pinned host rays in / host hit records out every "
-                            "step, two steps in flight (double-buffered)",
+                    "host_equals_resident": same and same_async and same_od,
+                    "call": "rtbvh_gpu_intersect_od_async + rtbvh_gpu_wait: pinned host origins[3n] + directions[3n] in (the "
+                            "reference FFI's argument shape, 24 B per ray), host hit records out every step, two steps in "
+                            "flight (double-buffered)",
+                    "rtray_async_value": world * e2e_steps * rays_per_step / e2e_rtray_ms / 1e3,
+                    "rtray_async": "rtbvh_gpu_intersect_async + rtbvh_gpu_wait with 32-byte RTRay records (256 MB H2D per step)",
                     "sync_call_value": world * e2e_steps * rays_per_step / e2e_sync_ms / 1e3,
-                    "sync_call": "rtbvh_gpu_intersect (blocking: the pipeline fills and drains inside every call)"},
+                    "sync_call": "rtbvh_gpu_intersect with RTRay records (blocking: the pipeline fills and drains inside every call)"},
             "roofline": roof, "cpu_baseline": cpu,
         }
         sys.stdout.flush()

@@ -129,6 +129,21 @@ ResultCode rtbvh_gpu_intersect_async(RTGpuScene scene, RTTreeKind tree, const RT
 ResultCode rtbvh_gpu_occluded_async(RTGpuScene scene, RTTreeKind tree, const RTRay *rays, size_t ray_count,
                                     uint8_t *occluded, uint64_t *ticket);
 ResultCode rtbvh_gpu_wait(RTGpuScene scene, uint64_t ticket);
+/* Split ray input — the argument shape of the reference's FFI intersect (origin[3], direction[3], t:
+ * rtbvh_ffi/src/lib.rs:551-581) for a batch: origins and directions are tightly packed float3 arrays (12 bytes per ray
+ * each), t_min and t_max (the initial ray.t) apply to every ray.  Same results as the RTRay calls with those t_min / t;
+ * 24 instead of 32 bytes per ray cross PCIe, which is what bounds the host-buffer path.  Ray sorting is not applied. */
+ResultCode rtbvh_gpu_intersect_od(RTGpuScene scene, RTTreeKind tree, const float *origins, const float *directions,
+                                  size_t ray_count, float t_min, float t_max, RTHit *hits);
+ResultCode rtbvh_gpu_occluded_od(RTGpuScene scene, RTTreeKind tree, const float *origins, const float *directions,
+                                 size_t ray_count, float t_min, float t_max, uint8_t *occluded);
+ResultCode rtbvh_gpu_intersect_od_async(RTGpuScene scene, RTTreeKind tree, const float *origins, const float *directions,
+                                        size_t ray_count, float t_min, float t_max, RTHit *hits, uint64_t *ticket);
+ResultCode rtbvh_gpu_occluded_od_async(RTGpuScene scene, RTTreeKind tree, const float *origins, const float *directions,
+                                       size_t ray_count, float t_min, float t_max, uint8_t *occluded, uint64_t *ticket);
+ResultCode rtbvh_gpu_intersect_od_device(RTGpuScene scene, RTTreeKind tree, const float *d_origins,
+                                         const float *d_directions, size_t ray_count, float t_min, float t_max,
+                                         RTHit *d_hits, void *stream);
 ResultCode rtbvh_gpu_host_alloc(size_t bytes, void **ptr); /* page-locked host memory */
 ResultCode rtbvh_gpu_host_free(void *ptr);
 /* Packets follow SpatialTriangle::intersect4 (eps 1e-6, t >= t_min): pass t_min = 1e-4f to match

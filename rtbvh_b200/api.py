@@ -51,7 +51,8 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_intersect_device_scatter", "rtbvh_gpu_occluded_device_scatter", "rtbvh_gpu_peer_barrier",
                "rtbvh_gpu_intersect_async", "rtbvh_gpu_occluded_async", "rtbvh_gpu_wait", "rtbvh_gpu_host_alloc",
                "rtbvh_gpu_host_free", "rtbvh_gpu_scene_refit", "rtbvh_gpu_scene_refit_device", "rtbvh_gpu_scene_read_nodes",
-               "rtbvh_gpu_trim_workspace", "rtbvh_gpu_scene_build", "rtbvh_gpu_scene_build_device", "rtbvh_gpu_scene_tree_size", "rtbvh_gpu_scene_read_indices")
+               "rtbvh_gpu_intersect_od", "rtbvh_gpu_occluded_od", "rtbvh_gpu_intersect_od_async", "rtbvh_gpu_occluded_od_async",
+               "rtbvh_gpu_intersect_od_device", "rtbvh_gpu_trim_workspace", "rtbvh_gpu_scene_build", "rtbvh_gpu_scene_build_device", "rtbvh_gpu_scene_tree_size", "rtbvh_gpu_scene_read_indices")
 
 
 class RTBvh(C.Structure):  # rtbvh_ffi/src/lib.rs:210-220
@@ -151,6 +152,15 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_intersect_async.argtypes = [u64, C.c_int, vp, sz, vp, C.POINTER(u64)]
     L.rtbvh_gpu_occluded_async.restype = rc
     L.rtbvh_gpu_occluded_async.argtypes = [u64, C.c_int, vp, sz, vp, C.POINTER(u64)]
+    f32 = C.c_float
+    for name in ("rtbvh_gpu_intersect_od", "rtbvh_gpu_occluded_od"):
+        getattr(L, name).restype = rc
+        getattr(L, name).argtypes = [u64, C.c_int, vp, vp, sz, f32, f32, vp]
+    for name in ("rtbvh_gpu_intersect_od_async", "rtbvh_gpu_occluded_od_async"):
+        getattr(L, name).restype = rc
+        getattr(L, name).argtypes = [u64, C.c_int, vp, vp, sz, f32, f32, vp, C.POINTER(u64)]
+    L.rtbvh_gpu_intersect_od_device.restype = rc
+    L.rtbvh_gpu_intersect_od_device.argtypes = [u64, C.c_int, vp, vp, sz, f32, f32, vp, vp]
     L.rtbvh_gpu_wait.restype = rc
     L.rtbvh_gpu_wait.argtypes = [u64, u64]
     L.rtbvh_gpu_host_alloc.restype = rc
@@ -466,6 +476,34 @@ class Scene:
         t = C.c_uint64(0)
         _check(lib().rtbvh_gpu_occluded_async(self.handle, tree, C.c_void_p(rays_ptr), n, C.c_void_p(occ_ptr), C.byref(t)))
         return t.value
+
+    # ---- split ray input: origins / directions as packed float3 arrays, common t_min / t_max ----
+    def intersect_od(self, origins: np.ndarray, directions: np.ndarray, tree: int = TREE_MBVH, t_min: float = 1e-4,
+                     t_max: float = 1e34, any_hit: bool = False) -> np.ndarray:
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+        assert o.shape == d.shape
+        out = np.zeros(len(o), dtype=np.uint8 if any_hit else HIT_DTYPE)
+        fn = lib().rtbvh_gpu_occluded_od if any_hit else lib().rtbvh_gpu_intersect_od
+        _check(fn(self.handle, tree, _p(o), _p(d), len(o), t_min, t_max, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def intersect_od_async(self, origins_ptr: int, directions_ptr: int, n: int, hits_ptr: int, tree: int = TREE_MBVH,
+                           t_min: float = 1e-4, t_max: float = 1e34) -> int:
+        t = C.c_uint64(0)
+        _check(lib().rtbvh_gpu_intersect_od_async(self.handle, tree, C.c_void_p(origins_ptr), C.c_void_p(directions_ptr), n,
+                                                  t_min, t_max, C.c_void_p(hits_ptr), C.byref(t)))
+        return t.value
+
+    def intersect_od_ptr(self, origins_ptr: int, directions_ptr: int, n: int, hits_ptr: int, tree: int = TREE_MBVH,
+                         t_min: float = 1e-4, t_max: float = 1e34):
+        _check(lib().rtbvh_gpu_intersect_od(self.handle, tree, C.c_void_p(origins_ptr), C.c_void_p(directions_ptr), n, t_min,
+                                            t_max, C.c_void_p(hits_ptr)))
+
+    def intersect_od_device(self, d_origins, d_directions, n: int, d_hits, tree: int = TREE_MBVH, t_min: float = 1e-4,
+                            t_max: float = 1e34, stream: int = 0):
+        _check(lib().rtbvh_gpu_intersect_od_device(self.handle, tree, _dev_ptr(d_origins), _dev_ptr(d_directions), n, t_min,
+                                                   t_max, _dev_ptr(d_hits), C.c_void_p(stream)))
 
     def wait(self, ticket: int = 0):
         _check(lib().rtbvh_gpu_wait(self.handle, ticket))

@@ -44,7 +44,7 @@ constexpr int kTickets = 64;                     // outstanding asynchronous sub
 constexpr int kPipeStreams = 4;                  // H2D / kernel / D2H of consecutive chunks overlap
 constexpr size_t kChunkRays = size_t(1) << 21;   // capacity of one pipeline stage: 2 Mi rays (64 MiB of RTRay)
 constexpr uint32_t kCounterSlots = 1024;
-constexpr size_t kSubChunkRays = size_t(1) << 18;  // gated pipeline: watermark granularity (8 MiB of RTRay per H2D copy)
+constexpr size_t kSubChunkRays = size_t(1) << 19;  // gated pipeline: watermark granularity (measured: 256 Ki 1.48, 512 Ki 1.52, 1 Mi 1.38 Grays/s)
 constexpr size_t kMinChunkRays = size_t(1) << 17;  // gated pipeline: smallest launch (the tail of a batch ramps down to this)
 constexpr int kReadySlots = 64;
 constexpr int kMarkSlots = 4096;
@@ -94,6 +94,8 @@ struct Scene {
     void* d_out[kPipeStreams] = {};
     std::mutex pipe_mutex;
     uint64_t chunk_seq = 0;  // staging slot rotation across batches
+    uint64_t gated_seq = 0;  // watermark slot rotation (gated flavour)
+    int marks_used = 0;      // pinned watermark source values in flight (memcpy fallback of the gated flavour)
     struct Ticket {
         uint64_t id = 0;
         cudaEvent_t ev[kPipeStreams] = {};
@@ -165,18 +167,19 @@ ResultCode ensure_pipeline(Scene& s) {
     return Ok;
 }
 
-enum HostMode { kHostStaged = 0, kHostGated = 1 };
-// Measured on B200 (profiles/r2_host_pipeline.md): staged 1.33 Grays/s; gated 1.30-1.34; kernels reading pinned host
-// rays directly over PCIe 1.11; reading rays and writing records directly 0.74.  Staged stays the default.
-constexpr int kDefaultHostMode = kHostStaged;
+enum HostMode { kHostAuto = 0, kHostStaged = 1, kHostGated = 2 };
+// Measured on B200, 8 M rays per step, two steps in flight (profiles/r2_host_pipeline.md): RTRay records (32 B per ray:
+// the copy engine is the busier stage) staged 1.37 vs gated 1.32 Grays/s; split origin / direction input (24 B per ray: the
+// kernel is the busier stage) staged 1.39 vs gated 1.47.  Auto picks accordingly; RTBVH_HOST_MODE=staged|gated forces one.
+// Rejected: kernels reading pinned host rays directly over PCIe 1.11; reading rays and writing records directly 0.74.
 int host_mode() {
     static const int v = [] {
         const char* e = std::getenv("RTBVH_HOST_MODE");
-        if (!e) return kDefaultHostMode;
+        if (!e) return (int)kHostAuto;
         const std::string m(e);
         if (m == "staged") return (int)kHostStaged;
         if (m == "gated") return (int)kHostGated;
-        return kDefaultHostMode;
+        return (int)kHostAuto;
     }();
     return v;
 }
@@ -196,9 +199,12 @@ ResultCode check_overflow(Scene& s) {
 // own staging slot, so the copy engines and the SMs overlap across chunks — and across consecutive batches when the
 // caller does not wait in between (the *_async entry points).  The caller holds s.pipe_mutex.
 // unit_in / unit_out are bytes per ray (single) or per packet; rays_per_unit is 1 or 4.
+// `in2` (optional): a second input array of unit_in2 bytes per unit, staged kSecondInputOffset bytes into the slot (the
+// split origin / direction format).
+constexpr size_t kSecondInputOffset = kChunkRays * 12;
 template <class Launch>
 ResultCode enqueue_host_batch(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit,
-                              void* out, Launch&& launch) {
+                              void* out, Launch&& launch, const void* in2 = nullptr, size_t unit_in2 = 0) {
     // Chunk size: a synchronous call drains its pipeline before returning, so the first H2D and the last kernel + D2H
     // are not overlapped with anything; many small chunks keep that fill/drain cost low (a batch is cut into >= 16
     // chunks), a floor of 256 Ki rays keeps every launch big enough to fill the machine.  RTBVH_CHUNK_RAYS overrides.
@@ -230,8 +236,11 @@ ResultCode enqueue_host_batch(Scene& s, const void* in, size_t units, size_t uni
         cudaStream_t st = s.streams[k];
         mark(st);
         RTB_CUDA(cudaMemcpyAsync(s.d_in[k], (const char*)in + done * unit_in, m * unit_in, cudaMemcpyHostToDevice, st));
+        if (in2)
+            RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + kSecondInputOffset, (const char*)in2 + done * unit_in2, m * unit_in2,
+                                     cudaMemcpyHostToDevice, st));
         mark(st);
-        RTB_CUDA(launch(s.d_in[k], m, s.d_out[k], st));
+        RTB_CUDA(launch(s.d_in[k], m, s.d_out[k], (const unsigned long long*)nullptr, st));
         mark(st);
         RTB_CUDA(cudaMemcpyAsync((char*)out + done * unit_out, s.d_out[k], m * unit_out, cudaMemcpyDeviceToHost, st));
         mark(st);
@@ -249,16 +258,103 @@ ResultCode enqueue_host_batch(Scene& s, const void* in, size_t units, size_t uni
     return Ok;
 }
 
+// Gated flavour of enqueue_host_batch for single rays (RTBVH_HOST_MODE=gated): the batch is cut into a few large launches;
+// ONE copy stream uploads the rays back to back in 8 MiB pieces, each followed by a watermark write, and every launch starts
+// as soon as its staging slot is free — its warps wait on the watermark for ranges that have not arrived
+// (PeerDests::ready).  The copy engine never waits for a kernel boundary and a launch is never smaller than its slot, so the
+// per-launch drain (warps that can no longer refill) is paid once per 2 Mi rays instead of once per 0.5 Mi.
+// `ramp`: a blocking call shrinks the last launches (down to 128 Ki rays) so that little is left to trace after the last
+// byte has crossed PCIe; a stream of asynchronous batches keeps them large.  The caller holds s.pipe_mutex.
+template <class Launch>
+ResultCode enqueue_host_batch_gated(Scene& s, const void* in, size_t n, size_t unit_in, size_t unit_out, void* out, bool ramp,
+                                    Launch&& launch, const void* in2) {
+    cudaStream_t cp = s.copy_stream;
+    // watermark writes: cuStreamWriteValue64 when the driver exports it (fetched at run time: no link-time libcuda
+    // dependency), else an 8-byte H2D copy from a pinned table
+    typedef int (*WriteValue64)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
+    static const WriteValue64 write_value = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (std::getenv("RTBVH_GATE_MEMCPY") != nullptr) return (WriteValue64) nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (WriteValue64) nullptr;
+        }
+        return (WriteValue64)fn;
+    }();
+    static const size_t sub_rays = [] {
+        const char* e = std::getenv("RTBVH_SUBCHUNK_RAYS");
+        const size_t v = e ? (size_t)std::strtoull(e, nullptr, 10) : 0;
+        return v ? v : kSubChunkRays;
+    }();
+    size_t done = 0;
+    while (done < n) {
+        const uint64_t seq = s.gated_seq++;
+        const int k = (int)(s.chunk_seq++ % kPipeStreams);
+        const size_t left = n - done;
+        size_t m = std::min(kChunkRays, left);
+        if (ramp) {
+            m = std::min(kChunkRays, std::max(kMinChunkRays, ((left / 2 + kMinChunkRays - 1) / kMinChunkRays) * kMinChunkRays));
+            if (m > left || left - m < kMinChunkRays / 2) m = std::min(left, kChunkRays);
+        }
+        unsigned long long* ready = s.d_ready + (seq % kReadySlots);
+        // the staging slot (and the watermark slot, at most kPipeStreams launches are in flight) is free once everything
+        // enqueued on streams[k] so far — the launch that used the slot and its D2H — has finished
+        RTB_CUDA(cudaEventRecord(s.ev_done[k], s.streams[k]));
+        RTB_CUDA(cudaStreamWaitEvent(cp, s.ev_done[k], 0));
+        RTB_CUDA(cudaMemsetAsync(ready, 0, sizeof(unsigned long long), cp));
+        RTB_CUDA(cudaEventRecord(s.ev_start[k], cp));
+        RTB_CUDA(cudaStreamWaitEvent(s.streams[k], s.ev_start[k], 0));
+        RTB_CUDA(launch(s.d_in[k], m, s.d_out[k], (const unsigned long long*)ready, s.streams[k]));
+        for (size_t off = 0; off < m; off += sub_rays) {
+            const size_t sub = std::min(sub_rays, m - off);
+            RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + off * unit_in, (const char*)in + (done + off) * unit_in, sub * unit_in,
+                                     cudaMemcpyHostToDevice, cp));
+            if (in2)
+                RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + kSecondInputOffset + off * unit_in, (const char*)in2 + (done + off) * unit_in,
+                                         sub * unit_in, cudaMemcpyHostToDevice, cp));
+            if (write_value) {  // stream memory operation: no DMA set-up, ordered behind the copies like any stream work
+                if (write_value(cp, (unsigned long long)(uintptr_t)ready, off + sub, 0) != 0) return fail("cuStreamWriteValue64 failed");
+            } else {
+                if (s.marks_used == kMarkSlots) {  // the pinned source values of in-flight watermark copies must stay intact
+                    RTB_CUDA(cudaStreamSynchronize(cp));
+                    s.marks_used = 0;
+                }
+                s.h_marks[s.marks_used] = off + sub;
+                RTB_CUDA(cudaMemcpyAsync(ready, &s.h_marks[s.marks_used], sizeof(unsigned long long), cudaMemcpyHostToDevice, cp));
+                s.marks_used++;
+            }
+        }
+        // enqueued after the uploads: with a pageable `out` this call blocks until the launch has finished
+        RTB_CUDA(cudaMemcpyAsync((char*)out + done * unit_out, s.d_out[k], m * unit_out, cudaMemcpyDeviceToHost, s.streams[k]));
+        done += m;
+    }
+    return Ok;
+}
+
+// gate_ok: the call is a single-ray call in the caller's order (no ray sorting, default kernel), i.e. it may use the
+// gated flavour when RTBVH_HOST_MODE selects it.
+template <class Launch>
+ResultCode enqueue_any(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit, void* out,
+                       Launch&& launch, const void* in2, size_t unit_in2, bool gate_ok, bool blocking) {
+    const int mode = host_mode();
+    const bool gated = mode == kHostGated || (mode == kHostAuto && in2 != nullptr);
+    if (gate_ok && gated && (in2 == nullptr || unit_in2 == unit_in))
+        return enqueue_host_batch_gated(s, in, units, unit_in, unit_out, out, blocking, launch, in2);
+    return enqueue_host_batch(s, in, units, unit_in, unit_out, rays_per_unit, out, launch, in2, unit_in2);
+}
+
 // Synchronous host-buffer call: enqueue, drain, check.
 template <class Launch>
 ResultCode run_host_batch(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit,
-                          void* out, Launch&& launch) {
+                          void* out, Launch&& launch, const void* in2 = nullptr, size_t unit_in2 = 0, bool gate_ok = false) {
     if (units == 0) return Ok;
     if (!in || !out) return fail("null host buffer");
     std::lock_guard<std::mutex> lk(s.pipe_mutex);
     RTB_CUDA(cudaSetDevice(s.device));
     if (ensure_pipeline(s) != Ok) return Error;
-    if (enqueue_host_batch(s, in, units, unit_in, unit_out, rays_per_unit, out, launch) != Ok) return Error;
+    if (enqueue_any(s, in, units, unit_in, unit_out, rays_per_unit, out, launch, in2, unit_in2, gate_ok, true) != Ok) return Error;
+    RTB_CUDA(cudaStreamSynchronize(s.copy_stream));
     for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s.streams[i]));
     return check_overflow(s);
 }
@@ -268,7 +364,8 @@ ResultCode run_host_batch(Scene& s, const void* in, size_t units, size_t unit_in
 // traces / downloads: the per-call pipeline fill and drain disappear from a steady stream of batches.
 template <class Launch>
 ResultCode submit_host_batch(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit,
-                             void* out, uint64_t* ticket, Launch&& launch) {
+                             void* out, uint64_t* ticket, Launch&& launch, const void* in2 = nullptr, size_t unit_in2 = 0,
+                             bool gate_ok = false) {
     if (!ticket) return fail("null ticket");
     if (units != 0 && (!in || !out)) return fail("null host buffer");
     std::unique_lock<std::mutex> lk(s.pipe_mutex);
@@ -279,7 +376,8 @@ ResultCode submit_host_batch(Scene& s, const void* in, size_t units, size_t unit
     if (t.id != 0) {  // the ring wrapped onto a ticket nobody waited for: it must have completed before its events are reused
         for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaEventSynchronize(t.ev[i]));
     }
-    if (units != 0 && enqueue_host_batch(s, in, units, unit_in, unit_out, rays_per_unit, out, launch) != Ok) return Error;
+    if (units != 0 && enqueue_any(s, in, units, unit_in, unit_out, rays_per_unit, out, launch, in2, unit_in2, gate_ok, false) != Ok)
+        return Error;
     for (int i = 0; i < kPipeStreams; i++) {
         if (!t.ev[i]) RTB_CUDA(cudaEventCreateWithFlags(&t.ev[i], cudaEventDisableTiming));
         RTB_CUDA(cudaEventRecord(t.ev[i], s.streams[i]));
@@ -306,104 +404,6 @@ ResultCode wait_ticket(Scene& s, uint64_t ticket) {
         for (int i = 0; i < kPipeStreams; i++) ev[i] = t.ev[i];
     }
     for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaEventSynchronize(ev[i]));
-    return check_overflow(s);
-}
-
-// Host-buffer batch of single rays, gated: the batch is cut into a few launches (<= 2 Mi rays, ramping down to 128 Ki
-// at the end); ONE copy stream uploads the rays back to back in 8 MiB pieces, each followed by an 8-byte watermark copy,
-// and every launch starts as soon as its slot is free — its warps wait on the watermark for ranges that have not arrived
-// (PeerDests::ready).  The copy engine therefore never waits for a kernel boundary, kernels of consecutive launches
-// overlap (streams), and what is left after the last byte has crossed PCIe is the traversal of the last 128 Ki rays and
-// a 1 MiB D2H.  launch(din, m, dout, ready, stream).
-template <class Launch>
-ResultCode run_host_batch_gated(Scene& s, const RTRay* in, size_t n, size_t unit_out, void* out, Launch&& launch) {
-    if (n == 0) return Ok;
-    if (!in || !out) return fail("null host buffer");
-    std::lock_guard<std::mutex> lk(s.pipe_mutex);
-    RTB_CUDA(cudaSetDevice(s.device));
-    if (ensure_pipeline(s) != Ok) return Error;
-    cudaStream_t cp = s.copy_stream;
-    // watermark writes: cuStreamWriteValue64 when the driver exports it (fetched at run time: no link-time libcuda
-    // dependency), else an 8-byte H2D copy from a pinned table
-    typedef int (*WriteValue64)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
-    static const WriteValue64 write_value = [] {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        if (std::getenv("RTBVH_GATE_MEMCPY") != nullptr) return (WriteValue64) nullptr;
-        if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            return (WriteValue64) nullptr;
-        }
-        return (WriteValue64)fn;
-    }();
-    static const size_t sub_rays = [] {
-        const char* e = std::getenv("RTBVH_SUBCHUNK_RAYS");
-        const size_t v = e ? (size_t)std::strtoull(e, nullptr, 10) : 0;
-        return v ? v : kSubChunkRays;
-    }();
-    int marks = 0;
-    size_t done = 0;
-    static const bool trace = std::getenv("RTBVH_PIPE_TRACE") != nullptr;  // debug: per-launch timeline on stderr
-    std::vector<cudaEvent_t> ev;
-    std::vector<size_t> ev_m;
-    auto mark = [&](cudaStream_t st) {
-        if (!trace) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, st);
-        ev.push_back(e);
-    };
-    mark(cp);
-    for (int c = 0; done < n; c++) {
-        const int k = c % kPipeStreams;
-        const size_t left = n - done;
-        size_t m = std::min(kChunkRays, std::max(kMinChunkRays, ((left / 2 + kMinChunkRays - 1) / kMinChunkRays) * kMinChunkRays));
-        if (m > left || left - m < kMinChunkRays / 2) m = std::min(left, kChunkRays);
-        unsigned long long* ready = s.d_ready + (c % kReadySlots);
-        // slot k is free once the launch that used it has finished (its D2H follows it on streams[k] anyway)
-        if (c >= kPipeStreams) RTB_CUDA(cudaStreamWaitEvent(cp, s.ev_done[k], 0));
-        RTB_CUDA(cudaMemsetAsync(ready, 0, sizeof(unsigned long long), cp));
-        RTB_CUDA(cudaEventRecord(s.ev_start[k], cp));
-        RTB_CUDA(cudaStreamWaitEvent(s.streams[k], s.ev_start[k], 0));
-        mark(s.streams[k]);
-        RTB_CUDA(launch(s.d_in[k], m, s.d_out[k], ready, s.streams[k]));
-        RTB_CUDA(cudaEventRecord(s.ev_done[k], s.streams[k]));
-        mark(s.streams[k]);
-        mark(cp);
-        ev_m.push_back(m);
-        for (size_t off = 0; off < m; off += sub_rays) {
-            const size_t sub = std::min(sub_rays, m - off);
-            RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + off * sizeof(RTRay), in + done + off, sub * sizeof(RTRay),
-                                     cudaMemcpyHostToDevice, cp));
-            if (marks == kMarkSlots) {  // the pinned source values of in-flight watermark copies must stay intact
-                RTB_CUDA(cudaStreamSynchronize(cp));
-                marks = 0;
-            }
-            if (write_value) {  // stream memory operation: no DMA set-up, ordered behind the copy like any stream work
-                if (write_value(cp, (unsigned long long)(uintptr_t)ready, off + sub, 0) != 0) return fail("cuStreamWriteValue64 failed");
-            } else {
-                s.h_marks[marks] = off + sub;
-                RTB_CUDA(cudaMemcpyAsync(ready, &s.h_marks[marks], sizeof(unsigned long long), cudaMemcpyHostToDevice, cp));
-                marks++;
-            }
-        }
-        // enqueued after the uploads: with a pageable `out` this call blocks until the launch has finished
-        mark(cp);
-        RTB_CUDA(cudaMemcpyAsync((char*)out + done * unit_out, s.d_out[k], m * unit_out, cudaMemcpyDeviceToHost, s.streams[k]));
-        mark(s.streams[k]);
-        done += m;
-    }
-    RTB_CUDA(cudaStreamSynchronize(cp));
-    for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s.streams[i]));
-    if (trace) {
-        for (size_t c = 0; 1 + 5 * c + 4 < ev.size(); c++) {
-            float t[5];
-            for (int j = 0; j < 5; j++) cudaEventElapsedTime(&t[j], ev[0], ev[1 + 5 * c + j]);
-            std::fprintf(stderr, "launch %2zu (%7zu rays): h2d %.3f-%.3f  kernel %.3f-%.3f  d2h -%.3f ms\n", c, ev_m[c], t[2], t[3],
-                         t[0], t[1], t[4]);
-        }
-        for (auto e : ev) cudaEventDestroy(e);
-    }
     return check_overflow(s);
 }
 
@@ -789,66 +789,92 @@ ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene h, uint32_t* overflowed) 
 }
 
 // ---- host buffers ------------------------------------------------------------------------------
-ResultCode rtbvh_gpu_intersect(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, RTHit* hits) {
+// One launch of the single-ray kernel for a staged chunk: RTRay records in `din`; `ready` is the gated flavour's watermark.
+static ResultCode rtray_host_call(RTGpuScene h, RTTreeKind tree, bool any, const RTRay* rays, size_t n, void* out, uint64_t* ticket,
+                                  bool async) {
     auto s = get_scene(h);
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
-    if (host_mode() == kHostGated && !s->sort_bounds() && persistent_mode() == kTracePersistent)
-        return run_host_batch_gated(*s, rays, n, sizeof(RTHit), hits,
-                                    [&](void* din, size_t m, void* dout, const unsigned long long* ready, cudaStream_t st) {
-                                        PeerDests pd{};
-                                        pd.ready = ready;
-                                        return launch_trace_single(*t, tree, false, (const RTRay*)din, m, (RTHit*)dout, nullptr,
-                                                                   s->counter_slot(), s->d_overflow, kTracePersistent, nullptr, &pd, st);
-                                    });
-    return run_host_batch(*s, rays, n, sizeof(RTRay), sizeof(RTHit), 1, hits,
-                          [&](void* din, size_t m, void* dout, cudaStream_t st) {
-                              return launch_trace_single(*t, tree, false, (const RTRay*)din, m, (RTHit*)dout, nullptr,
-                                                         s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), nullptr, st);
-                          });
+    const bool gate_ok = !s->sort_bounds() && persistent_mode() == kTracePersistent;
+    auto launch = [&](void* din, size_t m, void* dout, const unsigned long long* ready, cudaStream_t st) {
+        PeerDests pd{};
+        pd.ready = ready;
+        return launch_trace_single(*t, tree, any, (const RTRay*)din, m, any ? nullptr : (RTHit*)dout, any ? (uint8_t*)dout : nullptr,
+                                   s->counter_slot(), s->d_overflow, ready ? (int)kTracePersistent : persistent_mode(),
+                                   ready ? nullptr : s->sort_bounds(), ready ? &pd : nullptr, st);
+    };
+    const size_t unit_out = any ? 1 : sizeof(RTHit);
+    if (async) return submit_host_batch(*s, rays, n, sizeof(RTRay), unit_out, 1, out, ticket, launch, nullptr, 0, gate_ok);
+    return run_host_batch(*s, rays, n, sizeof(RTRay), unit_out, 1, out, launch, nullptr, 0, gate_ok);
+}
+ResultCode rtbvh_gpu_intersect(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, RTHit* hits) {
+    return rtray_host_call(h, tree, false, rays, n, hits, nullptr, false);
 }
 ResultCode rtbvh_gpu_occluded(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, uint8_t* occluded) {
-    auto s = get_scene(h);
-    if (!s) return fail("unknown scene");
-    const DeviceTree* t = pick_tree(*s, tree);
-    if (!t) return fail("scene has no such tree");
-    if (host_mode() == kHostGated && !s->sort_bounds() && persistent_mode() == kTracePersistent)
-        return run_host_batch_gated(*s, rays, n, 1, occluded,
-                                    [&](void* din, size_t m, void* dout, const unsigned long long* ready, cudaStream_t st) {
-                                        PeerDests pd{};
-                                        pd.ready = ready;
-                                        return launch_trace_single(*t, tree, true, (const RTRay*)din, m, nullptr, (uint8_t*)dout,
-                                                                   s->counter_slot(), s->d_overflow, kTracePersistent, nullptr, &pd, st);
-                                    });
-    return run_host_batch(*s, rays, n, sizeof(RTRay), 1, 1, occluded,
-                          [&](void* din, size_t m, void* dout, cudaStream_t st) {
-                              return launch_trace_single(*t, tree, true, (const RTRay*)din, m, nullptr, (uint8_t*)dout,
-                                                         s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), nullptr, st);
-                          });
+    return rtray_host_call(h, tree, true, rays, n, occluded, nullptr, false);
 }
 // ---- host buffers, asynchronous: submit / wait ------------------------------------------------------------------
 ResultCode rtbvh_gpu_intersect_async(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, RTHit* hits, uint64_t* ticket) {
-    auto s = get_scene(h);
-    if (!s) return fail("unknown scene");
-    const DeviceTree* t = pick_tree(*s, tree);
-    if (!t) return fail("scene has no such tree");
-    return submit_host_batch(*s, rays, n, sizeof(RTRay), sizeof(RTHit), 1, hits, ticket,
-                             [&](void* din, size_t m, void* dout, cudaStream_t st) {
-                                 return launch_trace_single(*t, tree, false, (const RTRay*)din, m, (RTHit*)dout, nullptr,
-                                                            s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), nullptr, st);
-                             });
+    return rtray_host_call(h, tree, false, rays, n, hits, ticket, true);
 }
 ResultCode rtbvh_gpu_occluded_async(RTGpuScene h, RTTreeKind tree, const RTRay* rays, size_t n, uint8_t* occluded, uint64_t* ticket) {
+    return rtray_host_call(h, tree, true, rays, n, occluded, ticket, true);
+}
+// ---- split ray input: origins[3n], directions[3n], common t_min / t_max (24 B per ray across PCIe) -----------------
+static cudaError_t launch_od(Scene& s, const DeviceTree& t, RTTreeKind tree, bool any, const float* d_origins,
+                             const float* d_directions, size_t m, float t_min, float t_max, void* d_out,
+                             const unsigned long long* ready, cudaStream_t st) {
+    PeerDests pd{};
+    pd.ready = ready;
+    pd.directions = d_directions;
+    pd.t_min = t_min;
+    pd.t_max = t_max;
+    return launch_trace_single(t, tree, any, reinterpret_cast<const RTRay*>(d_origins), m, any ? nullptr : (RTHit*)d_out,
+                               any ? (uint8_t*)d_out : nullptr, s.counter_slot(), s.d_overflow, kTracePersistent, nullptr, &pd, st);
+}
+static ResultCode od_host_call(RTGpuScene h, RTTreeKind tree, bool any, const float* origins, const float* directions, size_t n,
+                               float t_min, float t_max, void* out, uint64_t* ticket) {
     auto s = get_scene(h);
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
-    return submit_host_batch(*s, rays, n, sizeof(RTRay), 1, 1, occluded, ticket,
-                             [&](void* din, size_t m, void* dout, cudaStream_t st) {
-                                 return launch_trace_single(*t, tree, true, (const RTRay*)din, m, nullptr, (uint8_t*)dout,
-                                                            s->counter_slot(), s->d_overflow, persistent_mode(), s->sort_bounds(), nullptr, st);
-                             });
+    if (n != 0 && !directions) return fail("null host buffer");
+    auto launch = [&](void* din, size_t m, void* dout, const unsigned long long* ready, cudaStream_t st) {
+        return launch_od(*s, *t, tree, any, (const float*)din, (const float*)((const char*)din + kSecondInputOffset), m, t_min, t_max,
+                         dout, ready, st);
+    };
+    const size_t unit_out = any ? 1 : sizeof(RTHit);
+    if (ticket) return submit_host_batch(*s, origins, n, 12, unit_out, 1, out, ticket, launch, directions, 12, true);
+    return run_host_batch(*s, origins, n, 12, unit_out, 1, out, launch, directions, 12, true);
+}
+ResultCode rtbvh_gpu_intersect_od(RTGpuScene h, RTTreeKind tree, const float* origins, const float* directions, size_t n,
+                                  float t_min, float t_max, RTHit* hits) {
+    return od_host_call(h, tree, false, origins, directions, n, t_min, t_max, hits, nullptr);
+}
+ResultCode rtbvh_gpu_occluded_od(RTGpuScene h, RTTreeKind tree, const float* origins, const float* directions, size_t n,
+                                 float t_min, float t_max, uint8_t* occluded) {
+    return od_host_call(h, tree, true, origins, directions, n, t_min, t_max, occluded, nullptr);
+}
+ResultCode rtbvh_gpu_intersect_od_async(RTGpuScene h, RTTreeKind tree, const float* origins, const float* directions, size_t n,
+                                        float t_min, float t_max, RTHit* hits, uint64_t* ticket) {
+    if (!ticket) return fail("null ticket");
+    return od_host_call(h, tree, false, origins, directions, n, t_min, t_max, hits, ticket);
+}
+ResultCode rtbvh_gpu_occluded_od_async(RTGpuScene h, RTTreeKind tree, const float* origins, const float* directions, size_t n,
+                                       float t_min, float t_max, uint8_t* occluded, uint64_t* ticket) {
+    if (!ticket) return fail("null ticket");
+    return od_host_call(h, tree, true, origins, directions, n, t_min, t_max, occluded, ticket);
+}
+ResultCode rtbvh_gpu_intersect_od_device(RTGpuScene h, RTTreeKind tree, const float* d_origins, const float* d_directions,
+                                         size_t n, float t_min, float t_max, RTHit* d_hits, void* stream) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    const DeviceTree* t = pick_tree(*s, tree);
+    if (!t) return fail("scene has no such tree");
+    if (n != 0 && (!d_origins || !d_directions || !d_hits)) return fail("null device buffer");
+    RTB_CUDA(launch_od(*s, *t, tree, false, d_origins, d_directions, n, t_min, t_max, d_hits, nullptr, (cudaStream_t)stream));
+    return Ok;
 }
 ResultCode rtbvh_gpu_wait(RTGpuScene h, uint64_t ticket) {
     auto s = get_scene(h);
@@ -872,7 +898,7 @@ ResultCode rtbvh_gpu_intersect_packets(RTGpuScene h, RTTreeKind tree, const RTRa
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
     return run_host_batch(*s, packets, n, sizeof(RTRayPacket4), sizeof(RTHitPacket4), 4, hits,
-                          [&](void* din, size_t m, void* dout, cudaStream_t st) {
+                          [&](void* din, size_t m, void* dout, const unsigned long long*, cudaStream_t st) {
                               return launch_trace_packets(*t, tree, false, (const RTRayPacket4*)din, m, t_min,
                                                           (RTHitPacket4*)dout, nullptr, s->counter_slot(), s->d_overflow,
                                                           packet_mode(), st);
@@ -885,7 +911,7 @@ ResultCode rtbvh_gpu_occluded_packets(RTGpuScene h, RTTreeKind tree, const RTRay
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
     return run_host_batch(*s, packets, n, sizeof(RTRayPacket4), 4, 4, occluded,
-                          [&](void* din, size_t m, void* dout, cudaStream_t st) {
+                          [&](void* din, size_t m, void* dout, const unsigned long long*, cudaStream_t st) {
                               return launch_trace_packets(*t, tree, true, (const RTRayPacket4*)din, m, t_min, nullptr,
                                                           (uint8_t*)dout, s->counter_slot(), s->d_overflow, packet_mode(), st);
                           });

@@ -30,7 +30,10 @@ namespace {
 
 constexpr int kSmemStack = 32;    // entries kept in shared memory (the reference's whole stack, src/iter.rs:25)
 constexpr int kSpillStack = 96;   // further entries spill to thread-local memory (only touched by deep rays); beyond 128 -> overflow flag
-constexpr int kBlock = 128;
+#ifndef RTB_BLOCK
+#define RTB_BLOCK 128
+#endif
+constexpr int kBlock = RTB_BLOCK;
 #ifndef RTB_REFILL
 #define RTB_REFILL 8
 #endif
@@ -489,6 +492,16 @@ __device__ __forceinline__ void load_ray_cg(const RTRay* __restrict__ rays, size
     r.dx = b.x; r.dy = b.y; r.dz = b.z; r.t = b.w;
     finish_ray_setup(r);
 }
+// Split input: origins (the kernel's ray pointer) and directions as tightly packed float3 arrays, common t_min / t.
+__device__ __forceinline__ void load_ray_od(const float* __restrict__ origins, const PeerDests& pd, size_t i, RayRegs& r) {
+    const float* o = origins + i * 3;
+    const float* d = pd.directions + i * 3;
+    r.ox = __ldcg(o); r.oy = __ldcg(o + 1); r.oz = __ldcg(o + 2);
+    r.dx = __ldcg(d); r.dy = __ldcg(d + 1); r.dz = __ldcg(d + 2);
+    r.t_min = pd.t_min;
+    r.t = pd.t_max;
+    finish_ray_setup(r);
+}
 // Result store.  With peer destinations (multi-GPU gather fused into the kernel) the record is also written,
 // the moment its ray finishes, into the gather buffer of every peer GPU (P2P stores over NVLink / NVSwitch to
 // cudaIpc-mapped memory): the transfer overlaps the traversal ray by ray and no collective follows the kernel.
@@ -601,7 +614,9 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                 if (!active && rank < take) {
                     my = (size_t)(res_next + rank);
                     if (perm) my = (size_t)perm[my];
-                    if (pd.ready)
+                    if (pd.directions)
+                        load_ray_od(reinterpret_cast<const float*>(rays), pd, my, r);
+                    else if (pd.ready)
                         load_ray_cg(rays, my, r);
                     else
                         load_ray(rays, my, r);
@@ -966,7 +981,7 @@ template <int TREE, bool ANY>
 static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
                                    uint8_t* d_occluded, const uint32_t* d_perm, unsigned long long* d_counter,
                                    uint32_t* d_overflow, int mode, const PeerDests& pd, cudaStream_t stream) {
-    if ((pd.count > 0 || pd.ready) && mode != kTracePersistent) return cudaErrorNotSupported;  // fused gather / input gate live in the default kernel
+    if ((pd.count > 0 || pd.ready || pd.directions) && mode != kTracePersistent) return cudaErrorNotSupported;  // fused gather / input gate / split input live in the default kernel
     const size_t blocks_needed = ceil_div(n, kBlock);
     const bool persistent = mode != kTraceStatic;
     if (TREE == RT_TREE_MBVH && mode == kTraceCoop) {
@@ -998,7 +1013,7 @@ cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any,
     if (n == 0) return cudaSuccess;
     PeerDests pd{};
     if (peers) pd = *peers;
-    if (pd.ready && (sort_bounds != nullptr || mode != kTracePersistent)) return cudaErrorNotSupported;  // gate: default kernel, caller's order
+    if ((pd.ready || pd.directions) && (sort_bounds != nullptr || mode != kTracePersistent)) return cudaErrorNotSupported;  // gate / split input: default kernel, caller's order
     uint32_t* d_perm = nullptr;
     void* scratch = nullptr;
     if (sort_bounds != nullptr && n >= 4096 && n < (size_t(1) << 32)) {

@@ -21,6 +21,11 @@ struct PeerDests {
     // whose H2D copy has completed (written by the copy engine, stream-ordered behind each sub-chunk): a warp that
     // reserves rays [a, b) waits until *ready >= b, so ONE launch can start while its input is still arriving.
     const unsigned long long* ready;
+    // Split ray input (the argument shape of the reference's FFI intersect: origin[3], direction[3], t; rtbvh_ffi/src/lib.rs:
+    // 551-581): when `directions` is set, the kernel's ray pointer addresses 3 floats of origin per ray, `directions` 3 floats
+    // of direction per ray, and t_min / t_max apply to every ray — 24 instead of 32 bytes per ray across PCIe.
+    const float* directions;
+    float t_min, t_max;
 };
 // sort_bounds: null = trace in the caller's order; else {min xyz, max xyz} of the scene: the batch is traced in
 // Morton order of (origin, direction) and results are scattered back (same results, better coherence).

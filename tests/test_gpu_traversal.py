@@ -331,8 +331,56 @@ def test_gated_host_pipeline_in_a_subprocess(A):
         "    want = O.trace(m, tris, rays, threads=8)[0]\n"
         "    assert np.array_equal(sc.intersect(rays, api.TREE_MBVH), want), n\n"
         "    assert np.array_equal(sc.occluded(rays, api.TREE_MBVH), O.trace(m, tris, rays, mode='any', threads=8)[0]), n\n"
+        "    o = np.ascontiguousarray(rays['origin']); d = np.ascontiguousarray(rays['direction'])\n"
+        "    assert np.array_equal(sc.intersect_od(o, d, api.TREE_MBVH), want), n\n"
+        "import torch\n"
+        "rays = [W.random_rays(3_000_000, *W.bounds(tris), seed=k) for k in range(3)]\n"
+        "hr = [torch.from_numpy(r.view(np.float32).reshape(-1).copy()).pin_memory() for r in rays]\n"
+        "ho = [torch.from_numpy(np.ascontiguousarray(r['origin']).reshape(-1)).pin_memory() for r in rays]\n"
+        "hd = [torch.from_numpy(np.ascontiguousarray(r['direction']).reshape(-1)).pin_memory() for r in rays]\n"
+        "hh = [torch.zeros(6_000_000, dtype=torch.float32).pin_memory() for _ in range(6)]\n"
+        "tk = [sc.intersect_async(hr[k].data_ptr(), 3_000_000, hh[k].data_ptr(), api.TREE_MBVH) for k in range(3)]\n"
+        "tk += [sc.intersect_od_async(ho[k].data_ptr(), hd[k].data_ptr(), 3_000_000, hh[3 + k].data_ptr(), api.TREE_MBVH) for k in range(3)]\n"
+        "sc.wait(0)\n"
+        "for k in range(3):\n"
+        "    want = O.trace(m, tris, rays[k], threads=8)[0]\n"
+        "    assert np.array_equal(hh[k].numpy().view(api.HIT_DTYPE).reshape(-1), want), k\n"
+        "    assert np.array_equal(hh[3 + k].numpy().view(api.HIT_DTYPE).reshape(-1), want), k\n"
         "print('gated ok')\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, RTBVH_HOST_MODE="gated")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "gated ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_split_origin_direction_input(A, O, W, teapot, teapot_trees):
+    """rtbvh_gpu_intersect_od / _occluded_od / _od_async / _od_device: origins and directions as packed float3 arrays with a
+    common t_min / t_max (the reference FFI's argument shape) give the records of the RTRay calls, bit for bit."""
+    import torch
+    tris = teapot["tris"]
+    bvh, m = teapot_trees["sah"]
+    sc = _scene(A, tris, bvh, m)
+    try:
+        for n, t_max in ((1, 1e34), (100_003, 1e34), (300_000, 9.5)):
+            rays = W.random_rays(n, *W.bounds(tris), seed=0x0D + n)
+            rays["t"] = np.float32(t_max)
+            o = np.ascontiguousarray(rays["origin"]); d = np.ascontiguousarray(rays["direction"])
+            for tree, otree in ((A.TREE_BVH, bvh), (A.TREE_MBVH, m)):
+                want = O.trace(otree, tris, rays)[0]
+                assert np.array_equal(sc.intersect_od(o, d, tree, 1e-4, t_max), want), (n, tree)
+                assert np.array_equal(sc.intersect_od(o, d, tree, 1e-4, t_max, any_hit=True), O.trace(otree, tris, rays, mode="any")[0])
+            # asynchronous, pinned
+            ho, hd = torch.from_numpy(o.reshape(-1).copy()).pin_memory(), torch.from_numpy(d.reshape(-1).copy()).pin_memory()
+            hh = torch.zeros(n * 2, dtype=torch.float32).pin_memory()
+            t = sc.intersect_od_async(ho.data_ptr(), hd.data_ptr(), n, hh.data_ptr(), A.TREE_MBVH, 1e-4, t_max)
+            sc.wait(t)
+            assert np.array_equal(hh.numpy().view(A.HIT_DTYPE).reshape(-1), O.trace(m, tris, rays)[0])
+            # device resident
+            do, dd = ho.cuda(), hd.cuda()
+            dh = torch.zeros(n * 2, dtype=torch.float32, device="cuda")
+            sc.intersect_od_device(do, dd, n, dh, A.TREE_MBVH, 1e-4, t_max, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert np.array_equal(dh.cpu().numpy().view(A.HIT_DTYPE).reshape(-1), O.trace(m, tris, rays)[0])
+        assert len(sc.intersect_od(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))) == 0
+    finally:
+        sc.free()
