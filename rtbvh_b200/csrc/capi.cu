@@ -42,7 +42,8 @@ namespace {
 
 constexpr int kTickets = 64;                     // outstanding asynchronous submissions per scene
 constexpr int kPipeStreams = 4;                  // H2D / kernel / D2H of consecutive chunks overlap
-constexpr size_t kChunkRays = size_t(1) << 21;   // capacity of one pipeline stage: 2 Mi rays (64 MiB of RTRay)
+constexpr size_t kChunkRays = size_t(1) << 21;   // initial capacity of one staging slot: 2 Mi rays (64 MiB of RTRay)
+constexpr size_t kMaxSlotRays = size_t(1) << 23; // the gated flavour grows the slots up to 8 Mi rays: one launch per 8 M-ray batch
 constexpr uint32_t kCounterSlots = 1024;
 constexpr size_t kSubChunkRays = size_t(1) << 19;  // gated pipeline: watermark granularity (measured: 256 Ki 1.48, 512 Ki 1.52, 1 Mi 1.38 Grays/s)
 constexpr size_t kMinChunkRays = size_t(1) << 17;  // gated pipeline: smallest launch (the tail of a batch ramps down to this)
@@ -93,6 +94,7 @@ struct Scene {
     void* d_in[kPipeStreams] = {};
     void* d_out[kPipeStreams] = {};
     std::mutex pipe_mutex;
+    size_t slot_rays = 0;    // capacity of one staging slot
     uint64_t chunk_seq = 0;  // staging slot rotation across batches
     uint64_t gated_seq = 0;  // watermark slot rotation (gated flavour)
     int marks_used = 0;      // pinned watermark source values in flight (memcpy fallback of the gated flavour)
@@ -152,12 +154,30 @@ const DeviceTree* pick_tree(const Scene& s, RTTreeKind kind) {
     return t;
 }
 
-ResultCode ensure_pipeline(Scene& s) {
+// Staging slots hold `slot_rays` rays each (RTRay records, or origins at offset 0 and directions at slot_rays * 12; a packet
+// chunk is slot_rays / 4 * 112 B < this).  want_rays > slot_rays: drain the pipeline and grow the slots.
+ResultCode ensure_pipeline(Scene& s, size_t want_rays = 0) {
+    if (s.streams[0] && want_rays > s.slot_rays) {
+        for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s.streams[i]));
+        RTB_CUDA(cudaStreamSynchronize(s.copy_stream));
+        for (int i = 0; i < kPipeStreams; i++) {
+            cudaFree(s.d_in[i]);
+            cudaFree(s.d_out[i]);
+            s.d_in[i] = s.d_out[i] = nullptr;
+        }
+        s.slot_rays = want_rays;
+        for (int i = 0; i < kPipeStreams; i++) {
+            RTB_CUDA(cudaMalloc(&s.d_in[i], s.slot_rays * sizeof(RTRay)));
+            RTB_CUDA(cudaMalloc(&s.d_out[i], s.slot_rays * sizeof(RTHit)));
+        }
+        return Ok;
+    }
     if (s.streams[0]) return Ok;
+    s.slot_rays = std::max(kChunkRays, want_rays);
     for (int i = 0; i < kPipeStreams; i++) {
         RTB_CUDA(cudaStreamCreateWithFlags(&s.streams[i], cudaStreamNonBlocking));
-        RTB_CUDA(cudaMalloc(&s.d_in[i], kChunkRays * sizeof(RTRay)));  // a packet chunk is kChunkRays/4 * 112 B < this
-        RTB_CUDA(cudaMalloc(&s.d_out[i], kChunkRays * sizeof(RTHit)));
+        RTB_CUDA(cudaMalloc(&s.d_in[i], s.slot_rays * sizeof(RTRay)));
+        RTB_CUDA(cudaMalloc(&s.d_out[i], s.slot_rays * sizeof(RTHit)));
         RTB_CUDA(cudaEventCreateWithFlags(&s.ev_start[i], cudaEventDisableTiming));
         RTB_CUDA(cudaEventCreateWithFlags(&s.ev_done[i], cudaEventDisableTiming));
     }
@@ -168,9 +188,10 @@ ResultCode ensure_pipeline(Scene& s) {
 }
 
 enum HostMode { kHostAuto = 0, kHostStaged = 1, kHostGated = 2 };
-// Measured on B200, 8 M rays per step, two steps in flight (profiles/r2_host_pipeline.md): RTRay records (32 B per ray:
-// the copy engine is the busier stage) staged 1.37 vs gated 1.32 Grays/s; split origin / direction input (24 B per ray: the
-// kernel is the busier stage) staged 1.39 vs gated 1.47.  Auto picks accordingly; RTBVH_HOST_MODE=staged|gated forces one.
+// Measured on B200, 8 M rays per step, two steps in flight (profiles/r2_host_pipeline.md), staged (16 chunks over 4 streams)
+// vs gated (one launch per batch that starts before its input has arrived): RTRay records 1.37 vs 1.51 Grays/s, split
+// origin / direction input 1.39 vs 1.74-1.83; blocking calls 1.35 vs 1.36.  Auto = gated wherever the call allows it (single
+// rays, caller's order, default kernel); RTBVH_HOST_MODE=staged|gated forces one.
 // Rejected: kernels reading pinned host rays directly over PCIe 1.11; reading rays and writing records directly 0.74.
 int host_mode() {
     static const int v = [] {
@@ -199,9 +220,8 @@ ResultCode check_overflow(Scene& s) {
 // own staging slot, so the copy engines and the SMs overlap across chunks — and across consecutive batches when the
 // caller does not wait in between (the *_async entry points).  The caller holds s.pipe_mutex.
 // unit_in / unit_out are bytes per ray (single) or per packet; rays_per_unit is 1 or 4.
-// `in2` (optional): a second input array of unit_in2 bytes per unit, staged kSecondInputOffset bytes into the slot (the
-// split origin / direction format).
-constexpr size_t kSecondInputOffset = kChunkRays * 12;
+// `in2` (optional): a second input array of unit_in2 bytes per unit, staged slot_rays * 12 bytes into the slot (the split
+// origin / direction format).
 template <class Launch>
 ResultCode enqueue_host_batch(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit,
                               void* out, Launch&& launch, const void* in2 = nullptr, size_t unit_in2 = 0) {
@@ -237,7 +257,7 @@ ResultCode enqueue_host_batch(Scene& s, const void* in, size_t units, size_t uni
         mark(st);
         RTB_CUDA(cudaMemcpyAsync(s.d_in[k], (const char*)in + done * unit_in, m * unit_in, cudaMemcpyHostToDevice, st));
         if (in2)
-            RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + kSecondInputOffset, (const char*)in2 + done * unit_in2, m * unit_in2,
+            RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + s.slot_rays * 12, (const char*)in2 + done * unit_in2, m * unit_in2,
                                      cudaMemcpyHostToDevice, st));
         mark(st);
         RTB_CUDA(launch(s.d_in[k], m, s.d_out[k], (const unsigned long long*)nullptr, st));
@@ -292,10 +312,10 @@ ResultCode enqueue_host_batch_gated(Scene& s, const void* in, size_t n, size_t u
         const uint64_t seq = s.gated_seq++;
         const int k = (int)(s.chunk_seq++ % kPipeStreams);
         const size_t left = n - done;
-        size_t m = std::min(kChunkRays, left);
+        size_t m = std::min(s.slot_rays, left);
         if (ramp) {
-            m = std::min(kChunkRays, std::max(kMinChunkRays, ((left / 2 + kMinChunkRays - 1) / kMinChunkRays) * kMinChunkRays));
-            if (m > left || left - m < kMinChunkRays / 2) m = std::min(left, kChunkRays);
+            m = std::min(s.slot_rays, std::max(kMinChunkRays, ((left / 2 + kMinChunkRays - 1) / kMinChunkRays) * kMinChunkRays));
+            if (m > left || left - m < kMinChunkRays / 2) m = std::min(left, s.slot_rays);
         }
         unsigned long long* ready = s.d_ready + (seq % kReadySlots);
         // the staging slot (and the watermark slot, at most kPipeStreams launches are in flight) is free once everything
@@ -311,7 +331,7 @@ ResultCode enqueue_host_batch_gated(Scene& s, const void* in, size_t n, size_t u
             RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + off * unit_in, (const char*)in + (done + off) * unit_in, sub * unit_in,
                                      cudaMemcpyHostToDevice, cp));
             if (in2)
-                RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + kSecondInputOffset + off * unit_in, (const char*)in2 + (done + off) * unit_in,
+                RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + s.slot_rays * 12 + off * unit_in, (const char*)in2 + (done + off) * unit_in,
                                          sub * unit_in, cudaMemcpyHostToDevice, cp));
             if (write_value) {  // stream memory operation: no DMA set-up, ordered behind the copies like any stream work
                 if (write_value(cp, (unsigned long long)(uintptr_t)ready, off + sub, 0) != 0) return fail("cuStreamWriteValue64 failed");
@@ -338,9 +358,15 @@ template <class Launch>
 ResultCode enqueue_any(Scene& s, const void* in, size_t units, size_t unit_in, size_t unit_out, size_t rays_per_unit, void* out,
                        Launch&& launch, const void* in2, size_t unit_in2, bool gate_ok, bool blocking) {
     const int mode = host_mode();
-    const bool gated = mode == kHostGated || (mode == kHostAuto && in2 != nullptr);
-    if (gate_ok && gated && (in2 == nullptr || unit_in2 == unit_in))
+    const bool gated = mode != kHostStaged;
+    if (gate_ok && gated && (in2 == nullptr || unit_in2 == unit_in)) {
+        // every launch ends with a drain phase (its warps can no longer refill; the longest rays of a launch alone take
+        // ~0.25 ms): the fewer launches per batch the better, so the slots grow with the batch (up to 8 Mi rays)
+        size_t want = kChunkRays;
+        while (want < units && want < kMaxSlotRays) want <<= 1;
+        if (ensure_pipeline(s, want) != Ok) return Error;
         return enqueue_host_batch_gated(s, in, units, unit_in, unit_out, out, blocking, launch, in2);
+    }
     return enqueue_host_batch(s, in, units, unit_in, unit_out, rays_per_unit, out, launch, in2, unit_in2);
 }
 
@@ -841,7 +867,7 @@ static ResultCode od_host_call(RTGpuScene h, RTTreeKind tree, bool any, const fl
     if (!t) return fail("scene has no such tree");
     if (n != 0 && !directions) return fail("null host buffer");
     auto launch = [&](void* din, size_t m, void* dout, const unsigned long long* ready, cudaStream_t st) {
-        return launch_od(*s, *t, tree, any, (const float*)din, (const float*)((const char*)din + kSecondInputOffset), m, t_min, t_max,
+        return launch_od(*s, *t, tree, any, (const float*)din, (const float*)((const char*)din + s->slot_rays * 12), m, t_min, t_max,
                          dout, ready, st);
     };
     const size_t unit_out = any ? 1 : sizeof(RTHit);

@@ -312,9 +312,11 @@ def test_async_submit_wait(A, O, W, teapot, teapot_trees):
         sc.free()
 
 
-def test_gated_host_pipeline_in_a_subprocess(A):
-    """RTBVH_HOST_MODE=gated (launches that start before their input has arrived; read at library load, hence the
-    subprocess): the host-buffer calls return the same records as the device-resident launch."""
+@pytest.mark.parametrize("mode", ["gated", "staged"])
+def test_host_pipeline_flavours_in_a_subprocess(A, mode):
+    """RTBVH_HOST_MODE=gated (launches that start before their input has arrived; the default wherever allowed) and =staged
+    (chunks over four streams; what packets and sorted batches always use).  The variable is read once per process, hence
+    the subprocess: blocking, asynchronous, RTRay and split-input calls all return the oracle's records."""
     import subprocess
     import sys
     import os
@@ -348,7 +350,7 @@ def test_gated_host_pipeline_in_a_subprocess(A):
         "    assert np.array_equal(hh[3 + k].numpy().view(api.HIT_DTYPE).reshape(-1), want), k\n"
         "print('gated ok')\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, RTBVH_HOST_MODE="gated")
+    env = dict(os.environ, RTBVH_HOST_MODE=mode)
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "gated ok" in r.stdout, r.stdout + r.stderr
 
