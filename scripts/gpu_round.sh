@@ -13,7 +13,7 @@ echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== bench"; timeout 900 python bench.py --steps $STEPS --warmup 5 2> $OUT/${TAG}_bench.err | tee $OUT/${TAG}_bench.json
 tail -5 $OUT/${TAG}_bench.err
 echo "== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/${TAG}_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"trace_|camera_rays|gather_tris|ray_keys|peer_barrier" -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu --e2e-steps 1 > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:trace_single -s 3 -c 1 -f -o $OUT/${TAG}_prof \
