@@ -326,24 +326,38 @@ ResultCode enqueue_host_batch_gated(Scene& s, const void* in, size_t n, size_t u
         RTB_CUDA(cudaEventRecord(s.ev_start[k], cp));
         RTB_CUDA(cudaStreamWaitEvent(s.streams[k], s.ev_start[k], 0));
         RTB_CUDA(launch(s.d_in[k], m, s.d_out[k], (const unsigned long long*)ready, s.streams[k]));
-        for (size_t off = 0; off < m; off += sub_rays) {
-            const size_t sub = std::min(sub_rays, m - off);
-            RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + off * unit_in, (const char*)in + (done + off) * unit_in, sub * unit_in,
-                                     cudaMemcpyHostToDevice, cp));
-            if (in2)
-                RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + s.slot_rays * 12 + off * unit_in, (const char*)in2 + (done + off) * unit_in,
-                                         sub * unit_in, cudaMemcpyHostToDevice, cp));
-            if (write_value) {  // stream memory operation: no DMA set-up, ordered behind the copies like any stream work
-                if (write_value(cp, (unsigned long long)(uintptr_t)ready, off + sub, 0) != 0) return fail("cuStreamWriteValue64 failed");
-            } else {
-                if (s.marks_used == kMarkSlots) {  // the pinned source values of in-flight watermark copies must stay intact
-                    RTB_CUDA(cudaStreamSynchronize(cp));
-                    s.marks_used = 0;
+        // From here on a launch is waiting for its input: if feeding it fails (e.g. a bad host pointer), open the gate
+        // completely before reporting the error — the launch then runs over whatever the slot holds and ends, instead of
+        // spinning on the watermark for ever.
+        auto feed = [&]() -> cudaError_t {
+            for (size_t off = 0; off < m; off += sub_rays) {
+                const size_t sub = std::min(sub_rays, m - off);
+                cudaError_t e = cudaMemcpyAsync((char*)s.d_in[k] + off * unit_in, (const char*)in + (done + off) * unit_in,
+                                                sub * unit_in, cudaMemcpyHostToDevice, cp);
+                if (e == cudaSuccess && in2)
+                    e = cudaMemcpyAsync((char*)s.d_in[k] + s.slot_rays * 12 + off * unit_in, (const char*)in2 + (done + off) * unit_in,
+                                        sub * unit_in, cudaMemcpyHostToDevice, cp);
+                if (e != cudaSuccess) return e;
+                if (write_value) {  // stream memory operation: no DMA set-up, ordered behind the copies like any stream work
+                    if (write_value(cp, (unsigned long long)(uintptr_t)ready, off + sub, 0) != 0) return cudaErrorUnknown;
+                } else {
+                    if (s.marks_used == kMarkSlots) {  // the pinned source values of in-flight watermark copies must stay intact
+                        if ((e = cudaStreamSynchronize(cp)) != cudaSuccess) return e;
+                        s.marks_used = 0;
+                    }
+                    s.h_marks[s.marks_used] = off + sub;
+                    e = cudaMemcpyAsync(ready, &s.h_marks[s.marks_used], sizeof(unsigned long long), cudaMemcpyHostToDevice, cp);
+                    if (e != cudaSuccess) return e;
+                    s.marks_used++;
                 }
-                s.h_marks[s.marks_used] = off + sub;
-                RTB_CUDA(cudaMemcpyAsync(ready, &s.h_marks[s.marks_used], sizeof(unsigned long long), cudaMemcpyHostToDevice, cp));
-                s.marks_used++;
             }
+            return cudaSuccess;
+        };
+        const cudaError_t fed = feed();
+        if (fed != cudaSuccess) {
+            cudaGetLastError();
+            cudaMemsetAsync(ready, 0xFF, sizeof(unsigned long long), cp);  // watermark = 2^64 - 1
+            return fail("host-buffer pipeline: feeding a gated launch failed", fed);
         }
         // enqueued after the uploads: with a pageable `out` this call blocks until the launch has finished
         RTB_CUDA(cudaMemcpyAsync((char*)out + done * unit_out, s.d_out[k], m * unit_out, cudaMemcpyDeviceToHost, s.streams[k]));

@@ -598,10 +598,12 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                     if (pd.ready) {  // host-buffer pipeline: wait until the copy engine has delivered this range
                         if (lane == 0) {
                             unsigned long long have;
+                            unsigned backoff = 250;  // thousands of warps may wait on this one L2 line: poll politely
                             for (;;) {
                                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(have) : "l"(pd.ready) : "memory");
                                 if (have >= res_end) break;
-                                __nanosleep(500);
+                                __nanosleep(backoff);
+                                if (backoff < 4000) backoff <<= 1;
                             }
                         }
                         __syncwarp();

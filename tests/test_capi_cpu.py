@@ -62,6 +62,16 @@ def test_no_cpu_fallback_without_a_device(A):
     assert A.lib().create_bvh(None, 16, A._p(c), 12, 1, A.BINNED_SAH, C.byref(out)) == A.ERROR
     with pytest.raises(A.RtbvhError):
         A.Scene(np.zeros((1, 3, 3), np.float32), bvh=A.Bvh.from_arrays(np.zeros(1, A.NODE_DTYPE), np.zeros(1, np.uint32)))
+    # the entry points added later fail just as loudly: resident builds, unknown scenes for the batch / refit calls
+    with pytest.raises(A.RtbvhError):
+        A.Scene.build(np.zeros((4, 3, 3), np.float32))
+    L = A.lib()
+    t = C.c_uint64(0)
+    buf = np.zeros(8, np.float32)
+    assert L.rtbvh_gpu_intersect_async(1, A.TREE_MBVH, A._p(buf), 1, A._p(buf), C.byref(t)) == A.ERROR
+    assert L.rtbvh_gpu_intersect_od(1, A.TREE_MBVH, A._p(buf), A._p(buf), 1, 1e-4, 1e34, A._p(buf)) == A.ERROR
+    assert L.rtbvh_gpu_wait(1, 0) == A.ERROR
+    assert L.rtbvh_gpu_scene_refit(1, A._p(buf), 12, 1) == A.ERROR
 
 
 def _mt_callback(A, tris, o, d, eps_lo):
