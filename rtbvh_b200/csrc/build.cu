@@ -914,20 +914,46 @@ __global__ void __launch_bounds__(kSmallWarps * 32, RTB_SMALL_MINBLOCKS) sah_sma
         Box L1, R1, L2, R2;
         float c1 = FLT_MAX, c2 = FLT_MAX;
         L1 = R1 = L2 = R2 = box_empty();
-        if ((lane & 15) != 15) c1 = small_candidate(s_lo[w], s_hi[w], e.b, e.e, lane >> 4, (uint32_t)(lane & 15) + 1u, L1, R1);
-        if (lane < 15) c2 = small_candidate(s_lo[w], s_hi[w], e.b, e.e, 2, (uint32_t)lane + 1u, L2, R2);
-        float bc1, bc2;
-        uint32_t bn1, bn2;
-        small_argmin16(c1, lane, bc1, bn1);
-        small_argmin16(c2, lane, bc2, bn2);
         float best_cost[3];
         uint32_t best_count[3];
-        best_cost[0] = __shfl_sync(0xFFFFFFFFu, bc1, 0);
-        best_count[0] = __shfl_sync(0xFFFFFFFFu, bn1, 0);
-        best_cost[1] = __shfl_sync(0xFFFFFFFFu, bc1, 16);
-        best_count[1] = __shfl_sync(0xFFFFFFFFu, bn1, 16);
-        best_cost[2] = __shfl_sync(0xFFFFFFFFu, bc2, 0);
-        best_count[2] = __shfl_sync(0xFFFFFFFFu, bn2, 0);
+        // Up to 10 primitives (most nodes): only split positions right behind an occupied bin can differ from their
+        // predecessor — position s and the next occupied-bin boundary below it give the same partition, hence the same
+        // cost, and find_split keeps the first of equals — so lane (axis, j) evaluates the ONE candidate s = bin_j + 1:
+        // 3 nn <= 30 lanes, one round instead of two, and the per-axis "first strict minimum" is two integer warp
+        // reductions on order-preserving keys (minimum cost, then the smallest s among its holders).
+        const bool compact = nn <= 10;
+        int cax = 3;          // compact mode: this lane's axis (3: no candidate)
+        uint32_t cs = kBins;  // ... and split position
+        if (compact) {
+            if ((uint32_t)lane < 3u * nn) {
+                cax = lane / (int)nn;
+                const uint32_t j = e.b + (uint32_t)lane % nn;
+                cs = ((__float_as_uint(s_lo[w][j].w) >> (8 * cax)) & 0xFFu) + 1u;
+            }
+            const bool cvalid = cax < 3 && cs < (uint32_t)kBins;
+            if (cvalid) c1 = small_candidate(s_lo[w], s_hi[w], e.b, e.e, cax, cs, L1, R1);
+            const uint32_t key = (cvalid && c1 < FLT_MAX) ? fkey(c1) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, cax == a ? key : 0xFFFFFFFFu);
+                const uint32_t sa = __reduce_min_sync(0xFFFFFFFFu, (cax == a && key == m && m != 0xFFFFFFFFu) ? cs : (uint32_t)kBins);
+                best_cost[a] = m == 0xFFFFFFFFu ? FLT_MAX : fkey_inv(m);
+                best_count[a] = m == 0xFFFFFFFFu ? (uint32_t)kBins : sa;
+            }
+        } else {
+            if ((lane & 15) != 15) c1 = small_candidate(s_lo[w], s_hi[w], e.b, e.e, lane >> 4, (uint32_t)(lane & 15) + 1u, L1, R1);
+            if (lane < 15) c2 = small_candidate(s_lo[w], s_hi[w], e.b, e.e, 2, (uint32_t)lane + 1u, L2, R2);
+            float bc1, bc2;
+            uint32_t bn1, bn2;
+            small_argmin16(c1, lane, bc1, bn1);
+            small_argmin16(c2, lane, bc2, bn2);
+            best_cost[0] = __shfl_sync(0xFFFFFFFFu, bc1, 0);
+            best_count[0] = __shfl_sync(0xFFFFFFFFu, bn1, 0);
+            best_cost[1] = __shfl_sync(0xFFFFFFFFu, bc1, 16);
+            best_count[1] = __shfl_sync(0xFFFFFFFFu, bn1, 16);
+            best_cost[2] = __shfl_sync(0xFFFFFFFFu, bc2, 0);
+            best_count[2] = __shfl_sync(0xFFFFFFFFu, bn2, 0);
+        }
         int best_axis = 0;
         if (best_cost[0] > best_cost[1]) best_axis = 1;
         if ((best_axis == 0 ? best_cost[0] : best_cost[1]) > best_cost[2]) best_axis = 2;
@@ -970,7 +996,12 @@ __global__ void __launch_bounds__(kSmallWarps * 32, RTB_SMALL_MINBLOCKS) sah_sma
         // child boxes.  Regular split: the lane that evaluated the winning candidate already holds them.  Fallback:
         // quirk Q3 — the left box uses the SAH split count of the final axis, the right box the fallback index.
         Box lb, rb;
-        if (!fallback) {
+        if (!fallback && compact) {
+            const uint32_t holders = __ballot_sync(0xFFFFFFFFu, cax == best_axis && cs == split_index);
+            const int src = __ffs((int)holders) - 1;  // any holder has the same boxes (same partition, same order of unions)
+            lb = shfl_box(L1, src);
+            rb = shfl_box(R1, src);
+        } else if (!fallback) {
             const int src = best_axis < 2 ? 16 * best_axis + (int)split_index - 1 : (int)split_index - 1;
             lb = shfl_box(best_axis < 2 ? L1 : L2, src);
             rb = shfl_box(best_axis < 2 ? R1 : R2, src);
