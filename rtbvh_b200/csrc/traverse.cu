@@ -28,8 +28,11 @@ namespace rtb {
 
 namespace {
 
-constexpr int kSmemStack = 32;    // entries kept in shared memory (the reference's whole stack, src/iter.rs:25)
-constexpr int kSpillStack = 96;   // further entries spill to thread-local memory (only touched by deep rays); beyond 128 -> overflow flag
+#ifndef RTB_SMEM_STACK
+#define RTB_SMEM_STACK 32
+#endif
+constexpr int kSmemStack = RTB_SMEM_STACK;        // entries kept in shared memory (32 = the reference's whole stack, src/iter.rs:25)
+constexpr int kSpillStack = 128 - kSmemStack;     // further entries spill to thread-local memory (only touched by deep rays); beyond 128 -> overflow flag
 #ifndef RTB_BLOCK
 #define RTB_BLOCK 128
 #endif
