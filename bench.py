@@ -479,8 +479,22 @@ def build_trees(api, tris, info, rank):
             res_wall.append((time.perf_counter() - t0) * 1e3)
             res_dev.append(api.last_build_stats()["device_ms"])
             rs.free()
+        # the build's own roofline: 148 + 60 * D-bar algorithmic bytes per triangle, D-bar = mean
+        # leaf depth (per primitive) of the tree just built, over the measured device time of one build
+        try:
+            ds = W.leaf_depth_stats(bvh.nodes)
+            bpt = W.binned_sah_bytes_per_tri(ds["mean_leaf_depth_per_prim"])
+            peak, peak_src = measured_peak_gbs()
+            ach = bpt * len(tris) / (float(np.median(dev)) * 1e-3) / 1e9
+            build_roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                              "peak_source": peak_src, "bytes_per_tri": bpt,
+                              "mean_leaf_depth": ds["mean_leaf_depth_per_prim"], "max_depth": ds["max_depth"],
+                              "kernels": "all kernels of one binned-SAH build (level loop + small-subtree kernel)"}
+        except Exception as e:  # a statistics failure must not cost the bench line
+            build_roofline = {"error": f"{type(e).__name__}: {e}"}
         info.update(tree="gpu-built: rtbvh_gpu_create_bvh_triangles(BinnedSAH) + create_mbvh",
                     build={"binned_sah_ms_per_mtri": float(np.median(dev)) / mtri,
+                           "roofline": build_roofline,
                            "binned_sah_ms_per_mtri_incl_h2d_d2h": float(np.median(tot)) / mtri,
                            "binned_sah_device_ms_runs": dev, "collapse_device_ms": cst["device_ms"],
                            "collapse_ms_incl_h2d_d2h": cst["total_ms"], "bvh_nodes": int(bvh.rt.node_count),

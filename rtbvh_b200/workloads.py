@@ -270,3 +270,42 @@ def pack4(rays: np.ndarray) -> np.ndarray:
         p["direction_" + ax] = r["direction"][:, :, k]
     p["t"] = r["t"]
     return p
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# tree statistics for the builders' roofline
+# ------------------------------------------------------------------------------------------------------------------
+def leaf_depth_stats(nodes: np.ndarray) -> dict:
+    """Depth statistics of a binary tree in the reference's node format (`count >= 0` leaf, `count == -1` inner with
+    children `left_first`, `left_first + 1`; root at depth 0), computed level by level without recursion.
+    `mean_leaf_depth_per_prim` is D-bar of the binned-SAH byte model `148 + 60 * D-bar` B per triangle: the number of
+    levels whose bin and partition passes touch a primitive = the depth of its leaf."""
+    count = nodes["count"].astype(np.int64)
+    left = nodes["left_first"].astype(np.int64)
+    level = np.array([0], dtype=np.int64)
+    depth = 0
+    leaves = prims = 0
+    sum_leaf = sum_prim = 0
+    max_depth = 0
+    while len(level):
+        valid = level[left[level] >= 0]
+        is_leaf = count[valid] >= 0
+        lv = valid[is_leaf]
+        if len(lv):
+            leaves += len(lv)
+            p = int(count[lv].sum())
+            prims += p
+            sum_leaf += depth * len(lv)
+            sum_prim += depth * p
+            max_depth = depth
+        inner = left[valid[~is_leaf]]
+        level = np.concatenate([inner, inner + 1])
+        depth += 1
+    return {"leaves": int(leaves), "prims": int(prims), "max_depth": int(max_depth),
+            "mean_leaf_depth": sum_leaf / max(1, leaves), "mean_leaf_depth_per_prim": sum_prim / max(1, prims)}
+
+
+def binned_sah_bytes_per_tri(mean_leaf_depth_per_prim: float) -> float:
+    """36 (vertices in) + 44 (aabb + centroid out) + D-bar * [(4 + 12 + 24) bin pass + (4 + 12 + 4)
+    partition] + 2 * 32 (nodes out) + 4 (index out) = 148 + 60 * D-bar."""
+    return 148.0 + 60.0 * mean_leaf_depth_per_prim

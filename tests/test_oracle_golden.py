@@ -104,3 +104,29 @@ def test_refit_keeps_topology_and_bounds(O, teapot, teapot_trees):
         else:
             for c in (nd["left_first"], nd["left_first"] + 1):
                 assert np.all(r.nodes[c]["min"] >= nd["min"]) and np.all(r.nodes[c]["max"] <= nd["max"])
+
+
+def test_leaf_depth_stats_for_the_build_roofline(O, W, teapot, teapot_trees):
+    """bench.py's builder roofline uses D-bar = mean leaf depth per primitive: the level-by-level
+    numpy walk must equal a plain recursive walk, and reproduce the survey's teapot figures (6 154 leaves, depth 16)."""
+    nodes = teapot_trees["sah"][0].nodes
+    st = W.leaf_depth_stats(nodes)
+    acc = []
+    stack = [(0, 0)]
+    while stack:
+        i, d = stack.pop()
+        lf, cnt = int(nodes[i]["left_first"]), int(nodes[i]["count"])
+        if lf < 0:
+            continue
+        if cnt >= 0:
+            acc.append((d, cnt))
+        else:
+            stack += [(lf, d + 1), (lf + 1, d + 1)]
+    assert st["leaves"] == len(acc) == 6154 and st["prims"] == sum(c for _, c in acc) == 6320
+    assert st["max_depth"] == max(d for d, _ in acc) == 16
+    assert abs(st["mean_leaf_depth_per_prim"] - sum(d * c for d, c in acc) / 6320) < 1e-12
+    assert abs(W.binned_sah_bytes_per_tri(st["mean_leaf_depth_per_prim"]) - (148 + 60 * st["mean_leaf_depth_per_prim"])) < 1e-9
+    # a single-leaf tree: depth 0
+    one = nodes[:1].copy()
+    one["count"], one["left_first"] = 3, 0
+    assert W.leaf_depth_stats(one) == {"leaves": 1, "prims": 3, "max_depth": 0, "mean_leaf_depth": 0.0, "mean_leaf_depth_per_prim": 0.0}
