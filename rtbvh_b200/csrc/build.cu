@@ -1171,6 +1171,127 @@ struct PartitionScatterOut {
 };
 using PartitionFlagIter = cub::TransformInputIterator<FlagSum, PartitionFlagIn, cub::CountingInputIterator<uint32_t>>;
 
+// ---- the same stable partition without the chained scan (the default; RTBVH_SAH_PARTITION=cub selects the CUB pass
+// above).  ncu of a 1 Mi build (profiles/r3b_build_ncu.md): DeviceScanByKey needs 35 us (+ 4 us init) per level for 10 MB
+// of traffic — the latency of its decoupled look-back chain, not bandwidth.  Here every block owns a fixed chunk of
+// kPartChunk index positions and two short kernels replace the scan:
+//   count   : tail_left[c] = left-going positions of chunk c that belong to the task of the chunk's LAST position (the
+//             only task that can continue into chunk c + 1);
+//   scatter : the carry of the task running through the chunk's FIRST position is the sum of tail_left over the chunks
+//             since that task's begin (they lie in the task entirely, except the first one, whose tail is exactly the
+//             task's part); inside the chunk a block-wide segmented scan of the predicate gives every position its rank,
+//             and the destination rule is PartitionScatterOut's, verbatim.
+// Same inputs, same outputs (idx_out, pos_task_out), bit for bit: a stable partition has one result.
+constexpr int kPartBlock = 256, kPartItems = 8;
+constexpr uint32_t kPartChunk = kPartBlock * kPartItems;
+constexpr uint32_t kPartMaxChunks = 8192;  // the carry is a block reduction over the task's chunks: bound it (n <= 16 Mi)
+
+struct SegSum {
+    uint32_t sum, head;  // head: a segment (task) starts at or before this position, inside the scanned range
+};
+struct SegSumOp {
+    __device__ __forceinline__ SegSum operator()(const SegSum& a, const SegSum& b) const {
+        return SegSum{b.head ? b.sum : a.sum + b.sum, a.head | b.head};
+    }
+};
+__device__ __forceinline__ uint32_t part_flag(const PartitionParams* p, uint32_t i, int32_t t) {
+    if (t < 0) return 0u;
+    const uint2 k = *reinterpret_cast<const uint2*>(&p->ptask[t].shift);  // {shift, split_index}
+    return (k.y != 0u && (((uint32_t)p->binidx[i] >> k.x) & 15u) < k.y) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(kPartBlock) part_count_kernel(const PartitionParams* __restrict__ p, uint32_t n,
+                                                                uint32_t* __restrict__ tail_left) {
+    using Reduce = cub::BlockReduce<uint32_t, kPartBlock>;
+    __shared__ typename Reduce::TempStorage tmp;
+    const uint32_t base = blockIdx.x * kPartChunk;
+    const uint32_t end = min(n, base + kPartChunk);
+    const int32_t t_last = pt_task(p->pos_task[end - 1]);  // block-uniform
+    uint32_t cnt = 0;
+    if (t_last >= 0) {
+        const uint2 k = *reinterpret_cast<const uint2*>(&p->ptask[t_last].shift);
+        if (k.y != 0u) {
+            const uint32_t first = max(base, p->ptask[t_last].begin);  // the task's positions inside this chunk: [first, end)
+            for (uint32_t i = first + threadIdx.x; i < end; i += kPartBlock)
+                cnt += (((uint32_t)p->binidx[i] >> k.x) & 15u) < k.y ? 1u : 0u;
+        }
+    }
+    const uint32_t total = Reduce(tmp).Sum(cnt);
+    if (threadIdx.x == 0) tail_left[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kPartBlock) part_scatter_kernel(const PartitionParams* __restrict__ p, uint32_t n,
+                                                                  const uint32_t* __restrict__ tail_left) {
+    using Reduce = cub::BlockReduce<uint32_t, kPartBlock>;
+    using Scan = cub::BlockScan<SegSum, kPartBlock>;
+    __shared__ union {
+        typename Reduce::TempStorage reduce;
+        typename Scan::TempStorage scan;
+    } tmp;
+    __shared__ uint32_t s_carry;
+    const uint32_t base = blockIdx.x * kPartChunk;
+    const uint32_t end = min(n, base + kPartChunk);
+    // carry of the task that runs through the first position of the chunk
+    const int32_t t0 = pt_task(p->pos_task[base]);  // block-uniform
+    uint32_t part = 0;
+    if (t0 >= 0) {
+        const uint32_t tb = p->ptask[t0].begin;
+        if (tb < base)
+            for (uint32_t c = tb / kPartChunk + threadIdx.x; c < blockIdx.x; c += kPartBlock) part += tail_left[c];
+    }
+    const uint32_t carry = Reduce(tmp.reduce).Sum(part);
+    if (threadIdx.x == 0) s_carry = carry;
+    __syncthreads();  // also separates the two uses of the shared temp storage
+    // segmented inclusive scan of the predicate over the chunk (blocked arrangement: kPartItems consecutive positions per thread)
+    const uint32_t i0 = base + threadIdx.x * kPartItems;
+    int32_t task[kPartItems];
+    uint32_t flag[kPartItems];
+    SegSum v[kPartItems];
+    int32_t prev = (i0 > base && i0 < end) ? pt_task(p->pos_task[i0 - 1]) : 0;
+#pragma unroll
+    for (int k = 0; k < kPartItems; k++) {
+        const uint32_t i = i0 + k;
+        if (i < end) {
+            task[k] = pt_task(p->pos_task[i]);
+            flag[k] = part_flag(p, i, task[k]);
+            v[k] = SegSum{flag[k], (i > base && task[k] != prev) ? 1u : 0u};
+            prev = task[k];
+        } else {  // padding behind the end of the array: its own segments, never read
+            task[k] = -1;
+            flag[k] = 0u;
+            v[k] = SegSum{0u, 1u};
+        }
+    }
+    Scan(tmp.scan).InclusiveScan(v, v, SegSumOp());
+    const uint32_t first_carry = s_carry;
+#pragma unroll
+    for (int k = 0; k < kPartItems; k++) {
+        const uint32_t i = i0 + k;
+        if (i >= end) continue;
+        const int32_t t = task[k];
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (t >= 0) q = *reinterpret_cast<const uint4*>(&p->ptask[t]);  // {begin, nleft, child_left, child_right}
+        if (t < 0 || q.y == 0u) {  // finished position, or a task that became a leaf this level
+            p->idx_out[i] = p->idx[i];
+            p->pos_task_out[i] = -1;
+        } else {
+            const uint32_t incl = v[k].sum + (v[k].head ? 0u : first_carry);  // no segment start since the chunk's first position
+            const uint32_t r = incl - flag[k];
+            const bool left = flag[k] != 0u;
+            const uint32_t dest = left ? q.x + r : q.x + q.y + (i - q.x - r);
+            p->idx_out[dest] = p->idx[i];
+            p->pos_task_out[dest] = (int32_t)(left ? q.z : q.w);
+        }
+    }
+}
+// Default for builds of up to kPartMaxChunks chunks; RTBVH_SAH_PARTITION=cub selects the scan-by-key pass (A/B:
+// scripts/partition_ab.py — byte-identical trees on every scene, 1 Mi soup 2.44 -> 2.25 ms, 3 Mi 5.81 -> 5.45 ms).
+bool partition_block_mode() {
+    static const bool v = [] {
+        const char* e = std::getenv("RTBVH_SAH_PARTITION");
+        return !(e && std::string(e) == "cub");
+    }();
+    return v;
+}
+
 // =================================================================================================
 // LOCB
 // =================================================================================================
@@ -1691,6 +1812,10 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         RTB_CUDA(binidx.alloc((size_t)n * 2));
         RTB_CUDA(state.alloc((size_t)(kMaxDepth + 3) * sizeof(LevelState)));
         RTB_CUDA(params.alloc(2 * sizeof(PartitionParams)));
+        const uint32_t part_chunks = blocks(n, kPartChunk);
+        const bool part_block = partition_block_mode() && part_chunks <= kPartMaxChunks;
+        DevBuf part_tail;
+        if (part_block) RTB_CUDA(part_tail.alloc((size_t)part_chunks * 4));
         PartitionParams hp[2];
         for (int k = 0; k < 2; k++)
             hp[k] = PartitionParams{idxB[k].as<uint32_t>(), ptB[k].as<int32_t>(), ptask.as<PartTask>(), binidx.as<uint16_t>(),
@@ -1770,10 +1895,15 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
                                                         small_tasks.as<SmallTask>(), ptask.as<PartTask>(),
                                                         span_tasks.as<uint32_t>(), d_state);
             if (span_left) {
-                tbytes = temp.bytes;
-                RTB_CUDA(cub::DeviceScan::InclusiveScanByKey(temp.p, tbytes, ptB[parity].as<int32_t>(),
-                                                             PartitionFlagIter(cub::CountingInputIterator<uint32_t>(0), PartitionFlagIn{dp + parity}),
-                                                             PartitionScatterOut{dp + parity, 0}, FlagSumOp(), n));
+                if (part_block) {
+                    part_count_kernel<<<part_chunks, kPartBlock>>>(dp + parity, n, part_tail.as<uint32_t>());
+                    part_scatter_kernel<<<part_chunks, kPartBlock>>>(dp + parity, n, part_tail.as<uint32_t>());
+                } else {
+                    tbytes = temp.bytes;
+                    RTB_CUDA(cub::DeviceScan::InclusiveScanByKey(temp.p, tbytes, ptB[parity].as<int32_t>(),
+                                                                 PartitionFlagIter(cub::CountingInputIterator<uint32_t>(0), PartitionFlagIn{dp + parity}),
+                                                                 PartitionScatterOut{dp + parity, 0}, FlagSumOp(), n));
+                }
                 parity ^= 1;
             }
             RTB_CUDA(cudaMemcpyAsync(&h_state[depth + 1], d_state + depth + 1, sizeof(LevelState), cudaMemcpyDeviceToHost, 0));
