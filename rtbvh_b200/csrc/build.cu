@@ -611,6 +611,11 @@ __global__ void zero_counts_tail_kernel(uint4* __restrict__ counts, uint32_t A_u
 // destinations).  Such a task never shows up in the global partition pass, and once a level holds no span-class task
 // any more the level loop consists of this kernel, the scan of the per-task counts and the emit kernel only.
 constexpr int kWarpTaskWarps = 4;
+// MERGED (the default, RTBVH_SAH_MERGE=0 turns it off): the same launch also plays sah_split_kernel's part for the
+// span-class tasks of the level (after the bin pass) and zeroes the counts beyond A, so a level needs neither
+// sah_split_kernel nor zero_counts_tail_kernel: one launch less per level, and the handful of latency-bound split warps
+// (9 us for ONE task under ncu, profiles/r3b_build_ncu.md) run next to the warp-class tasks instead of before them.
+template <bool MERGED>
 __global__ void __launch_bounds__(kWarpTaskWarps * 32) sah_warp_task_kernel(const Task* __restrict__ tasks,
                                                                             uint32_t* __restrict__ idx,
                                                                             const TaskAux* __restrict__ aux,
@@ -619,17 +624,37 @@ __global__ void __launch_bounds__(kWarpTaskWarps * 32) sah_warp_task_kernel(cons
                                                                             const float4* __restrict__ nodes, uint32_t max_leaf,
                                                                             uint32_t depth, Decision* __restrict__ dec,
                                                                             uint4* __restrict__ counts,
-                                                                            const LevelState* __restrict__ state) {
+                                                                            const LevelState* __restrict__ state, uint32_t A_ub,
+                                                                            uint32_t* __restrict__ bins) {
     __shared__ uint32_t sb[kWarpTaskWarps][kTaskBinWords];
     __shared__ uint32_t s_idx[kWarpTaskWarps][kWarpTask];   // the task's index range as read
     __shared__ uint32_t s_out[kWarpTaskWarps][kWarpTask];   // ... and partitioned
     __shared__ uint16_t s_pk[kWarpTaskWarps][kWarpTask];    // 3 x 4-bit bin per primitive
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x * kWarpTaskWarps + w;
-    if (t >= state->A) return;
+    if (MERGED) {
+        if (t >= A_ub) return;
+        if (t >= state->A) {  // the scan over A_ub entries that follows must see zeros here
+            if (lane == 0) counts[t] = make_uint4(0u, 0u, 0u, 0u);
+            return;
+        }
+    } else if (t >= state->A) {
+        return;
+    }
     const Task task = tasks[t];
     const uint32_t n = task.end - task.begin;
-    if (n > kWarpTask) return;
+    if (n > kWarpTask) {
+        if (MERGED) {  // span-class task: its bins are in HBM (sah_bin_kernel ran before this launch)
+            uint32_t* tb = bins + (size_t)aux[t].slot * kTaskBinWords;
+            sah_split_task(task, t, lane, tb, nodes, max_leaf, depth, dec, counts);
+            __syncwarp();
+            for (int k = lane; k < kTaskBinWords; k += 32) {  // leave the bin block clean for its next owner
+                const int f = k % kBinWords;
+                tb[k] = f < 3 ? fkey(1e34f) : (f < 6 ? fkey(-1e34f) : 0u);
+            }
+        }
+        return;
+    }
     for (int k = lane; k < kTaskBinWords; k += 32) {
         const int f = k % kBinWords;
         sb[w][k] = f < 3 ? fkey(1e34f) : (f < 6 ? fkey(-1e34f) : 0u);
@@ -691,22 +716,13 @@ struct SmallTask {
 // pad + binning transform, so the next level starts with its bin pass) and small subtrees.
 // rank[t] = exclusive scan of counts: x pairs, y next-level tasks, z small subtrees, w node slots of small subtrees.
 // The thread of the last task publishes the next level's state.
-__global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, const Decision* __restrict__ dec,
-                                const uint4* __restrict__ rank, const uint4* __restrict__ counts, uint32_t depth, float4* nodes,
-                                Task* __restrict__ next_tasks, TaskAux* __restrict__ next_aux,
-                                SmallTask* __restrict__ small_tasks,
-                                PartTask* __restrict__ ptask /* per task: what the partition pass needs */,
-                                uint32_t* __restrict__ span_tasks /* [depth + 1]: bin blocks handed out for the next level */,
-                                LevelState* __restrict__ state /* [depth] in, [depth + 1] out */) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const LevelState cur = state[depth];
-    if (cur.A == 0) {
-        if (t == 0) state[depth + 1] = cur;
-        return;
-    }
-    if (t >= cur.A) return;
+__device__ __forceinline__ void sah_emit_task(const uint32_t t, const LevelState cur, const uint4 r /* rank[t] */,
+                                              const uint4 c /* counts[t] */, const Task* __restrict__ tasks,
+                                              const Decision* __restrict__ dec, uint32_t depth, float4* nodes,
+                                              Task* __restrict__ next_tasks, TaskAux* __restrict__ next_aux,
+                                              SmallTask* __restrict__ small_tasks, PartTask* __restrict__ ptask,
+                                              uint32_t* __restrict__ span_tasks, LevelState* __restrict__ state) {
     if (t == cur.A - 1) {
-        const uint4 r = rank[t], c = counts[t];
         state[depth + 1] = LevelState{r.y + c.y, cur.node_count + 2u * (r.x + c.x), cur.S + r.z + c.z, cur.small_slots + r.w + c.w};
     }
     const uint32_t node_base = cur.node_count, small_base = cur.S, small_node_base = cur.small_slots;
@@ -719,7 +735,6 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, c
         ptask[t] = PartTask{task.begin, 0u, -1, -1, 0u, 0u, {0u, 0u}};
         return;
     }
-    const uint4 r = rank[t];
     const uint32_t left = node_base + 2u * r.x;
     store_node(nodes, task.node, nb, -1, (int)left);
     const bool cap = depth + 1 >= (uint32_t)kMaxDepth;
@@ -748,6 +763,81 @@ __global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, c
         }
     }
     ptask[t] = PartTask{task.begin, d.nleft, child[0], child[1], 4u * d.axis, d.split_index, {0u, 0u}};
+}
+__global__ void sah_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub, const Decision* __restrict__ dec,
+                                const uint4* __restrict__ rank, const uint4* __restrict__ counts, uint32_t depth, float4* nodes,
+                                Task* __restrict__ next_tasks, TaskAux* __restrict__ next_aux,
+                                SmallTask* __restrict__ small_tasks,
+                                PartTask* __restrict__ ptask /* per task: what the partition pass needs */,
+                                uint32_t* __restrict__ span_tasks /* [depth + 1]: bin blocks handed out for the next level */,
+                                LevelState* __restrict__ state /* [depth] in, [depth + 1] out */) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const LevelState cur = state[depth];
+    if (cur.A == 0) {
+        if (t == 0) state[depth + 1] = cur;
+        return;
+    }
+    if (t >= cur.A) return;
+    sah_emit_task(t, cur, rank[t], counts[t], tasks, dec, depth, nodes, next_tasks, next_aux, small_tasks, ptask, span_tasks, state);
+}
+struct Uint4Sum {
+    __device__ __forceinline__ uint4 operator()(const uint4& a, const uint4& b) const {
+        return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+};
+// Levels with at most kScanEmitTasks tasks (the top ten): ONE block scans the per-task counts and emits, instead of
+// cub::DeviceScan (two launches) + sah_emit_kernel — the scan of <= 1024 entries is a block scan (the default;
+// RTBVH_SAH_SCANEMIT=0 turns it off).  Same ranks, same emit code.
+constexpr int kScanEmitTasks = 1024;
+__global__ void __launch_bounds__(kScanEmitTasks, 1) sah_scan_emit_kernel(const Task* __restrict__ tasks, uint32_t A_ub,
+                                                                       const Decision* __restrict__ dec,
+                                                                       const uint4* __restrict__ counts, uint32_t depth,
+                                                                       float4* nodes, Task* __restrict__ next_tasks,
+                                                                       TaskAux* __restrict__ next_aux,
+                                                                       SmallTask* __restrict__ small_tasks,
+                                                                       PartTask* __restrict__ ptask,
+                                                                       uint32_t* __restrict__ span_tasks,
+                                                                       LevelState* __restrict__ state) {
+    __shared__ uint4 s_warp[kScanEmitTasks / 32];
+    const uint32_t t = threadIdx.x;
+    const int lane = (int)(t & 31u), w = (int)(t >> 5);
+    const LevelState cur = state[depth];  // block-uniform
+    if (cur.A == 0) {
+        if (t == 0) state[depth + 1] = cur;
+        return;
+    }
+    const uint4 c = (t < cur.A && t < A_ub) ? counts[t] : make_uint4(0u, 0u, 0u, 0u);
+    // exclusive block scan: shuffles inside the warps, the 32 warp totals scanned by warp 0
+    const Uint4Sum add;
+    uint4 inc = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint4 o = make_uint4(__shfl_up_sync(0xFFFFFFFFu, inc.x, off), __shfl_up_sync(0xFFFFFFFFu, inc.y, off),
+                                   __shfl_up_sync(0xFFFFFFFFu, inc.z, off), __shfl_up_sync(0xFFFFFFFFu, inc.w, off));
+        if (lane >= off) inc = add(inc, o);
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const uint4 mine = s_warp[lane];
+        uint4 ws = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint4 o = make_uint4(__shfl_up_sync(0xFFFFFFFFu, ws.x, off), __shfl_up_sync(0xFFFFFFFFu, ws.y, off),
+                                       __shfl_up_sync(0xFFFFFFFFu, ws.z, off), __shfl_up_sync(0xFFFFFFFFu, ws.w, off));
+            if (lane >= off) ws = add(ws, o);
+        }
+        s_warp[lane] = make_uint4(ws.x - mine.x, ws.y - mine.y, ws.z - mine.z, ws.w - mine.w);  // exclusive warp offsets
+    }
+    __syncthreads();
+    const uint4 base = s_warp[w];
+    const uint4 r = make_uint4(base.x + inc.x - c.x, base.y + inc.y - c.y, base.z + inc.z - c.z, base.w + inc.w - c.w);
+    if (t >= cur.A) return;
+    sah_emit_task(t, cur, r, c, tasks, dec, depth, nodes, next_tasks, next_aux, small_tasks, ptask, span_tasks, state);
+}
+bool level_flag(const char* name) {  // the level-loop variants above default to on; NAME=0 selects the older path
+    const char* e = std::getenv(name);
+    return !(e && e[0] == '0');
 }
 
 // ---- small subtrees: one warp runs BinnedSahBuildTask::run for every node below a <= 32-primitive task -----
@@ -1862,6 +1952,7 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         if (!h_span) RTB_CUDA(cudaHostAlloc(&h_span, (size_t)(kMaxDepth + 3) * 4, cudaHostAllocDefault));
         uint32_t first_check = 0;
         while ((uint64_t(kWarpTask) << (first_check + 1)) < n) first_check++;
+        static const bool merge_split = level_flag("RTBVH_SAH_MERGE"), scan_emit = level_flag("RTBVH_SAH_SCANEMIT");
         uint32_t depth = 0;
         bool done = false, span_left = true;
         for (; !done && depth <= (uint32_t)kMaxDepth; depth++) {
@@ -1879,21 +1970,34 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
                     sah_bin_kernel<false><<<bin_grid, kBinBlock>>>(idxB[parity].as<uint32_t>(), ptB[parity].as<int32_t>(), n, bin_span, t_cur,
                                                                    aux_cur, d_bb, d_cen, cstride, bins.as<uint32_t>(), binidx.as<uint16_t>(),
                                                                    st, span_tasks.as<uint32_t>() + depth);
-                sah_split_kernel<<<blocks((size_t)A_ub * 32, 128), 128>>>(t_cur, A_ub, aux_cur, bins.as<uint32_t>(), nodes, max_leaf, depth,
-                                                                          dec.as<Decision>(), counts.as<uint4>(), st);
-            } else {
+                if (!merge_split)
+                    sah_split_kernel<<<blocks((size_t)A_ub * 32, 128), 128>>>(t_cur, A_ub, aux_cur, bins.as<uint32_t>(), nodes, max_leaf,
+                                                                              depth, dec.as<Decision>(), counts.as<uint4>(), st);
+            } else if (!merge_split) {
                 zero_counts_tail_kernel<<<blocks(A_ub, 256), 256>>>(counts.as<uint4>(), A_ub, st);
             }
-            sah_warp_task_kernel<<<blocks(A_ub, kWarpTaskWarps), kWarpTaskWarps * 32>>>(t_cur, idxB[parity].as<uint32_t>(), aux_cur, d_bb,
-                                                                                        d_cen, cstride, nodes, max_leaf, depth,
-                                                                                        dec.as<Decision>(), counts.as<uint4>(), st);
+            if (merge_split)
+                sah_warp_task_kernel<true><<<blocks(A_ub, kWarpTaskWarps), kWarpTaskWarps * 32>>>(
+                    t_cur, idxB[parity].as<uint32_t>(), aux_cur, d_bb, d_cen, cstride, nodes, max_leaf, depth, dec.as<Decision>(),
+                    counts.as<uint4>(), st, A_ub, bins.as<uint32_t>());
+            else
+                sah_warp_task_kernel<false><<<blocks(A_ub, kWarpTaskWarps), kWarpTaskWarps * 32>>>(
+                    t_cur, idxB[parity].as<uint32_t>(), aux_cur, d_bb, d_cen, cstride, nodes, max_leaf, depth, dec.as<Decision>(),
+                    counts.as<uint4>(), st, A_ub, bins.as<uint32_t>());
             size_t tbytes = temp.bytes;
-            RTB_CUDA(cub::DeviceScan::ExclusiveScan(temp.p, tbytes, counts.as<uint4>(), ranks4.as<uint4>(), Uint4Add(),
-                                                    make_uint4(0, 0, 0, 0), (int)A_ub));
-            sah_emit_kernel<<<blocks(A_ub, 128), 128>>>(t_cur, A_ub, dec.as<Decision>(), ranks4.as<uint4>(), counts.as<uint4>(), depth,
-                                                        nodes, tasksB[par ^ 1].as<Task>(), auxB[par ^ 1].as<TaskAux>(),
-                                                        small_tasks.as<SmallTask>(), ptask.as<PartTask>(),
-                                                        span_tasks.as<uint32_t>(), d_state);
+            if (scan_emit && A_ub <= (uint32_t)kScanEmitTasks) {
+                sah_scan_emit_kernel<<<1, kScanEmitTasks>>>(t_cur, A_ub, dec.as<Decision>(), counts.as<uint4>(), depth, nodes,
+                                                            tasksB[par ^ 1].as<Task>(), auxB[par ^ 1].as<TaskAux>(),
+                                                            small_tasks.as<SmallTask>(), ptask.as<PartTask>(),
+                                                            span_tasks.as<uint32_t>(), d_state);
+            } else {
+                RTB_CUDA(cub::DeviceScan::ExclusiveScan(temp.p, tbytes, counts.as<uint4>(), ranks4.as<uint4>(), Uint4Add(),
+                                                        make_uint4(0, 0, 0, 0), (int)A_ub));
+                sah_emit_kernel<<<blocks(A_ub, 128), 128>>>(t_cur, A_ub, dec.as<Decision>(), ranks4.as<uint4>(), counts.as<uint4>(),
+                                                            depth, nodes, tasksB[par ^ 1].as<Task>(), auxB[par ^ 1].as<TaskAux>(),
+                                                            small_tasks.as<SmallTask>(), ptask.as<PartTask>(),
+                                                            span_tasks.as<uint32_t>(), d_state);
+            }
             if (span_left) {
                 if (part_block) {
                     part_count_kernel<<<part_chunks, kPartBlock>>>(dp + parity, n, part_tail.as<uint32_t>());
