@@ -262,3 +262,23 @@ def test_full_size_build_soup_1m(A, O, W):
     m = A.Mbvh.construct(g)
     assert len(m.nodes) == len(w.collapse().nodes)
     print("build stats", stats)
+
+
+@pytest.mark.gpu
+def test_level_loop_variants_build_identical_trees():
+    """The binned-SAH level loop has three switchable pieces (block-chunk partition vs CUB scan-by-key, split merged into
+    the warp-task launch, one-block scan + emit); every combination must produce the legacy path's tree byte for byte
+    (a stable partition and an exclusive scan have one result).  The knobs are read once per process, so
+    scripts/partition_ab.py runs each mode in a child process."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AB_QUICK="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "partition_ab.py")], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    summary = json.loads(r.stdout.strip().splitlines()[-1])
+    assert set(summary["identical_to_legacy"]) == {"legacy", "part", "part+merge", "part+scanemit", "all"}
+    assert all(summary["identical_to_legacy"].values()), summary
