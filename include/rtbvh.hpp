@@ -8,7 +8,9 @@
 //        .construct_binned_sah() / .construct_locally_ordered_clustered() -> Result<Bvh>      src/bvh.rs:49-138
 //   rtbvh::Bvh  : nodes(), indices(), prim_count(), refit(), validate(), bounds(), traverse_iter_indices*   src/bvh.rs:143-284
 //   rtbvh::Mbvh : construct(bvh) / Mbvh(Bvh), nodes(), quad_nodes(), indices(), traverse_iter_indices*       src/bvh.rs:320-450
-//   rtbvh::SpatialTriangle helpers : intersect(tri, ray), the canonical triangle test           src/builders/spatial_sah.rs:131-163
+//   rtbvh::SpatialTriangle helpers : intersect(tri, ray) / intersect4(tri, packet, t_min)        src/builders/spatial_sah.rs:131-244
+//   traverse_iter / traverse_iter_packet : the `&T` iterators of src/iter.rs over the index iterators
+//   Bvh::from_raw / into_raw, Mbvh::from_raw / construct_from_raw / into_raw : trees that live in caller memory   src/bvh.rs:246-256, 353-416
 //   rtbvh::Scene : the batched GPU traversal (closest hit / any hit) that replaces the per-ray iterator loops
 //
 // Header only; link with -lrtbvh_rs (rtbvh_b200/librtbvh_rs.so).  Builds run on the GPU; the iterators walk the
@@ -88,6 +90,43 @@ inline Aabb aabb_of(V... v) {
 
 using Ray = rtbvh_host::Ray;                // src/ray.rs:9-16 (Ray::make == Ray::new)
 using RayPacket4 = rtbvh_host::RayPacket4;  // src/ray.rs:47-61
+
+// RayPacket4::new (src/ray.rs:64-107) from SoA lanes; t starts at 1e34 like the reference's
+inline RayPacket4 make_packet(const float ox[4], const float oy[4], const float oz[4], const float dx[4], const float dy[4],
+                              const float dz[4]) {
+    RayPacket4 p;
+    const float* o[3] = {ox, oy, oz};
+    const float* d[3] = {dx, dy, dz};
+    for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 4; l++) {
+            p.origin[k][l] = o[k][l];
+            p.direction[k][l] = d[k][l];
+            p.inv_direction[k][l] = 1.0f / d[k][l];
+        }
+    for (int l = 0; l < 4; l++) p.t[l] = 1e34f;
+    return p;
+}
+
+// The `&T` iterators of src/iter.rs (BvhIterator :22-129, BvhPacketIterator :131-244, MbvhIterator :246-356,
+// MbvhPacketIterator :358-469): the index iterator with the primitive looked up.  `bool next(const T** prim)` ==
+// `next() -> Option<(&T, &mut Ray)>`.  REJECT_EMPTY: the Bvh flavours yield nothing for an empty primitive slice
+// (iter.rs:36-44, :145-158); the Mbvh flavours do not look at it (iter.rs:262-280).
+template <class IndexIt, class T, bool REJECT_EMPTY>
+class PrimIterator {
+  public:
+    PrimIterator(IndexIt it, const T* prims, size_t count) : it_(it), prims_(prims), live_(!REJECT_EMPTY || count > 0) {}
+    bool next(const T** prim) {
+        uint32_t id;
+        if (!live_ || !it_.next(&id)) return false;
+        *prim = prims_ + id;
+        return true;
+    }
+
+  private:
+    IndexIt it_;
+    const T* prims_;
+    bool live_;
+};
 
 enum class BuildType { None, LocallyOrderedClustered, BinnedSAH, Spatial };  // src/bvh.rs:18-23
 
@@ -179,6 +218,29 @@ class Bvh {
     rtbvh_host::BvhPacketIndexIterator traverse_iter_indices_packet(RayPacket4& p) const {
         return {&p, rt_.nodes, rt_.node_count, rt_.indices};
     }
+    // IntoRayIterator / IntoPacketIterator (iter.rs:9-19)
+    template <class T>
+    PrimIterator<rtbvh_host::BvhIndexIterator, T, true> traverse_iter(Ray& ray, const T* prims, size_t count) const {
+        return {traverse_iter_indices(ray), prims, count};
+    }
+    template <class T>
+    PrimIterator<rtbvh_host::BvhPacketIndexIterator, T, true> traverse_iter_packet(RayPacket4& p, const T* prims, size_t count) const {
+        return {traverse_iter_indices_packet(p), prims, count};
+    }
+    // A tree that lives in the caller's memory (deserialised, or built by the reference): not owned, never freed here.
+    // The struct is trusted like the reference's intersect* trust theirs (rtbvh_ffi/src/lib.rs:551-581).
+    static Bvh from_raw(const RTBvhNode* nodes, size_t node_count, const uint32_t* indices, size_t index_count,
+                        BuildType type = BuildType::None) {
+        Bvh b;
+        b.rt_ = RTBvh{UINT32_MAX, (uint32_t)node_count, nodes, (uint32_t)index_count, indices};
+        b.type_ = type;
+        return b;
+    }
+    // into_raw (bvh.rs:246-256): the arrays, copied out of the library's mirror
+    std::pair<std::vector<RTBvhNode>, std::vector<uint32_t>> into_raw() const {
+        return {std::vector<RTBvhNode>(rt_.nodes, rt_.nodes + rt_.node_count),
+                std::vector<uint32_t>(rt_.indices, rt_.indices + rt_.index_count)};
+    }
 
   private:
     void release() {
@@ -224,7 +286,34 @@ class Mbvh {
     rtbvh_host::MbvhPacketIndexIterator traverse_iter_indices_packet(RayPacket4& p) const {
         return {&p, rt_.nodes, rt_.node_count, rt_.indices};
     }
-
+    template <class T>
+    PrimIterator<rtbvh_host::MbvhIndexIterator, T, false> traverse_iter(Ray& ray, const T* prims, size_t count) const {
+        return {traverse_iter_indices(ray), prims, count};
+    }
+    template <class T>
+    PrimIterator<rtbvh_host::MbvhPacketIndexIterator, T, false> traverse_iter_packet(RayPacket4& p, const T* prims, size_t count) const {
+        return {traverse_iter_indices_packet(p), prims, count};
+    }
+    // 4-wide nodes that live in the caller's memory: not owned
+    static Mbvh from_raw(const RTMbvhNode* nodes, size_t node_count, const uint32_t* indices, size_t index_count) {
+        Mbvh m;
+        m.rt_ = RTMbvh{UINT32_MAX, (uint32_t)node_count, nodes, (uint32_t)index_count, indices};
+        return m;
+    }
+    // Mbvh::construct_from_raw (bvh.rs:353-379) for binary nodes in caller memory, collapsed on the GPU.  Always the
+    // merge_nodes path: the reference's special case for <= 4 nodes mislabels inner nodes.
+    static Mbvh construct_from_raw(const RTBvhNode* nodes, size_t node_count, const uint32_t* indices, size_t index_count) {
+        Mbvh m;
+        if (node_count == 0) return m;
+        const RTBvh src{UINT32_MAX, (uint32_t)node_count, nodes, (uint32_t)index_count, indices};
+        if (rtbvh_gpu_create_mbvh_from(&src, &m.rt_) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
+        m.owned_ = true;
+        return m;
+    }
+    std::pair<std::vector<RTMbvhNode>, std::vector<uint32_t>> into_raw() const {  // bvh.rs:406-416
+        return {std::vector<RTMbvhNode>(rt_.nodes, rt_.nodes + rt_.node_count),
+                std::vector<uint32_t>(rt_.indices, rt_.indices + rt_.index_count)};
+    }
   private:
     void release() {
         if (owned_) free_mbvh(rt_);
@@ -297,6 +386,36 @@ inline bool intersect(const T& tri, Ray& ray) {
     return false;
 }
 
+// SpatialTriangle::intersect4 (src/builders/spatial_sah.rs:165-244): four lanes, its own constants (determinant eps 1e-6
+// with a <= -eps | a >= eps; t >= t_min, non-strict; t < packet.t), `packet.t = select(mask, t, packet.t)`.  Returns the
+// lane mask (0 == None).  The lanes are independent, so the per-lane loop equals the reference's SSE code bit for bit
+// (compile without FMA contraction: -ffp-contract=off).
+template <class T>
+inline unsigned intersect4(const T& tri, RayPacket4& p, const float t_min[4]) {
+    const Vec3 v0 = tri.vertex0(), v1 = tri.vertex1(), v2 = tri.vertex2();
+    const float e1x = v1.x - v0.x, e1y = v1.y - v0.y, e1z = v1.z - v0.z;
+    const float e2x = v2.x - v0.x, e2y = v2.y - v0.y, e2z = v2.z - v0.z;
+    unsigned mask = 0;
+    for (int l = 0; l < 4; l++) {
+        const float dx = p.direction[0][l], dy = p.direction[1][l], dz = p.direction[2][l];
+        const float hx = (dy * e2z) - (dz * e2y), hy = (dz * e2x) - (dx * e2z), hz = (dx * e2y) - (dy * e2x);
+        const float a = ((e1x * hx) + (e1y * hy)) + (e1z * hz);
+        if (!(a <= -1e-6f || a >= 1e-6f)) continue;
+        const float f = 1.0f / a;
+        const float sx = p.origin[0][l] - v0.x, sy = p.origin[1][l] - v0.y, sz = p.origin[2][l] - v0.z;
+        const float u = f * (((sx * hx) + (sy * hy)) + (sz * hz));
+        if (!(u >= 0.0f && u <= 1.0f)) continue;
+        const float qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;
+        const float v = f * (((dx * qx) + (dy * qy)) + (dz * qz));
+        if (!(v >= 0.0f && (u + v) <= 1.0f)) continue;
+        const float t = f * (((e2x * qx) + (e2y * qy)) + (e2z * qz));
+        if (!(t >= t_min[l] && t < p.t[l])) continue;
+        p.t[l] = t;
+        mask |= 1u << l;
+    }
+    return mask;
+}
+
 // The batched GPU traversal: what `for (prim, ray) in tree.iter(ray) { prim.intersect(ray) }` becomes on a B200.
 class Scene {
   public:
@@ -353,6 +472,29 @@ class Scene {
         std::vector<uint8_t> occ(rays.size());
         if (rtbvh_gpu_occluded(h_, tree, rays.data(), rays.size(), occ.data()) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
         return occ;
+    }
+    // packets of four rays, SpatialTriangle::intersect4 semantics; pass t_min = 1e-4f for examples/benchmark.rs:58
+    std::vector<RTHitPacket4> intersect_packets(const std::vector<RTRayPacket4>& packets, float t_min = 1e-4f,
+                                                RTTreeKind tree = RT_TREE_MBVH) const {
+        std::vector<RTHitPacket4> hits(packets.size());
+        if (rtbvh_gpu_intersect_packets(h_, tree, packets.data(), packets.size(), t_min, hits.data()) != Ok)
+            throw std::runtime_error(rtbvh_gpu_last_error());
+        return hits;
+    }
+    std::vector<uint8_t> occluded_packets(const std::vector<RTRayPacket4>& packets, float t_min = 1e-4f,
+                                          RTTreeKind tree = RT_TREE_MBVH) const {
+        std::vector<uint8_t> occ(4 * packets.size());
+        if (rtbvh_gpu_occluded_packets(h_, tree, packets.data(), packets.size(), t_min, occ.data()) != Ok)
+            throw std::runtime_error(rtbvh_gpu_last_error());
+        return occ;
+    }
+    // split input: packed origins / directions (3 floats per ray), one t_min / initial t for the batch
+    std::vector<RTHit> intersect_od(const float* origins, const float* directions, size_t n, float t_min = 1e-4f,
+                                    float t_max = 1e34f, RTTreeKind tree = RT_TREE_MBVH) const {
+        std::vector<RTHit> hits(n);
+        if (rtbvh_gpu_intersect_od(h_, tree, origins, directions, n, t_min, t_max, hits.data()) != Ok)
+            throw std::runtime_error(rtbvh_gpu_last_error());
+        return hits;
     }
     void set_ray_sorting(bool on) { rtbvh_gpu_scene_set_ray_sorting(h_, on ? 1 : 0); }
 
