@@ -152,6 +152,16 @@ def cpu_sample_rate(O, m, tris, rays, target_s=10.0):
     return n / ms / 1e3, n, {k: cnt[k] / nc for k in ("node_visits", "prim_tests")}, cnt["max_stack"], threads
 
 
+def cpu_single_thread_rate(O, m, tris, rays, n=400_000):
+    """The same loop on ONE thread (SURVEY.md section 8d asks for it next to the all-core figure); None on any failure."""
+    try:
+        sample = rays[: min(len(rays), n)]
+        _, ms, _ = O.trace(m, tris, sample, threads=1)
+        return len(sample) / max(ms, 1e-3) / 1e3
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -177,6 +187,7 @@ def run_reference(args):
         ms_tot += ms
     v = n_tot / ms_tot / 1e3
     sample = f"{rows}x{WIDTH} jittered camera rays per step ({n_tot} rays total), Mbvh single-ray closest hit"
+    one = cpu_single_thread_rate(O, m, tris, W.camera_rays(cam, y0=0, y1=400, jitter_seed=W.SEED_SOUP, frame=0))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_tot / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -184,7 +195,8 @@ def run_reference(args):
         "config": {"workload": "soup-1Mi-tris binned-SAH Mbvh primary rays closest-hit (BASELINE configs[1])",
                    "note": "reference is Rust and cannot be built in this image (no rustc/cargo): this is the C++ "
                            "oracle port of its loop, OpenMP dynamic chunks of 1000 rays like benchmark.rs:25"},
-        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample,
+                         "single_thread_value": one},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "oracle_build_ms_per_mtri": build_s * 1e3 / (N_TRIS / 1e6),
     }))
@@ -399,7 +411,8 @@ def run_gpu(args):
             bytes_per_ray = 32 + 8 + 128 * nm + 40 * npr
             cpu = {"value": rate, "unit": "Mrays/s", "cores": threads, "kind": "port",
                    "sample": f"first {n_s} rays of the timed workload (the very rays the GPU steps trace), Mbvh single-ray "
-                             f"closest hit, OpenMP dynamic chunks of 1000"}
+                             f"closest hit, OpenMP dynamic chunks of 1000",
+                   "single_thread_value": cpu_single_thread_rate(O, otree, tris, host_rays)}
             # parity spot check inside the bench: oracle vs GPU on the sample
             want, _, _ = O.trace(otree, tris, host_rays[:200_000], threads=threads)
             got = d_hits[0][: 200_000 * 2].cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
