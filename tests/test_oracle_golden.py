@@ -130,3 +130,23 @@ def test_leaf_depth_stats_for_the_build_roofline(O, W, teapot, teapot_trees):
     one = nodes[:1].copy()
     one["count"], one["left_first"] = 3, 0
     assert W.leaf_depth_stats(one) == {"leaves": 1, "prims": 3, "max_depth": 0, "mean_leaf_depth": 0.0, "mean_leaf_depth_per_prim": 0.0}
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 1000, 20000])
+def test_locb_trees_equal_brute_force_on_random_soups(O, W, n):
+    """Size-independent property: a LOCB tree has conservative boxes (plain unions, no quirk Q3), so
+    closest hit through the Bvh and through its collapsed Mbvh must equal the brute-force arbiter record for record
+    (same triangle test, lowest id on exact ties), for ragged sizes down to a single triangle."""
+    tris = W.soup(n, seed=0xC0FFEE + n)
+    aabbs, centers = O.prims_from_triangles(tris)
+    rc, bvh = O.build(O.LOCB, aabbs, centers, 1)
+    assert rc == 0 and bvh.validate(n)
+    m = bvh.collapse()
+    lo, hi = W.bounds(tris)
+    rays = W.random_rays(4000, lo, hi, seed=7 + n)
+    bf = O.brute_force(tris, rays)
+    for tree in (bvh, m):
+        got, _, _ = O.trace(tree, tris, rays)
+        assert np.array_equal(got, bf)
+        occ, _, _ = O.trace(tree, tris, rays, mode="any")
+        assert np.array_equal(occ.astype(bool), bf["prim"] != 0xFFFFFFFF)
