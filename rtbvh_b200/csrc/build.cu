@@ -1150,6 +1150,268 @@ __global__ void __launch_bounds__(kSmallWarps * 32, RTB_SMALL_MINBLOCKS) sah_sma
     if (lane == 0) used_nodes[t] = next_free - task.node_base;
 }
 
+// ---- EXPERIMENTAL (RTBVH_SAH_SMALL=ls, default off): the same subtrees, LEVEL-SYNCHRONOUS inside the warp.  Measured
+// (profiles/r3e_ls_ab.json, AB_LS=1 scripts/partition_ab.py): trees byte-identical to sah_small_kernel's on every scene, but
+// 1.7x SLOWER per build at 1 Mi triangles — every pass walks as far as the largest open node of its depth, so small
+// siblings wait for big ones.  Kept as a verified-correct base for a variant with per-node walk lengths.
+// sah_small_kernel is issue-bound at ~530 warp instructions per inner node (profiles/r3b_build_ncu.md) because the warp
+// works on one node at a time and most nodes hold 2-8 primitives.  Here lane j holds tile position j, every position
+// belongs to exactly one OPEN node of the current subtree depth (a contiguous range [b, e)), and all open nodes of a depth
+// go through the same instructions:
+//   * candidates: lane j evaluates, per axis, the one split position s = bin_j + 1 of its own node (the rule of the
+//     compact path of sah_small_kernel, valid for any node size: a position that is not right behind an occupied bin
+//     repeats its predecessor's partition and can never be find_split's first strict minimum) by walking its node's range
+//     in the shared-memory tile;
+//   * per-node minima, counts and child boxes: warp reductions over the node's lanes (__match_any_sync on b);
+//   * stable partition of all open nodes with one ballot;
+//   * nodes are collected in a shared-memory table and written at the end with sah_small_kernel's numbering (child pairs in
+//     DFS pre-order of the splitting nodes: rank = # splitting nodes with a smaller b, or the same b and a smaller depth).
+// Decisions, boxes, index order and node numbering are meant to be identical to sah_small_kernel's, bit for bit.
+constexpr int kLsWarps = 4;
+constexpr int kLsNodes = 64;  // <= 31 inner + 32 leaf nodes per subtree
+__device__ __forceinline__ uint32_t seg_min_key(unsigned peers, bool in, float v) { return __reduce_min_sync(peers, in ? fkey(v) : fkey(1e34f)); }
+__device__ __forceinline__ uint32_t seg_max_key(unsigned peers, bool in, float v) { return __reduce_max_sync(peers, in ? fkey(v) : fkey(-1e34f)); }
+__global__ void __launch_bounds__(kLsWarps * 32, 4) sah_small_ls_kernel(const SmallTask* __restrict__ tasks, uint32_t S,
+                                                                        uint32_t* __restrict__ idx, const float4* __restrict__ bb,
+                                                                        const float* __restrict__ cen, uint32_t cstride,
+                                                                        float4* nodes, uint32_t max_leaf,
+                                                                        uint32_t* __restrict__ used_nodes) {
+    __shared__ float4 s_lo[kLsWarps][32];       // min xyz | packed bin ids (this level)
+    __shared__ float4 s_hi[kLsWarps][32];       // max xyz | primitive id
+    __shared__ float s_cen[kLsWarps][32][3];
+    __shared__ float4 t_lo[kLsWarps][kLsNodes];  // node table: min xyz | count (-1: inner)
+    __shared__ float4 t_hi[kLsWarps][kLsNodes];  //             max xyz | left_first of a leaf
+    __shared__ uint32_t t_meta[kLsWarps][kLsNodes];  // parent | side << 8 | b << 16 | level << 24
+    __shared__ uint32_t t_pair[kLsWarps][kLsNodes];  // inner nodes: global index of the child pair
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * kLsWarps + w;
+    if (t >= S) return;
+    const SmallTask task = tasks[t];
+    const uint32_t n = task.end - task.begin;
+    if ((uint32_t)lane < n) {
+        const uint32_t p = idx[task.begin + lane];
+        const float4 l4 = bb[(size_t)p * 2], h4 = bb[(size_t)p * 2 + 1];
+        s_lo[w][lane] = make_float4(l4.x, l4.y, l4.z, 0.f);
+        s_hi[w][lane] = make_float4(h4.x, h4.y, h4.z, __uint_as_float(p));
+        for (int k = 0; k < 3; k++) s_cen[w][lane][k] = cen[(size_t)p * cstride + k];
+    }
+    // per-lane view of the open node this tile position belongs to (uniform over the node's lanes)
+    bool open = (uint32_t)lane < n;
+    uint32_t sb = 0, se = n, entry = 0;
+    Box nbox = load_box(nodes, task.node);  // as left by sah_emit_kernel: the un-padded child box
+    uint32_t n_entries = 1, level = 0;
+    if (lane == 0) t_meta[w][0] = 0u;  // the root: parent / side unused, b = 0, level = 0
+    __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
+    while (__any_sync(0xFFFFFFFFu, open)) {
+        const uint32_t depth = task.depth + level;  // of every open node of this pass
+        const uint32_t nn = se - sb;
+        Box nb = nbox;
+        box_pad(nb, kPad);  // entry pad (binned_sah.rs:133)
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, open ? sb : 0x100u + (uint32_t)lane);
+        // an open node always has >= 2 primitives and depth < kMaxDepth: leaves on entry are finalised by their parent,
+        // and a small task is created with >= 2 primitives below the depth cap
+        uint32_t bins3 = 0;
+        if (open) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float kk = fmul(fdiv(1.0f, fsub(nb.mx[k], nb.mn[k])), (float)kBins);
+                const float off = fmul(-nb.mn[k], kk);
+                bins3 |= (uint32_t)bin_index(s_cen[w][lane][k], kk, off) << (8 * k);
+            }
+            s_lo[w][lane].w = __uint_as_float(bins3);
+        }
+        __syncwarp();
+        // ---- candidates: s = bin + 1 per axis, cost over the node's range --------------------------------------------
+        uint32_t cs[3], cl[3], cr[3];
+        Box L[3], R[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            cs[a] = ((bins3 >> (8 * a)) & 0xFFu) + 1u;
+            cl[a] = cr[a] = 0u;
+            L[a] = R[a] = box_empty();
+        }
+        const uint32_t maxlen = __reduce_max_sync(0xFFFFFFFFu, open ? nn : 0u);
+        for (uint32_t d = 0; d < maxlen; d++) {
+            const uint32_t j = sb + d;
+            if (open && j < se) {
+                const float4 l4 = s_lo[w][j], h4 = s_hi[w][j];
+                const Box pb{{l4.x, l4.y, l4.z}, {h4.x, h4.y, h4.z}};
+                const uint32_t bj = __float_as_uint(l4.w);
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    if (((bj >> (8 * a)) & 0xFFu) < cs[a]) {
+                        L[a] = box_union(L[a], pb);
+                        cl[a]++;
+                    } else {
+                        R[a] = box_union(R[a], pb);
+                        cr[a]++;
+                    }
+                }
+            }
+        }
+        // ---- find_split per axis: first strict minimum below f32::MAX in order s = 1..15 (binned_sah.rs:95-111) ------
+        float best_cost[3];
+        uint32_t best_count[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const bool valid = open && cs[a] < (uint32_t)kBins;
+            const float c = fadd(fmul(box_half_area(L[a]), (float)cl[a]), fmul(box_half_area(R[a]), (float)cr[a]));
+            const uint32_t key = (valid && c < FLT_MAX) ? fkey(c) : 0xFFFFFFFFu;
+            const uint32_t m = __reduce_min_sync(peers, key);
+            const uint32_t sa = __reduce_min_sync(peers, (key == m && m != 0xFFFFFFFFu) ? cs[a] : (uint32_t)kBins);
+            best_cost[a] = m == 0xFFFFFFFFu ? FLT_MAX : fkey_inv(m);
+            best_count[a] = m == 0xFFFFFFFFu ? (uint32_t)kBins : sa;
+        }
+        int best_axis = 0;
+        if (best_cost[0] > best_cost[1]) best_axis = 1;
+        if ((best_axis == 0 ? best_cost[0] : best_cost[1]) > best_cost[2]) best_axis = 2;
+        uint32_t split_index = best_axis == 0 ? best_count[0] : (best_axis == 1 ? best_count[1] : best_count[2]);
+        const float axis_cost = best_axis == 0 ? best_cost[0] : (best_axis == 1 ? best_cost[1] : best_cost[2]);
+        const float max_split_cost = fmul(box_half_area(nb), fsub((float)nn, 1.0f));
+        bool do_split = open, fallback = false;
+        if (open && (split_index == (uint32_t)kBins || axis_cost >= max_split_cost)) {
+            if (nn > max_leaf) {
+                fallback = true;  // ~40 % median on the longest axis (binned_sah.rs:189-205)
+                best_axis = box_longest_axis(nb);
+            } else {
+                do_split = false;
+            }
+        }
+        {   // fallback index: first bin i < 15 whose cumulative count reaches floor(2n/5) + 1.  cl[axis] of lane j is the
+            // number of primitives of the node with bin <= bin_j; empty bins repeat their predecessor's count, so the
+            // first bin that qualifies is an occupied one.  All lanes take part in the reduction (segments are disjoint).
+            const uint32_t need = (uint32_t)(((uint64_t)nn * 2ull) / 5ull + 1ull);
+            const uint32_t mycl = best_axis == 0 ? cl[0] : (best_axis == 1 ? cl[1] : cl[2]);
+            const uint32_t mys = best_axis == 0 ? cs[0] : (best_axis == 1 ? cs[1] : cs[2]);
+            const uint32_t cand = (fallback && mys < (uint32_t)kBins && mycl >= need) ? mys : (uint32_t)kBins;
+            const uint32_t fs = __reduce_min_sync(peers, cand);
+            if (fallback && fs < (uint32_t)kBins) split_index = fs;
+        }
+        const uint32_t mybin = (bins3 >> (8 * best_axis)) & 0xFFu;
+        const bool goes_left = do_split && mybin < split_index;
+        const uint32_t lmask = __ballot_sync(0xFFFFFFFFu, goes_left) & peers;
+        const uint32_t nleft = (uint32_t)__popc(lmask);
+        if (nleft == 0 || nleft == nn) do_split = false;  // one side empty -> leaf (binned_sah.rs:222, :277-281)
+        // ---- child boxes: unions over the node's lanes.  Regular split: bins < split_index | >= split_index (what the
+        // winning candidate accumulated); fallback, quirk Q3: the left box uses the SAH split count of the final axis.
+        const uint32_t q_left = fallback ? (best_axis == 0 ? best_count[0] : (best_axis == 1 ? best_count[1] : best_count[2])) : split_index;
+        const bool in_l = do_split && mybin < q_left, in_r = do_split && mybin >= split_index;
+        const float4 mylo = s_lo[w][lane], myhi = s_hi[w][lane];
+        Box lb, rb;
+        lb.mn[0] = fkey_inv(seg_min_key(peers, in_l, mylo.x));
+        lb.mn[1] = fkey_inv(seg_min_key(peers, in_l, mylo.y));
+        lb.mn[2] = fkey_inv(seg_min_key(peers, in_l, mylo.z));
+        lb.mx[0] = fkey_inv(seg_max_key(peers, in_l, myhi.x));
+        lb.mx[1] = fkey_inv(seg_max_key(peers, in_l, myhi.y));
+        lb.mx[2] = fkey_inv(seg_max_key(peers, in_l, myhi.z));
+        rb.mn[0] = fkey_inv(seg_min_key(peers, in_r, mylo.x));
+        rb.mn[1] = fkey_inv(seg_min_key(peers, in_r, mylo.y));
+        rb.mn[2] = fkey_inv(seg_min_key(peers, in_r, mylo.z));
+        rb.mx[0] = fkey_inv(seg_max_key(peers, in_r, myhi.x));
+        rb.mx[1] = fkey_inv(seg_max_key(peers, in_r, myhi.y));
+        rb.mx[2] = fkey_inv(seg_max_key(peers, in_r, myhi.z));
+        // ---- node table: this node, and two entries per splitting node (numbered by the order of the nodes' b) --------
+        const bool leader = open && (uint32_t)lane == sb;
+        const uint32_t split_leaders = __ballot_sync(0xFFFFFFFFu, leader && do_split);
+        const uint32_t child0 = n_entries + 2u * (uint32_t)__popc(split_leaders & ((1u << sb) - 1u));  // left child entry
+        const bool cap = depth + 1 >= (uint32_t)kMaxDepth;
+        const uint32_t nright = nn - nleft;
+        const bool l_leaf = nleft <= 1 || cap, r_leaf = nright <= 1 || cap;
+        if (leader) {
+            if (!do_split) {  // make_leaf(nb): second pad, left_first = begin, count = n
+                Box b2 = nb;
+                box_pad(b2, kPad);
+                t_lo[w][entry] = make_float4(b2.mn[0], b2.mn[1], b2.mn[2], __int_as_float((int)nn));
+                t_hi[w][entry] = make_float4(b2.mx[0], b2.mx[1], b2.mx[2], __int_as_float((int)(task.begin + sb)));
+            } else {
+                t_lo[w][entry] = make_float4(nb.mn[0], nb.mn[1], nb.mn[2], __int_as_float(-1));
+                t_hi[w][entry] = make_float4(nb.mx[0], nb.mx[1], nb.mx[2], __int_as_float(-1));
+                t_meta[w][child0] = entry | (0u << 8) | (sb << 16) | ((level + 1u) << 24);
+                t_meta[w][child0 + 1] = entry | (1u << 8) | ((sb + nleft) << 16) | ((level + 1u) << 24);
+                if (l_leaf) {  // leaf on entry: entry pad + make_leaf pad (binned_sah.rs:133-143)
+                    Box b2 = lb;
+                    box_pad(b2, kPad);
+                    box_pad(b2, kPad);
+                    t_lo[w][child0] = make_float4(b2.mn[0], b2.mn[1], b2.mn[2], __int_as_float((int)nleft));
+                    t_hi[w][child0] = make_float4(b2.mx[0], b2.mx[1], b2.mx[2], __int_as_float((int)(task.begin + sb)));
+                }
+                if (r_leaf) {
+                    Box b2 = rb;
+                    box_pad(b2, kPad);
+                    box_pad(b2, kPad);
+                    t_lo[w][child0 + 1] = make_float4(b2.mn[0], b2.mn[1], b2.mn[2], __int_as_float((int)nright));
+                    t_hi[w][child0 + 1] = make_float4(b2.mx[0], b2.mx[1], b2.mx[2], __int_as_float((int)(task.begin + sb + nleft)));
+                }
+            }
+        }
+        n_entries += 2u * (uint32_t)__popc(split_leaders);
+        // ---- stable partition of every splitting node, all at once ---------------------------------------------------
+        const uint32_t inmask = __ballot_sync(0xFFFFFFFFu, open && do_split) & peers;
+        uint32_t dest = (uint32_t)lane;
+        if (open && do_split)
+            dest = goes_left ? sb + (uint32_t)__popc(lmask & lt) : sb + nleft + (uint32_t)__popc((inmask & ~lmask) & lt);
+        float myc[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) myc[k] = s_cen[w][lane][k];
+        __syncwarp();
+        if ((uint32_t)lane < n) {
+            s_lo[w][dest] = mylo;
+            s_hi[w][dest] = myhi;
+#pragma unroll
+            for (int k = 0; k < 3; k++) s_cen[w][dest][k] = myc[k];
+        }
+        __syncwarp();
+        // ---- next pass: tile position `lane` now belongs to the left or the right child of the node it was in ----------
+        if (open && do_split) {
+            const bool is_left = (uint32_t)lane < sb + nleft;
+            open = is_left ? !l_leaf : !r_leaf;
+            entry = is_left ? child0 : child0 + 1u;
+            nbox = is_left ? lb : rb;
+            const uint32_t mid = sb + nleft;
+            if (is_left) se = mid; else sb = mid;
+        } else {
+            open = false;
+        }
+        level++;
+    }
+    __syncwarp();
+    // ---- numbering and write-out --------------------------------------------------------------------------------------
+    // child pair of a splitting node = node_base + 2 * (# splitting nodes before it in DFS pre-order); in pre-order node A
+    // precedes node B iff A.b < B.b, or A.b == B.b and A is the shallower one (then A is an ancestor of B).
+    uint32_t inner_count = 0;
+    for (uint32_t i = (uint32_t)lane; i < n_entries; i += 32) {
+        if (__float_as_int(t_lo[w][i].w) >= 0) continue;  // a leaf
+        const uint32_t mi = t_meta[w][i], bi = (mi >> 16) & 0xFFu, li = mi >> 24;
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n_entries; j++) {
+            if (j == i || __float_as_int(t_lo[w][j].w) >= 0) continue;
+            const uint32_t mj = t_meta[w][j], bj = (mj >> 16) & 0xFFu, lj = mj >> 24;
+            if (bj < bi || (bj == bi && lj < li)) rank++;
+        }
+        t_pair[w][i] = task.node_base + 2u * rank;
+    }
+    for (uint32_t j = 0; j < n_entries; j++) inner_count += __float_as_int(t_lo[w][j].w) < 0 ? 1u : 0u;
+    __syncwarp();
+    for (uint32_t i = (uint32_t)lane; i < n_entries; i += 32) {
+        const uint32_t mi = t_meta[w][i];
+        const uint32_t gid = i == 0 ? task.node : t_pair[w][mi & 0xFFu] + ((mi >> 8) & 1u);
+        float4 lo = t_lo[w][i], hi = t_hi[w][i];
+        if (__float_as_int(lo.w) < 0) hi.w = __int_as_float((int)t_pair[w][i]);  // inner: left_first = its child pair
+        nodes[(size_t)gid * 2] = lo;
+        nodes[(size_t)gid * 2 + 1] = hi;
+    }
+    if ((uint32_t)lane < n) idx[task.begin + lane] = __float_as_uint(s_hi[w][lane].w);
+    if (lane == 0) used_nodes[t] = 2u * inner_count;
+}
+bool small_ls_mode() {
+    static const bool v = [] {
+        const char* e = std::getenv("RTBVH_SAH_SMALL");
+        return e && std::string(e) == "ls";
+    }();
+    return v;
+}
+
 // ---- compaction of the node array when small subtrees used fewer slots than reserved ---------------
 // waste_prefix[t] = exclusive scan of (reserved - used) over the small tasks (ordered by node_base).
 __device__ __forceinline__ uint32_t small_remap(uint32_t node, uint32_t level_nodes, const SmallTask* __restrict__ tasks,
@@ -2035,8 +2297,12 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         // rebase the reserved ranges behind the level nodes, then let one warp finish each subtree
         RTB_CUDA(used.alloc((size_t)S * 4));
         small_rebase_kernel<<<blocks(S, 256), 256>>>(small_tasks.as<SmallTask>(), S, level_nodes);
-        sah_small_kernel<<<blocks(S, kSmallWarps), kSmallWarps * 32>>>(small_tasks.as<SmallTask>(), S, idx_cur, d_bb, d_cen, cstride,
-                                                                       nodes, max_leaf, used.as<uint32_t>());
+        if (small_ls_mode())
+            sah_small_ls_kernel<<<blocks(S, kLsWarps), kLsWarps * 32>>>(small_tasks.as<SmallTask>(), S, idx_cur, d_bb, d_cen, cstride,
+                                                                        nodes, max_leaf, used.as<uint32_t>());
+        else
+            sah_small_kernel<<<blocks(S, kSmallWarps), kSmallWarps * 32>>>(small_tasks.as<SmallTask>(), S, idx_cur, d_bb, d_cen, cstride,
+                                                                           nodes, max_leaf, used.as<uint32_t>());
         // compaction only if some subtree ended early (leaves with several primitives)
         RTB_CUDA(waste.alloc((size_t)S * 4));
         RTB_CUDA(waste_prefix.alloc((size_t)(S + 1) * 4));

@@ -43,11 +43,15 @@ MODES = {  # environment of every child; "all" = the library's defaults
     "part+scanemit": {"RTBVH_SAH_MERGE": "0"},
     "all": {},
 }
+if os.environ.get("AB_LS") == "1":  # the experimental level-synchronous small-subtree kernel (never verified on a GPU yet)
+    MODES["all+ls"] = {"RTBVH_SAH_SMALL": "ls"}
 
 
 def main():
     res = {}
-    for mode, extra in MODES.items():
+    only = [m for m in os.environ.get("AB_ONLY", "").split(",") if m]
+    modes = {m: e for m, e in MODES.items() if not only or m in only or m == "legacy"}
+    for mode, extra in modes.items():
         env = {k: v for k, v in os.environ.items() if not k.startswith("RTBVH_SAH_")}
         env.update(extra)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=env, capture_output=True, text=True, timeout=300)
@@ -62,7 +66,7 @@ def main():
                "device_ms_median": {k: {m: round(sorted(res[m][k]["device_ms"])[len(res[m][k]["device_ms"]) // 2], 3) for m in res}
                                     for k in ref}}
     print(json.dumps(summary))
-    sys.exit(0 if all(summary["identical_to_legacy"].values()) and len(res) == len(MODES) else 2)
+    sys.exit(0 if all(summary["identical_to_legacy"].values()) and len(res) == len(modes) else 2)
 
 
 if __name__ == "__main__":
