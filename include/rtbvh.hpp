@@ -16,6 +16,9 @@
 // Header only; link with -lrtbvh_rs (rtbvh_b200/librtbvh_rs.so).  Builds run on the GPU; the iterators walk the
 // host mirror exactly like the reference's (rtbvh_iter.hpp).
 #pragma once
+#ifndef RTBVH_HPP  // the include guard of the reference's generated C++ header (rtbvh_ffi/build.rs:37)
+#define RTBVH_HPP
+#endif
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -29,6 +32,28 @@
 #include "rtbvh_iter.hpp"
 
 namespace rtbvh {
+
+// The reference also generates a C++ flavour of its FFI header (rtbvh_ffi/build.rs:33-45: cbindgen Language::Cxx,
+// namespace `rtbvh`, guard RTBVH_HPP), whose callers spell the C ABI as rtbvh::create_bvh(..), rtbvh::RTBvh,
+// rtbvh::ResultCode::Ok, rtbvh::BvhType::BinnedSAH.  The same spellings resolve here (the enums are the C header's
+// unscoped ones, so the qualified names work and the values are the same).
+using ::BvhType;
+using ::ResultCode;
+using ::RTAabb;
+using ::RTBvh;
+using ::RTBvhNode;
+using ::RTMbvh;
+using ::RTMbvhNode;
+using ::create_bvh;
+using ::create_mbvh;
+using ::create_spatial_Bvh;
+using ::free_bvh;
+using ::free_mbvh;
+using ::intersect;
+using ::intersect_mbvh;
+using ::intersect_mbvh_packet;
+using ::intersect_packet;
+using ::refit;
 
 struct Vec3 {
     float x = 0, y = 0, z = 0;
