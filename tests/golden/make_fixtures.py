@@ -66,6 +66,23 @@ def main():
         h4, _, _ = O.trace(m, tris, rays)
         out[name + "_bvh_hits"] = h2
         out[name + "_mbvh_hits"] = h4
+        # the flavours the first version did not pin: any hit, packets of four (closest + any), on a smaller ray set
+        sub = rays[::5][: 16384 // 4 * 4]
+        packets = W.pack4(sub)
+        for tag, tree in (("bvh", bvh), ("mbvh", m)):
+            out[f"{name}_{tag}_any"] = O.trace(tree, tris, sub, mode="any")[0]
+            out[f"{name}_{tag}_packet_hits"] = O.trace_packets(tree, tris, packets)[0]
+            out[f"{name}_{tag}_packet_any"] = O.trace_packets(tree, tris, packets, mode="any")[0]
+    # refit (src/bvh.rs:176-205, topology kept) and the spatial-split restatement (fixed child ranges)
+    rc, bvh = O.build(O.BINNED_SAH, aabbs, centers, 1)
+    moved = aabbs.copy()
+    moved["min"] += np.float32(0.25)
+    moved["max"] += np.float32(0.5)
+    out["refit_nodes_sha"] = sha(bvh.refit(moved).nodes)
+    sp = O.build_spatial(tris[:2000], 1)
+    sp = sp[1] if isinstance(sp, tuple) else sp
+    out["spatial_nodes_sha"] = sha(sp.nodes)
+    out["spatial_indices_sha"] = sha(sp.indices)
     np.savez_compressed(os.path.join(HERE, "oracle_golden.npz"), **out)
     print({k: v for k, v in out.items() if not isinstance(v, np.ndarray)})
 

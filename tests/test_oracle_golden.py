@@ -26,6 +26,25 @@ def test_oracle_matches_golden(O, W, teapot, teapot_trees, name):
     h2, _, _ = O.trace(bvh, teapot["tris"], rays)
     h4, _, _ = O.trace(m, teapot["tris"], rays)
     assert np.array_equal(h2, g[name + "_bvh_hits"]) and np.array_equal(h4, g[name + "_mbvh_hits"])
+    # any hit and packets of four (closest + any), pinned on a subset of the same rays
+    sub = rays[::5][: 16384 // 4 * 4]
+    packets = W.pack4(sub)
+    for tag, tree in (("bvh", bvh), ("mbvh", m)):
+        assert np.array_equal(O.trace(tree, teapot["tris"], sub, mode="any")[0], g[f"{name}_{tag}_any"])
+        assert np.array_equal(O.trace_packets(tree, teapot["tris"], packets)[0], g[f"{name}_{tag}_packet_hits"])
+        assert np.array_equal(O.trace_packets(tree, teapot["tris"], packets, mode="any")[0], g[f"{name}_{tag}_packet_any"])
+
+
+def test_refit_and_spatial_builder_match_golden(O, teapot, teapot_trees):
+    g = np.load(GOLDEN)
+    bvh, _ = teapot_trees["sah"]
+    moved = teapot["aabbs"].copy()
+    moved["min"] += np.float32(0.25)
+    moved["max"] += np.float32(0.5)
+    assert sha(bvh.refit(moved).nodes) == str(g["refit_nodes_sha"])
+    rc, sp = O.build_spatial(teapot["tris"][:2000], 1)
+    assert rc == 0
+    assert sha(sp.nodes) == str(g["spatial_nodes_sha"]) and sha(sp.indices) == str(g["spatial_indices_sha"])
 
 
 def test_locb_tree_equals_brute_force(O, W, teapot, teapot_trees):
