@@ -467,59 +467,54 @@ def run_gpu(args):
 
 
 def build_trees(api, tris, info, rank):
-    """Tree for the bench.  The GPU builder (create_bvh -> create_mbvh) is the product path; while it is not
-    available the reference-format tree built by the CPU oracle is uploaded unchanged (north_star check 1)."""
-    if os.environ.get("RTBVH_BENCH_TREE", "gpu") == "gpu":
-        mtri = len(tris) / 1e6
-        api.build_triangles(tris, api.BINNED_SAH, 1).free()  # warm-up: module load, memory pool growth
-        dev, tot, bvh = [], [], None
-        for _ in range(3):
-            if bvh is not None:
-                bvh.free()
-            bvh = api.build_triangles(tris, api.BINNED_SAH, 1)
-            st = api.last_build_stats()
-            dev.append(st["device_ms"])
-            tot.append(st["total_ms"])
-        mbvh = api.Mbvh.construct(bvh)
-        cst = api.last_build_stats()
-        # the same build straight into a device-resident scene (no host mirror): wall clock of the whole call from host
-        # vertices, i.e. H2D of 36 MB of vertices + prims + binned SAH + collapse + triangle records
-        api.Scene.build(tris, api.BINNED_SAH, 1, mbvh=True).free()
-        res_wall, res_dev = [], []
-        for _ in range(3):
-            t0 = time.perf_counter()
-            rs = api.Scene.build(tris, api.BINNED_SAH, 1, mbvh=True)
-            res_wall.append((time.perf_counter() - t0) * 1e3)
-            res_dev.append(api.last_build_stats()["device_ms"])
-            rs.free()
-        # the build's own roofline (SURVEY.md section 8d): 148 + 60 * D-bar algorithmic bytes per triangle, D-bar = mean
-        # leaf depth (per primitive) of the tree just built, over the measured device time of one build
-        try:
-            ds = W.leaf_depth_stats(bvh.nodes)
-            bpt = W.binned_sah_bytes_per_tri(ds["mean_leaf_depth_per_prim"])
-            peak, peak_src = measured_peak_gbs()
-            ach = bpt * len(tris) / (float(np.median(dev)) * 1e-3) / 1e9
-            build_roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                              "peak_source": peak_src, "bytes_per_tri": bpt,
-                              "mean_leaf_depth": ds["mean_leaf_depth_per_prim"], "max_depth": ds["max_depth"],
-                              "kernels": "all kernels of one binned-SAH build (level loop + small-subtree kernel)"}
-        except Exception as e:  # a statistics failure must not cost the bench line
-            build_roofline = {"error": f"{type(e).__name__}: {e}"}
-        info.update(tree="gpu-built: rtbvh_gpu_create_bvh_triangles(BinnedSAH) + create_mbvh",
-                    build={"binned_sah_ms_per_mtri": float(np.median(dev)) / mtri,
-                           "roofline": build_roofline,
-                           "binned_sah_ms_per_mtri_incl_h2d_d2h": float(np.median(tot)) / mtri,
-                           "binned_sah_device_ms_runs": dev, "collapse_device_ms": cst["device_ms"],
-                           "collapse_ms_incl_h2d_d2h": cst["total_ms"], "bvh_nodes": int(bvh.rt.node_count),
-                           "mbvh_nodes": int(mbvh.rt.node_count),
-                           "resident_scene_build_wall_ms": float(np.median(res_wall)),
-                           "resident_scene_build_device_ms": float(np.median(res_dev)),
-                           "timing": "CUDA events around the builder kernels, triangles resident -> tree resident; median of 3"})
-        return bvh, mbvh, info
-    O, obvh, om, build_s = oracle_tree(tris)
-    info.update(tree="reference-format tree built by the CPU oracle, uploaded unchanged",
-                oracle_build_ms_per_mtri=build_s * 1e3 / (len(tris) / 1e6))
-    return api.Bvh.from_arrays(obvh.nodes, obvh.indices), api.Mbvh.from_arrays(om.nodes, om.indices), info
+    """Tree for the bench: built on the GPU (rtbvh_gpu_create_bvh_triangles -> create_mbvh), the product path.  (Reference-built
+    trees uploaded unchanged are measured by scripts/matrix.py and scripts/config5.py, not here.)"""
+    mtri = len(tris) / 1e6
+    api.build_triangles(tris, api.BINNED_SAH, 1).free()  # warm-up: module load, memory pool growth
+    dev, tot, bvh = [], [], None
+    for _ in range(3):
+        if bvh is not None:
+            bvh.free()
+        bvh = api.build_triangles(tris, api.BINNED_SAH, 1)
+        st = api.last_build_stats()
+        dev.append(st["device_ms"])
+        tot.append(st["total_ms"])
+    mbvh = api.Mbvh.construct(bvh)
+    cst = api.last_build_stats()
+    # the same build straight into a device-resident scene (no host mirror): wall clock of the whole call from host
+    # vertices, i.e. H2D of 36 MB of vertices + prims + binned SAH + collapse + triangle records
+    api.Scene.build(tris, api.BINNED_SAH, 1, mbvh=True).free()
+    res_wall, res_dev = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        rs = api.Scene.build(tris, api.BINNED_SAH, 1, mbvh=True)
+        res_wall.append((time.perf_counter() - t0) * 1e3)
+        res_dev.append(api.last_build_stats()["device_ms"])
+        rs.free()
+    # the build's own roofline (SURVEY.md section 8d): 148 + 60 * D-bar algorithmic bytes per triangle, D-bar = mean
+    # leaf depth (per primitive) of the tree just built, over the measured device time of one build
+    try:
+        ds = W.leaf_depth_stats(bvh.nodes)
+        bpt = W.binned_sah_bytes_per_tri(ds["mean_leaf_depth_per_prim"])
+        peak, peak_src = measured_peak_gbs()
+        ach = bpt * len(tris) / (float(np.median(dev)) * 1e-3) / 1e9
+        build_roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                          "peak_source": peak_src, "bytes_per_tri": bpt,
+                          "mean_leaf_depth": ds["mean_leaf_depth_per_prim"], "max_depth": ds["max_depth"],
+                          "kernels": "all kernels of one binned-SAH build (level loop + small-subtree kernel)"}
+    except Exception as e:  # a statistics failure must not cost the bench line
+        build_roofline = {"error": f"{type(e).__name__}: {e}"}
+    info.update(tree="gpu-built: rtbvh_gpu_create_bvh_triangles(BinnedSAH) + create_mbvh",
+                build={"binned_sah_ms_per_mtri": float(np.median(dev)) / mtri,
+                       "roofline": build_roofline,
+                       "binned_sah_ms_per_mtri_incl_h2d_d2h": float(np.median(tot)) / mtri,
+                       "binned_sah_device_ms_runs": dev, "collapse_device_ms": cst["device_ms"],
+                       "collapse_ms_incl_h2d_d2h": cst["total_ms"], "bvh_nodes": int(bvh.rt.node_count),
+                       "mbvh_nodes": int(mbvh.rt.node_count),
+                       "resident_scene_build_wall_ms": float(np.median(res_wall)),
+                       "resident_scene_build_device_ms": float(np.median(res_dev)),
+                       "timing": "CUDA events around the builder kernels, triangles resident -> tree resident; median of 3"})
+    return bvh, mbvh, info
 
 
 def main():
