@@ -20,6 +20,8 @@ fov, hashed sub-pixel jitter per (frame, pixel).  One STEP = `--frames-per-step`
            examples/benchmark.rs:25) on all host cores, on a bounded sample of the same rays.
 
 `--impl reference` times that CPU port alone (the reference itself is Rust and cannot be built in this image).
+`--config {1,3,4,5}` runs the other BASELINE.json configs (bench_configs.py) with the same JSON shape; config 1 (teapot,
+examples/benchmark.rs) is the one with published reference numbers and fills `vs_baseline`.
 """
 from __future__ import annotations
 
@@ -43,72 +45,7 @@ WIDTH = HEIGHT = 1000
 N_TRIS = 1 << 20
 
 
-def log(*a):
-    print(*a, file=sys.stderr, flush=True)
-
-
-def measured_peak_gbs():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        except Exception:
-            pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-
-
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the traversal kernel per launch, from the committed
-    `ncu --set full` capture of this same workload (profiles/ncu_traffic.json); None if absent."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    try:
-        return float(json.load(open(p))["dram_bytes_per_launch"])
-    except Exception:
-        return None
-
-
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+from bench_common import ClockSampler, host_threads, log, measured_peak_gbs, ncu_traffic  # noqa: E402,F401
 
 
 def build_scene_host():
@@ -129,14 +66,6 @@ def oracle_tree(tris):
     build_s = time.time() - t0
     m = bvh.collapse()
     return O, bvh, m, build_s
-
-
-def host_threads():
-    """All host cores this process may use (torchrun sets OMP_NUM_THREADS=1, which must not shrink the CPU arm)."""
-    try:
-        return max(1, len(os.sched_getaffinity(0)))
-    except AttributeError:
-        return max(1, os.cpu_count() or 1)
 
 
 def cpu_sample_rate(O, m, tris, rays, target_s=10.0):
@@ -520,9 +449,12 @@ def build_trees(api, tris, info, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=125)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="default: 125 (config 2: the config's 1 B rays), 40 / 10 / 20 / 20 for configs 1 / 3 / 4 / 5")
+    ap.add_argument("--warmup", type=int, default=None, help="default 5 (config 3: 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json config (1-based): 2 = the config the metric is quoted on (default); 1, 3, 4, 5 live in "
+                         "bench_configs.py with the same JSON shape")
     ap.add_argument("--frames-per-step", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / roofline sample (profiling runs)")
@@ -530,6 +462,10 @@ def main():
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N > 1: fused = P2P stores from inside the traversal kernel; nccl = all_gather on a side stream")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = {1: 40, 2: 125, 3: 10, 4: 20, 5: 20}[args.config]
+    if args.warmup is None:
+        args.warmup = 3 if args.config == 3 else 5
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: `python bench.py --gpus N` re-launches itself one rank per GPU (the driver uses torchrun directly)
         import socket
@@ -540,7 +476,10 @@ def main():
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", str(port),
                                    os.path.abspath(__file__)] + sys.argv[1:])
-    if args.impl == "reference":
+    if args.config != 2:
+        import bench_configs
+        bench_configs.run(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

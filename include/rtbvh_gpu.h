@@ -103,7 +103,12 @@ ResultCode rtbvh_gpu_trim_workspace(void);
  * (the reference never refreshes m_nodes) — and re-gathers the triangle records.  Nothing leaves the device; the host
  * mirrors behind RTBvh / RTMbvh are not touched (rtbvh_gpu_scene_read_nodes reads the device copy).  The scene must hold
  * the Bvh; an Mbvh in it must be the collapse of that Bvh.  The _device flavour takes device vertices and only
- * enqueues work on `stream`: traversal calls enqueued behind it on that stream see the refitted trees. */
+ * enqueues work on `stream`: traversal calls enqueued behind it on that stream see the refitted trees.
+ * Ordering: both flavours are ordered against the scene's own host-buffer pipeline — batches submitted before the refit
+ * (rtbvh_gpu_*_async included) finish on the old trees, batches submitted after it see the new ones — and consecutive
+ * refits of one scene are chained (they share one scratch area), whatever streams they were given.  Device-pointer
+ * traversal calls (*_device, *_device_scatter) run on the CALLER's streams and are ordered by the caller like any
+ * stream-ordered work: use the refit's stream, or an event.  The blocking flavour returns when the refit has finished. */
 ResultCode rtbvh_gpu_scene_refit(RTGpuScene scene, const float *vertices, size_t vertex_stride, size_t triangle_count);
 ResultCode rtbvh_gpu_scene_refit_device(RTGpuScene scene, const float *d_vertices, size_t vertex_stride,
                                         size_t triangle_count, void *stream);

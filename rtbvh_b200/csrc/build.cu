@@ -2202,7 +2202,14 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
         // input is degenerate; a level enqueued after the last one is a no-op that passes the index order through).
         static thread_local LevelState* h_state = nullptr;
         if (!h_state) RTB_CUDA(cudaHostAlloc(&h_state, (size_t)(kMaxDepth + 3) * sizeof(LevelState), cudaHostAllocDefault));
-        cudaEvent_t ev[2];
+        struct EventPair {  // destroyed on every exit path of the level loop
+            cudaEvent_t e[2] = {nullptr, nullptr};
+            ~EventPair() {
+                if (e[0]) cudaEventDestroy(e[0]);
+                if (e[1]) cudaEventDestroy(e[1]);
+            }
+            cudaEvent_t& operator[](unsigned i) { return e[i]; }
+        } ev;
         RTB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
         RTB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
         // From the first level that could be free of span-class tasks (all tasks <= kWarpTask needs log2(n / kWarpTask)
@@ -2282,8 +2289,6 @@ static ResultCode build_binned_sah_device(const float4* d_bb, const float* d_cen
             }
         }
         RTB_CUDA(cudaEventSynchronize(ev[(depth - 1) & 1u]));
-        cudaEventDestroy(ev[0]);
-        cudaEventDestroy(ev[1]);
         RTB_CUDA(cudaGetLastError());
         fin = h_state[depth];
         if (fin.A != 0) return fail("binned SAH: level loop did not terminate");

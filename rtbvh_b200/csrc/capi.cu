@@ -51,7 +51,10 @@ constexpr int kReadySlots = 64;
 constexpr int kMarkSlots = 4096;
 
 // RTBVH_TRACE_MODE selects the single-ray kernel variant (A/B measurements); default: see kDefaultTraceMode
-constexpr int kDefaultTraceMode = kTracePersistent;
+#ifndef RTB_DEFAULT_TRACE_MODE
+#define RTB_DEFAULT_TRACE_MODE kTracePhased
+#endif
+constexpr int kDefaultTraceMode = RTB_DEFAULT_TRACE_MODE;
 int persistent_mode() {
     static const int v = [] {
         const char* e = std::getenv("RTBVH_TRACE_MODE");
@@ -59,16 +62,23 @@ int persistent_mode() {
         const std::string m(e);
         if (m == "static") return (int)kTraceStatic;
         if (m == "persistent") return (int)kTracePersistent;
+        if (m == "phased") return (int)kTracePhased;
         if (m == "coop") return (int)kTraceCoop;
         return kDefaultTraceMode;
     }();
     return v;
 }
 
+// the refill-kernel flavour for calls that need one (input gate, split input, fused gather)
+int refill_mode() {
+    const int m = persistent_mode();
+    return (m == kTracePersistent || m == kTracePhased) ? m : kDefaultTraceMode;
+}
+
 struct Scene {
     int device = 0;
-    DeviceTree bvh{nullptr, 0, nullptr, 0};
-    DeviceTree mbvh{nullptr, 0, nullptr, 0};
+    DeviceTree bvh{nullptr, 0, nullptr, 0, nullptr, 0};
+    DeviceTree mbvh{nullptr, 0, nullptr, 0, nullptr, 0};
     void* d_bvh_nodes = nullptr;
     void* d_mbvh_nodes = nullptr;
     TriRec* d_tris_bvh = nullptr;   // leaf order of the Bvh's indices
@@ -76,6 +86,8 @@ struct Scene {
     uint32_t* d_idx_bvh = nullptr;   // prim_indices of the trees (kept for refit: re-gathering the triangle records)
     uint32_t* d_idx_mbvh = nullptr;  // may alias d_idx_bvh
     uint32_t tri_count = 0;
+    float4* d_top = nullptr;          // staged-top table of the Mbvh (DeviceTree::top), rebuilt after every refit
+    uint32_t* d_top_count = nullptr;
     ResidentRefit refit_cache;       // topology analysis + scratch of rtbvh_gpu_scene_refit*
     float* d_refit_verts = nullptr;  // staging of the host-buffer refit call
     size_t refit_verts_bytes = 0;
@@ -107,10 +119,14 @@ struct Scene {
     // gated pipeline (single rays): one copy stream feeds launches that start before their input has arrived
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_start[kPipeStreams] = {}, ev_done[kPipeStreams] = {};
+    cudaEvent_t ev_refit = nullptr;          // scratch event: orders a scene refit against the pipeline streams
+    cudaEvent_t ev_refit_done = nullptr;     // end of the latest refit (refits share one scratch: they are chained)
     unsigned long long* d_ready = nullptr;   // kReadySlots watermarks (rays delivered per launch)
     unsigned long long* h_marks = nullptr;   // pinned source values of the watermark copies
 
     ~Scene() {
+        int prev_device = -1;
+        cudaGetDevice(&prev_device);
         cudaSetDevice(device);
         for (int i = 0; i < kPipeStreams; i++) {
             if (streams[i]) cudaStreamDestroy(streams[i]);
@@ -123,6 +139,8 @@ struct Scene {
             for (auto e : t.ev)
                 if (e) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_refit) cudaEventDestroy(ev_refit);
+        if (ev_refit_done) cudaEventDestroy(ev_refit_done);
         cudaFree(d_ready);
         if (h_marks) cudaFreeHost(h_marks);
         cudaFree(d_bvh_nodes);
@@ -132,9 +150,28 @@ struct Scene {
         if (d_idx_mbvh != d_idx_bvh) cudaFree(d_idx_mbvh);
         cudaFree(d_idx_bvh);
         cudaFree(d_refit_verts);
+        cudaFree(d_top);
+        cudaFree(d_top_count);
         cudaFree(d_overflow);
         cudaFree(d_counters);
+        if (prev_device >= 0 && prev_device != device) cudaSetDevice(prev_device);
     }
+};
+
+// Makes `device` current for the scope and restores the caller's device afterwards (the C ABI must not leave the
+// calling thread on another device).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    bool ok() const { return err == cudaSuccess; }
 };
 
 struct SceneTable {
@@ -148,6 +185,16 @@ std::shared_ptr<Scene> get_scene(RTGpuScene h) {
     return g_scenes.scenes[h - 1];
 }
 
+// Device-pointer entry points launch on the caller's stream, i.e. on the caller's current device: the scene must live there.
+bool on_scene_device(const Scene& s) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return cur == s.device;
+}
+
 const DeviceTree* pick_tree(const Scene& s, RTTreeKind kind) {
     const DeviceTree* t = kind == RT_TREE_MBVH ? &s.mbvh : (kind == RT_TREE_BVH ? &s.bvh : nullptr);
     if (!t || !t->nodes) return nullptr;
@@ -158,32 +205,106 @@ const DeviceTree* pick_tree(const Scene& s, RTTreeKind kind) {
 // chunk is slot_rays / 4 * 112 B < this).  want_rays > slot_rays: drain the pipeline and grow the slots.
 ResultCode ensure_pipeline(Scene& s, size_t want_rays = 0) {
     if (s.streams[0] && want_rays > s.slot_rays) {
-        for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s.streams[i]));
-        RTB_CUDA(cudaStreamSynchronize(s.copy_stream));
+        // grow: the new slots are allocated first and committed only when every allocation has succeeded, so a failed
+        // cudaMalloc leaves the old (smaller, still valid) pipeline in place
+        void* nin[kPipeStreams] = {};
+        void* nout[kPipeStreams] = {};
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < kPipeStreams && e == cudaSuccess; i++) {
+            e = cudaMalloc(&nin[i], want_rays * sizeof(RTRay));
+            if (e == cudaSuccess) e = cudaMalloc(&nout[i], want_rays * sizeof(RTHit));
+        }
+        if (e == cudaSuccess) {
+            for (int i = 0; i < kPipeStreams && e == cudaSuccess; i++) e = cudaStreamSynchronize(s.streams[i]);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s.copy_stream);
+        }
+        if (e != cudaSuccess) {
+            for (int i = 0; i < kPipeStreams; i++) {
+                cudaFree(nin[i]);
+                cudaFree(nout[i]);
+            }
+            return fail("host-buffer pipeline: growing the staging slots failed", e);
+        }
         for (int i = 0; i < kPipeStreams; i++) {
             cudaFree(s.d_in[i]);
             cudaFree(s.d_out[i]);
-            s.d_in[i] = s.d_out[i] = nullptr;
+            s.d_in[i] = nin[i];
+            s.d_out[i] = nout[i];
         }
         s.slot_rays = want_rays;
-        for (int i = 0; i < kPipeStreams; i++) {
-            RTB_CUDA(cudaMalloc(&s.d_in[i], s.slot_rays * sizeof(RTRay)));
-            RTB_CUDA(cudaMalloc(&s.d_out[i], s.slot_rays * sizeof(RTHit)));
-        }
         return Ok;
     }
     if (s.streams[0]) return Ok;
-    s.slot_rays = std::max(kChunkRays, want_rays);
-    for (int i = 0; i < kPipeStreams; i++) {
-        RTB_CUDA(cudaStreamCreateWithFlags(&s.streams[i], cudaStreamNonBlocking));
-        RTB_CUDA(cudaMalloc(&s.d_in[i], s.slot_rays * sizeof(RTRay)));
-        RTB_CUDA(cudaMalloc(&s.d_out[i], s.slot_rays * sizeof(RTHit)));
-        RTB_CUDA(cudaEventCreateWithFlags(&s.ev_start[i], cudaEventDisableTiming));
-        RTB_CUDA(cudaEventCreateWithFlags(&s.ev_done[i], cudaEventDisableTiming));
+    // first use: if anything fails the half-built pipeline is torn down again (streams[0] stays null: the next call retries)
+    const size_t rays = std::max(kChunkRays, want_rays);
+    auto teardown = [&]() {
+        for (int i = 0; i < kPipeStreams; i++) {
+            if (s.streams[i]) cudaStreamDestroy(s.streams[i]);
+            s.streams[i] = nullptr;
+            cudaFree(s.d_in[i]);
+            cudaFree(s.d_out[i]);
+            s.d_in[i] = s.d_out[i] = nullptr;
+            if (s.ev_start[i]) cudaEventDestroy(s.ev_start[i]);
+            if (s.ev_done[i]) cudaEventDestroy(s.ev_done[i]);
+            s.ev_start[i] = s.ev_done[i] = nullptr;
+        }
+        if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+        s.copy_stream = nullptr;
+        cudaFree(s.d_ready);
+        s.d_ready = nullptr;
+        if (s.h_marks) cudaFreeHost(s.h_marks);
+        s.h_marks = nullptr;
+        s.slot_rays = 0;
+    };
+    cudaError_t e = cudaSuccess;
+    cudaStream_t st[kPipeStreams] = {};
+    for (int i = 0; i < kPipeStreams && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_in[i], rays * sizeof(RTRay));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_out[i], rays * sizeof(RTHit));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.ev_start[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.ev_done[i], cudaEventDisableTiming);
     }
-    RTB_CUDA(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
-    RTB_CUDA(cudaMalloc(&s.d_ready, kReadySlots * sizeof(unsigned long long)));
-    RTB_CUDA(cudaHostAlloc(&s.h_marks, kMarkSlots * sizeof(unsigned long long), cudaHostAllocDefault));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&s.d_ready, kReadySlots * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaHostAlloc(&s.h_marks, kMarkSlots * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        for (int i = 0; i < kPipeStreams; i++) {
+            s.streams[i] = st[i];  // so that teardown destroys them
+        }
+        teardown();
+        return fail("host-buffer pipeline: set-up failed", e);
+    }
+    for (int i = 0; i < kPipeStreams; i++) s.streams[i] = st[i];  // committed last: streams[0] != null <=> pipeline complete
+    s.slot_rays = rays;
+    return Ok;
+}
+
+// slot capacity the gated flavour wants for a batch of `units` rays: every launch ends with a drain phase, so the fewer
+// launches per batch the better — the slots grow with the batch, up to 8 Mi rays
+size_t gated_slot_rays(size_t units) {
+    size_t want = kChunkRays;
+    while (want < units && want < kMaxSlotRays) want <<= 1;
+    return want;
+}
+
+// Builds (or, after a refit, refreshes) the staged-top table of the scene's Mbvh.  `read_count`: also fetch the slot count
+// (scene creation; a refit keeps the topology and with it the count).
+ResultCode scene_build_top(Scene& s, cudaStream_t st, bool read_count) {
+    const int cap = top_table_capacity();
+    if (cap == 0 || !s.d_mbvh_nodes || s.mbvh.node_count == 0) return Ok;
+    if (!s.d_top) {
+        RTB_CUDA(cudaMalloc((void**)&s.d_top, (size_t)cap * 128));
+        RTB_CUDA(cudaMalloc((void**)&s.d_top_count, sizeof(uint32_t)));
+    }
+    RTB_CUDA(launch_build_top_table((const float4*)s.d_mbvh_nodes, s.mbvh.node_count, s.d_top, s.d_top_count, st));
+    if (read_count) {
+        uint32_t cnt = 0;
+        RTB_CUDA(cudaMemcpyAsync(&cnt, s.d_top_count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        RTB_CUDA(cudaStreamSynchronize(st));
+        s.mbvh.top = s.d_top;
+        s.mbvh.top_count = cnt;
+    }
     return Ok;
 }
 
@@ -211,7 +332,7 @@ ResultCode check_overflow(Scene& s) {
     RTB_CUDA(cudaMemcpy(&ovf, s.d_overflow, sizeof(ovf), cudaMemcpyDeviceToHost));
     if (ovf) {
         RTB_CUDA(cudaMemset(s.d_overflow, 0, sizeof(uint32_t)));
-        return fail("traversal stack overflow (> 64 entries)");
+        return fail("traversal stack overflow (> 128 entries)");
     }
     return Ok;
 }
@@ -318,48 +439,41 @@ ResultCode enqueue_host_batch_gated(Scene& s, const void* in, size_t n, size_t u
             if (m > left || left - m < kMinChunkRays / 2) m = std::min(left, s.slot_rays);
         }
         unsigned long long* ready = s.d_ready + (seq % kReadySlots);
+        if (!s.d_in[k] || !s.d_out[k]) return fail("host-buffer pipeline: staging slot missing");
         // the staging slot (and the watermark slot, at most kPipeStreams launches are in flight) is free once everything
         // enqueued on streams[k] so far — the launch that used the slot and its D2H — has finished
         RTB_CUDA(cudaEventRecord(s.ev_done[k], s.streams[k]));
         RTB_CUDA(cudaStreamWaitEvent(cp, s.ev_done[k], 0));
         RTB_CUDA(cudaMemsetAsync(ready, 0, sizeof(unsigned long long), cp));
         RTB_CUDA(cudaEventRecord(s.ev_start[k], cp));
+        // ORDER MATTERS: every upload and watermark write of this launch is queued on the copy stream BEFORE the kernel is
+        // launched.  The kernel still starts (on streams[k], behind ev_start only) before its input has arrived, but nothing
+        // it waits for is host-ordered behind the launch call — so the call also returns when launches are synchronous
+        // (ncu, compute-sanitizer, CUDA_LAUNCH_BLOCKING=1), where a launch-then-feed order never gets to feed.
+        // If feeding fails (e.g. a bad host pointer) no launch is waiting yet: report the error, nothing spins.
+        for (size_t off = 0; off < m; off += sub_rays) {
+            const size_t sub = std::min(sub_rays, m - off);
+            RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + off * unit_in, (const char*)in + (done + off) * unit_in, sub * unit_in,
+                                     cudaMemcpyHostToDevice, cp));
+            if (in2)
+                RTB_CUDA(cudaMemcpyAsync((char*)s.d_in[k] + s.slot_rays * 12 + off * unit_in, (const char*)in2 + (done + off) * unit_in,
+                                         sub * unit_in, cudaMemcpyHostToDevice, cp));
+            if (write_value) {  // stream memory operation: no DMA set-up, ordered behind the copies like any stream work
+                if (write_value(cp, (unsigned long long)(uintptr_t)ready, off + sub, 0) != 0)
+                    return fail("host-buffer pipeline: cuStreamWriteValue64 failed");
+            } else {
+                if (s.marks_used == kMarkSlots) {  // the pinned source values of in-flight watermark copies must stay intact
+                    RTB_CUDA(cudaStreamSynchronize(cp));
+                    s.marks_used = 0;
+                }
+                s.h_marks[s.marks_used] = off + sub;
+                RTB_CUDA(cudaMemcpyAsync(ready, &s.h_marks[s.marks_used], sizeof(unsigned long long), cudaMemcpyHostToDevice, cp));
+                s.marks_used++;
+            }
+        }
         RTB_CUDA(cudaStreamWaitEvent(s.streams[k], s.ev_start[k], 0));
         RTB_CUDA(launch(s.d_in[k], m, s.d_out[k], (const unsigned long long*)ready, s.streams[k]));
-        // From here on a launch is waiting for its input: if feeding it fails (e.g. a bad host pointer), open the gate
-        // completely before reporting the error — the launch then runs over whatever the slot holds and ends, instead of
-        // spinning on the watermark for ever.
-        auto feed = [&]() -> cudaError_t {
-            for (size_t off = 0; off < m; off += sub_rays) {
-                const size_t sub = std::min(sub_rays, m - off);
-                cudaError_t e = cudaMemcpyAsync((char*)s.d_in[k] + off * unit_in, (const char*)in + (done + off) * unit_in,
-                                                sub * unit_in, cudaMemcpyHostToDevice, cp);
-                if (e == cudaSuccess && in2)
-                    e = cudaMemcpyAsync((char*)s.d_in[k] + s.slot_rays * 12 + off * unit_in, (const char*)in2 + (done + off) * unit_in,
-                                        sub * unit_in, cudaMemcpyHostToDevice, cp);
-                if (e != cudaSuccess) return e;
-                if (write_value) {  // stream memory operation: no DMA set-up, ordered behind the copies like any stream work
-                    if (write_value(cp, (unsigned long long)(uintptr_t)ready, off + sub, 0) != 0) return cudaErrorUnknown;
-                } else {
-                    if (s.marks_used == kMarkSlots) {  // the pinned source values of in-flight watermark copies must stay intact
-                        if ((e = cudaStreamSynchronize(cp)) != cudaSuccess) return e;
-                        s.marks_used = 0;
-                    }
-                    s.h_marks[s.marks_used] = off + sub;
-                    e = cudaMemcpyAsync(ready, &s.h_marks[s.marks_used], sizeof(unsigned long long), cudaMemcpyHostToDevice, cp);
-                    if (e != cudaSuccess) return e;
-                    s.marks_used++;
-                }
-            }
-            return cudaSuccess;
-        };
-        const cudaError_t fed = feed();
-        if (fed != cudaSuccess) {
-            cudaGetLastError();
-            cudaMemsetAsync(ready, 0xFF, sizeof(unsigned long long), cp);  // watermark = 2^64 - 1
-            return fail("host-buffer pipeline: feeding a gated launch failed", fed);
-        }
-        // enqueued after the uploads: with a pageable `out` this call blocks until the launch has finished
+        // with a pageable `out` this call blocks until the launch has finished
         RTB_CUDA(cudaMemcpyAsync((char*)out + done * unit_out, s.d_out[k], m * unit_out, cudaMemcpyDeviceToHost, s.streams[k]));
         done += m;
     }
@@ -373,12 +487,23 @@ ResultCode enqueue_any(Scene& s, const void* in, size_t units, size_t unit_in, s
                        Launch&& launch, const void* in2, size_t unit_in2, bool gate_ok, bool blocking) {
     const int mode = host_mode();
     const bool gated = mode != kHostStaged;
-    if (gate_ok && gated && (in2 == nullptr || unit_in2 == unit_in)) {
+    // The gated flavour queues all uploads of a launch before the launch itself (see there); cudaMemcpyAsync from PAGEABLE
+    // memory returns only once the source has been staged, which would serialise upload and traversal — pageable inputs
+    // therefore take the staged flavour (chunk i traces while chunk i+1 is staged).  RTBVH_HOST_MODE=gated forces gated.
+    auto pinned = [](const void* p) {
+        if (!p) return true;
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+    };
+    const bool overlap_ok = mode == kHostGated || (pinned(in) && pinned(in2));
+    if (gate_ok && gated && overlap_ok && (in2 == nullptr || unit_in2 == unit_in)) {
         // every launch ends with a drain phase (its warps can no longer refill; the longest rays of a launch alone take
         // ~0.25 ms): the fewer launches per batch the better, so the slots grow with the batch (up to 8 Mi rays)
-        size_t want = kChunkRays;
-        while (want < units && want < kMaxSlotRays) want <<= 1;
-        if (ensure_pipeline(s, want) != Ok) return Error;
+        if (ensure_pipeline(s, gated_slot_rays(units)) != Ok) return Error;
         return enqueue_host_batch_gated(s, in, units, unit_in, unit_out, out, blocking, launch, in2);
     }
     return enqueue_host_batch(s, in, units, unit_in, unit_out, rays_per_unit, out, launch, in2, unit_in2);
@@ -391,8 +516,9 @@ ResultCode run_host_batch(Scene& s, const void* in, size_t units, size_t unit_in
     if (units == 0) return Ok;
     if (!in || !out) return fail("null host buffer");
     std::lock_guard<std::mutex> lk(s.pipe_mutex);
-    RTB_CUDA(cudaSetDevice(s.device));
-    if (ensure_pipeline(s) != Ok) return Error;
+    DeviceGuard dg(s.device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
+    if (ensure_pipeline(s, gate_ok ? gated_slot_rays(units) : 0) != Ok) return Error;
     if (enqueue_any(s, in, units, unit_in, unit_out, rays_per_unit, out, launch, in2, unit_in2, gate_ok, true) != Ok) return Error;
     RTB_CUDA(cudaStreamSynchronize(s.copy_stream));
     for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s.streams[i]));
@@ -409,8 +535,9 @@ ResultCode submit_host_batch(Scene& s, const void* in, size_t units, size_t unit
     if (!ticket) return fail("null ticket");
     if (units != 0 && (!in || !out)) return fail("null host buffer");
     std::unique_lock<std::mutex> lk(s.pipe_mutex);
-    RTB_CUDA(cudaSetDevice(s.device));
-    if (ensure_pipeline(s) != Ok) return Error;
+    DeviceGuard dg(s.device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
+    if (ensure_pipeline(s, gate_ok ? gated_slot_rays(units) : 0) != Ok) return Error;
     const uint64_t id = s.next_ticket++;
     Scene::Ticket& t = s.tickets[id % kTickets];
     if (t.id != 0) {  // the ring wrapped onto a ticket nobody waited for: it must have completed before its events are reused
@@ -428,7 +555,8 @@ ResultCode submit_host_batch(Scene& s, const void* in, size_t units, size_t unit
 }
 
 ResultCode wait_ticket(Scene& s, uint64_t ticket) {
-    RTB_CUDA(cudaSetDevice(s.device));
+    DeviceGuard dg(s.device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
     cudaEvent_t ev[kPipeStreams] = {};
     {
         std::lock_guard<std::mutex> lk(s.pipe_mutex);
@@ -503,7 +631,7 @@ ResultCode rtbvh_gpu_scene_create(const RTBvh* bvh, const RTMbvh* mbvh, const fl
     if (bvh) {
         rc = upload(&s->d_bvh_nodes, bvh->nodes, (size_t)bvh->node_count * sizeof(RTBvhNode));
         if (rc == Ok) rc = gather(bvh->indices, bvh->index_count, &s->d_tris_bvh, &s->d_idx_bvh);
-        s->bvh = DeviceTree{(const float4*)s->d_bvh_nodes, bvh->node_count, s->d_tris_bvh, bvh->index_count};
+        s->bvh = DeviceTree{(const float4*)s->d_bvh_nodes, bvh->node_count, s->d_tris_bvh, bvh->index_count, nullptr, 0};
     }
     if (rc == Ok && mbvh) {
         rc = upload(&s->d_mbvh_nodes, mbvh->nodes, (size_t)mbvh->node_count * sizeof(RTMbvhNode));
@@ -518,10 +646,11 @@ ResultCode rtbvh_gpu_scene_create(const RTBvh* bvh, const RTMbvh* mbvh, const fl
                 rc = gather(mbvh->indices, mbvh->index_count, &s->d_tris_mbvh, &s->d_idx_mbvh);
             }
         }
-        s->mbvh = DeviceTree{(const float4*)s->d_mbvh_nodes, mbvh->node_count, s->d_tris_mbvh, mbvh->index_count};
+        s->mbvh = DeviceTree{(const float4*)s->d_mbvh_nodes, mbvh->node_count, s->d_tris_mbvh, mbvh->index_count, nullptr, 0};
     }
     cudaFree(d_verts);
     if (rc != Ok) return rc;
+    if (mbvh && scene_build_top(*s, 0, true) != Ok) return Error;
     if (bvh && bvh->node_count) {
         const RTAabb& r = bvh->nodes[0].aabb;
         for (int k = 0; k < 3; k++) {
@@ -570,10 +699,11 @@ static ResultCode scene_build_common(const float* vertices, bool on_device, size
     RTB_CUDA(cudaMalloc((void**)&s->d_tris_bvh, (size_t)rt.index_count * sizeof(TriRec)));
     RTB_CUDA(launch_gather_tris(d_verts, (uint32_t)(vertex_stride / 4), rt.d_indices, rt.index_count, (uint32_t)triangle_count,
                                 s->d_tris_bvh, 0));
-    s->bvh = DeviceTree{(const float4*)s->d_bvh_nodes, rt.node_count, s->d_tris_bvh, rt.index_count};
+    s->bvh = DeviceTree{(const float4*)s->d_bvh_nodes, rt.node_count, s->d_tris_bvh, rt.index_count, nullptr, 0};
     if (rt.d_mnodes) {
         s->d_tris_mbvh = s->d_tris_bvh;
-        s->mbvh = DeviceTree{(const float4*)s->d_mbvh_nodes, rt.m_count, s->d_tris_mbvh, rt.index_count};
+        s->mbvh = DeviceTree{(const float4*)s->d_mbvh_nodes, rt.m_count, s->d_tris_mbvh, rt.index_count, nullptr, 0};
+        if (scene_build_top(*s, 0, true) != Ok) return Error;
     }
     float4 root[2];
     RTB_CUDA(cudaMemcpy(root, s->d_bvh_nodes, 32, cudaMemcpyDeviceToHost));  // also drains the gather
@@ -608,7 +738,8 @@ ResultCode rtbvh_gpu_scene_read_indices(RTGpuScene h, RTTreeKind tree, uint32_t*
     const uint32_t* d = tree == RT_TREE_MBVH ? s->d_idx_mbvh : s->d_idx_bvh;
     if (!t || !d) return fail("scene has no such tree");
     if (count != t->index_count) return fail("rtbvh_gpu_scene_read_indices: count must equal the tree's index_count");
-    RTB_CUDA(cudaSetDevice(s->device));
+    DeviceGuard dg(s->device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
     RTB_CUDA(cudaMemcpy(out, d, count * 4, cudaMemcpyDeviceToHost));
     return Ok;
 }
@@ -626,6 +757,30 @@ static ResultCode scene_refit_on(Scene& s, const float* d_vertices, size_t verte
                            d_vertices, vs, s.tri_count, (float4*)s.d_mbvh_nodes, (uint32_t)s.mbvh.node_count, st) != Ok)
         return Error;
     RTB_CUDA(launch_gather_tris(d_vertices, vs, s.d_idx_bvh, (uint32_t)s.bvh.index_count, s.tri_count, s.d_tris_bvh, st));
+    return scene_build_top(s, st, false);  // the slot boxes of the staged top follow the refitted Mbvh
+}
+// Ordering of a refit against the scene's own work (the caller holds refit_mutex and pipe_mutex):
+//  * before: the refit stream waits for everything queued so far on the host-buffer pipeline streams (those batches still
+//    read the old nodes and records) and for the previous refit (all refits of a scene share one scratch area);
+//  * after: the pipeline streams wait for the refit, so host-buffer batches submitted later see the refitted trees.
+// Device-resident traversal calls on the CALLER's streams are ordered by the caller (same stream, or events), as for any
+// stream-ordered API; rtbvh_gpu.h says so.
+static ResultCode refit_order_begin(Scene& s, cudaStream_t st) {
+    if (!s.ev_refit) RTB_CUDA(cudaEventCreateWithFlags(&s.ev_refit, cudaEventDisableTiming));
+    if (s.streams[0]) {
+        for (int i = 0; i < kPipeStreams; i++) {
+            RTB_CUDA(cudaEventRecord(s.ev_refit, s.streams[i]));
+            RTB_CUDA(cudaStreamWaitEvent(st, s.ev_refit, 0));
+        }
+    }
+    if (s.ev_refit_done) RTB_CUDA(cudaStreamWaitEvent(st, s.ev_refit_done, 0));
+    return Ok;
+}
+static ResultCode refit_order_end(Scene& s, cudaStream_t st) {
+    if (!s.ev_refit_done) RTB_CUDA(cudaEventCreateWithFlags(&s.ev_refit_done, cudaEventDisableTiming));
+    RTB_CUDA(cudaEventRecord(s.ev_refit_done, st));
+    if (s.streams[0])
+        for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamWaitEvent(s.streams[i], s.ev_refit_done, 0));
     return Ok;
 }
 ResultCode rtbvh_gpu_scene_refit_device(RTGpuScene h, const float* d_vertices, size_t vertex_stride, size_t triangle_count,
@@ -633,25 +788,42 @@ ResultCode rtbvh_gpu_scene_refit_device(RTGpuScene h, const float* d_vertices, s
     auto s = get_scene(h);
     if (!s || !d_vertices) return fail("unknown scene / null vertices");
     std::lock_guard<std::mutex> lk(s->refit_mutex);
-    RTB_CUDA(cudaSetDevice(s->device));
-    return scene_refit_on(*s, d_vertices, vertex_stride, triangle_count, (cudaStream_t)stream);
+    std::lock_guard<std::mutex> lp(s->pipe_mutex);
+    DeviceGuard dg(s->device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
+    if (refit_order_begin(*s, (cudaStream_t)stream) != Ok) return Error;
+    const ResultCode rc = scene_refit_on(*s, d_vertices, vertex_stride, triangle_count, (cudaStream_t)stream);
+    if (refit_order_end(*s, (cudaStream_t)stream) != Ok) return Error;  // also after a failed enqueue: whatever was queued is chained
+    return rc;
 }
 ResultCode rtbvh_gpu_scene_refit(RTGpuScene h, const float* vertices, size_t vertex_stride, size_t triangle_count) {
     auto s = get_scene(h);
     if (!s || !vertices) return fail("unknown scene / null vertices");
     std::lock_guard<std::mutex> lk(s->refit_mutex);
-    RTB_CUDA(cudaSetDevice(s->device));
+    std::lock_guard<std::mutex> lp(s->pipe_mutex);
+    DeviceGuard dg(s->device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
+    // blocking flavour: drain the scene's pipeline (outstanding *_async batches still traverse the old trees), refit on
+    // the legacy stream, wait for it
+    if (s->streams[0]) {
+        for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaStreamSynchronize(s->streams[i]));
+        RTB_CUDA(cudaStreamSynchronize(s->copy_stream));
+    }
     const size_t bytes = triangle_count * 3 * vertex_stride;
     if (bytes > s->refit_verts_bytes) {
+        RTB_CUDA(cudaDeviceSynchronize());  // an earlier refit_device may still read the old staging buffer
         cudaFree(s->d_refit_verts);
         s->d_refit_verts = nullptr;
         s->refit_verts_bytes = 0;
         RTB_CUDA(cudaMalloc(&s->d_refit_verts, bytes ? bytes : 16));
         s->refit_verts_bytes = bytes;
     }
-    RTB_CUDA(cudaMemcpy(s->d_refit_verts, vertices, bytes, cudaMemcpyHostToDevice));
-    if (scene_refit_on(*s, s->d_refit_verts, vertex_stride, triangle_count, 0) != Ok) return Error;
-    RTB_CUDA(cudaDeviceSynchronize());
+    if (refit_order_begin(*s, 0) != Ok) return Error;
+    RTB_CUDA(cudaMemcpyAsync(s->d_refit_verts, vertices, bytes, cudaMemcpyHostToDevice, 0));
+    const ResultCode rc = scene_refit_on(*s, s->d_refit_verts, vertex_stride, triangle_count, 0);
+    if (refit_order_end(*s, 0) != Ok) return Error;
+    if (rc != Ok) return rc;
+    RTB_CUDA(cudaStreamSynchronize(0));
     float4 root[2];  // the keys of the optional ray sort follow the new root box
     RTB_CUDA(cudaMemcpy(root, s->d_bvh_nodes, 32, cudaMemcpyDeviceToHost));
     s->bounds[0] = root[0].x; s->bounds[1] = root[0].y; s->bounds[2] = root[0].z;
@@ -665,7 +837,8 @@ ResultCode rtbvh_gpu_scene_read_nodes(RTGpuScene h, RTTreeKind tree, void* out, 
     if (!t) return fail("scene has no such tree");
     const size_t have = (size_t)t->node_count * (tree == RT_TREE_MBVH ? sizeof(RTMbvhNode) : sizeof(RTBvhNode));
     if (bytes != have) return fail("rtbvh_gpu_scene_read_nodes: buffer size must be node_count * sizeof(node)");
-    RTB_CUDA(cudaSetDevice(s->device));
+    DeviceGuard dg(s->device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
     RTB_CUDA(cudaDeviceSynchronize());
     RTB_CUDA(cudaMemcpy(out, t->nodes, bytes, cudaMemcpyDeviceToHost));
     return Ok;
@@ -703,6 +876,7 @@ ResultCode rtbvh_gpu_intersect_device(RTGpuScene h, RTTreeKind tree, const RTRay
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
+    if (!on_scene_device(*s)) return fail("the scene lives on another device than the current one (cudaSetDevice / rtbvh_gpu_set_device first)");
     RTB_CUDA(launch_trace_single(*t, tree, false, d_rays, n, d_hits, nullptr, s->counter_slot(), s->d_overflow,
                                  persistent_mode(), s->sort_bounds(), nullptr, (cudaStream_t)stream));
     return Ok;
@@ -713,6 +887,7 @@ ResultCode rtbvh_gpu_occluded_device(RTGpuScene h, RTTreeKind tree, const RTRay*
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
+    if (!on_scene_device(*s)) return fail("the scene lives on another device than the current one (cudaSetDevice / rtbvh_gpu_set_device first)");
     RTB_CUDA(launch_trace_single(*t, tree, true, d_rays, n, nullptr, d_occ, s->counter_slot(), s->d_overflow,
                                  persistent_mode(), s->sort_bounds(), nullptr, (cudaStream_t)stream));
     return Ok;
@@ -723,6 +898,7 @@ ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene h, RTTreeKind tree, con
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
+    if (!on_scene_device(*s)) return fail("the scene lives on another device than the current one (cudaSetDevice / rtbvh_gpu_set_device first)");
     RTB_CUDA(launch_trace_packets(*t, tree, false, d_packets, n, t_min, d_hits, nullptr, s->counter_slot(), s->d_overflow,
                                   packet_mode(), (cudaStream_t)stream));
     return Ok;
@@ -733,6 +909,7 @@ ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene h, RTTreeKind tree, cons
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
+    if (!on_scene_device(*s)) return fail("the scene lives on another device than the current one (cudaSetDevice / rtbvh_gpu_set_device first)");
     RTB_CUDA(launch_trace_packets(*t, tree, true, d_packets, n, t_min, nullptr, d_occ, s->counter_slot(), s->d_overflow,
                                   packet_mode(), (cudaStream_t)stream));
     return Ok;
@@ -744,13 +921,14 @@ static ResultCode scatter_call(RTGpuScene h, RTTreeKind tree, bool any, const RT
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
+    if (!on_scene_device(*s)) return fail("the scene lives on another device than the current one (cudaSetDevice / rtbvh_gpu_set_device first)");
     if (dest_count < 0 || dest_count > 8 || (dest_count > 0 && !dests)) return fail("0..8 destinations");
     PeerDests pd{};
     for (int k = 0; k < dest_count; k++) pd.p[k] = dests[k];
     pd.count = dest_count;
     pd.offset = dest_offset;
     RTB_CUDA(launch_trace_single(*t, tree, any, d_rays, n, any ? nullptr : (RTHit*)d_local, any ? (uint8_t*)d_local : nullptr,
-                                 s->counter_slot(), s->d_overflow, kTracePersistent, s->sort_bounds(), &pd, (cudaStream_t)stream));
+                                 s->counter_slot(), s->d_overflow, refill_mode(), s->sort_bounds(), &pd, (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_intersect_device_scatter(RTGpuScene h, RTTreeKind tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
@@ -821,7 +999,8 @@ ResultCode rtbvh_gpu_peer_buffer_free(void* d_ptr) {
 ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene h, uint32_t* overflowed) {
     auto s = get_scene(h);
     if (!s || !overflowed) return fail("unknown scene");
-    RTB_CUDA(cudaSetDevice(s->device));
+    DeviceGuard dg(s->device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
     RTB_CUDA(cudaDeviceSynchronize());
     RTB_CUDA(cudaMemcpy(overflowed, s->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     RTB_CUDA(cudaMemset(s->d_overflow, 0, sizeof(uint32_t)));
@@ -836,12 +1015,12 @@ static ResultCode rtray_host_call(RTGpuScene h, RTTreeKind tree, bool any, const
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
-    const bool gate_ok = !s->sort_bounds() && persistent_mode() == kTracePersistent;
+    const bool gate_ok = !s->sort_bounds() && persistent_mode() == refill_mode();
     auto launch = [&](void* din, size_t m, void* dout, const unsigned long long* ready, cudaStream_t st) {
         PeerDests pd{};
         pd.ready = ready;
         return launch_trace_single(*t, tree, any, (const RTRay*)din, m, any ? nullptr : (RTHit*)dout, any ? (uint8_t*)dout : nullptr,
-                                   s->counter_slot(), s->d_overflow, ready ? (int)kTracePersistent : persistent_mode(),
+                                   s->counter_slot(), s->d_overflow, ready ? refill_mode() : persistent_mode(),
                                    ready ? nullptr : s->sort_bounds(), ready ? &pd : nullptr, st);
     };
     const size_t unit_out = any ? 1 : sizeof(RTHit);
@@ -871,7 +1050,7 @@ static cudaError_t launch_od(Scene& s, const DeviceTree& t, RTTreeKind tree, boo
     pd.t_min = t_min;
     pd.t_max = t_max;
     return launch_trace_single(t, tree, any, reinterpret_cast<const RTRay*>(d_origins), m, any ? nullptr : (RTHit*)d_out,
-                               any ? (uint8_t*)d_out : nullptr, s.counter_slot(), s.d_overflow, kTracePersistent, nullptr, &pd, st);
+                               any ? (uint8_t*)d_out : nullptr, s.counter_slot(), s.d_overflow, refill_mode(), nullptr, &pd, st);
 }
 static ResultCode od_host_call(RTGpuScene h, RTTreeKind tree, bool any, const float* origins, const float* directions, size_t n,
                                float t_min, float t_max, void* out, uint64_t* ticket) {
@@ -912,6 +1091,7 @@ ResultCode rtbvh_gpu_intersect_od_device(RTGpuScene h, RTTreeKind tree, const fl
     if (!s) return fail("unknown scene");
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
+    if (!on_scene_device(*s)) return fail("the scene lives on another device than the current one (cudaSetDevice / rtbvh_gpu_set_device first)");
     if (n != 0 && (!d_origins || !d_directions || !d_hits)) return fail("null device buffer");
     RTB_CUDA(launch_od(*s, *t, tree, false, d_origins, d_directions, n, t_min, t_max, d_hits, nullptr, (cudaStream_t)stream));
     return Ok;

@@ -73,7 +73,12 @@ struct DeviceTree {
     uint32_t node_count;
     const TriRec* tris;       // index_count records (leaf order: tris[k] = triangle indices[k])
     uint32_t index_count;
+    // Mbvh only, optional: copies of the top `top_count` nodes in breadth-first order whose child fields address other
+    // copies as (slot | kTopFlag); the persistent kernel stages them in shared memory (traverse.cu, RTB_TOPK)
+    const float4* top;
+    uint32_t top_count;
 };
+constexpr int kTopFlag = 1 << 30;
 
 inline __host__ __device__ size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
 

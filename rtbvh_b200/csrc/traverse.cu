@@ -37,6 +37,16 @@ constexpr int kSpillStack = 128 - kSmemStack;     // further entries spill to th
 #define RTB_BLOCK 128
 #endif
 constexpr int kBlock = RTB_BLOCK;
+#ifndef RTB_PBLOCK
+#define RTB_PBLOCK RTB_BLOCK
+#endif
+constexpr int kPBlock = RTB_PBLOCK;  // threads per block of the persistent single-ray kernel
+#ifndef RTB_TOPK
+#define RTB_TOPK 0
+#endif
+constexpr int kTopK = RTB_TOPK;      // Mbvh nodes staged in shared memory by the persistent single-ray kernel (0: none)
+constexpr int kTopRow = 9;           // float4 per staged node: 128 B + 16 B padding (rows 144 B apart: LDS.128 of lanes on
+                                     // different rows spreads over all banks)
 #ifndef RTB_REFILL
 #define RTB_REFILL 8
 #endif
@@ -214,13 +224,14 @@ __device__ __forceinline__ int sel4(const int4 v, int s) { return s == 0 ? v.x :
     }
 
 struct Stack {
-    int* base;     // &smem[threadIdx.x]; entry e < kSmemStack at base[e * kBlock]
+    int* base;     // &smem[threadIdx.x]; entry e < kSmemStack at base[e * stride]
     int* spill;    // thread-local array; entry e >= kSmemStack at spill[e - kSmemStack]
     int sp;
     uint32_t* overflow;
+    int stride;    // threads per block
     __device__ __forceinline__ void push(int v) {
         if (sp < kSmemStack) {
-            base[sp * kBlock] = v;
+            base[sp * stride] = v;
             sp++;
         } else if (sp < kSmemStack + kSpillStack) {
             spill[sp - kSmemStack] = v;
@@ -231,7 +242,7 @@ struct Stack {
     }
     __device__ __forceinline__ int pop() {
         --sp;
-        return sp < kSmemStack ? base[sp * kBlock] : spill[sp - kSmemStack];
+        return sp < kSmemStack ? base[sp * stride] : spill[sp - kSmemStack];
     }
     __device__ __forceinline__ void reset() { sp = 0; }
 };
@@ -284,11 +295,11 @@ __device__ __forceinline__ int mbvh_visit_push(const MNode& nd, const RayRegs& r
         const int next = pay[0] >= 0 ? pay[0] : (pay[1] >= 0 ? pay[1] : (pay[2] >= 0 ? pay[2] : pay[3]));
         const int skip = pay[0] >= 0 ? 0 : (pay[1] >= 0 ? 1 : (pay[2] >= 0 ? 2 : 3));
         if (st.sp + 3 <= kSmemStack) {  // fast path: compact predicated stores
-            int* b = st.base + st.sp * kBlock;
+            int* b = st.base + st.sp * st.stride;
             int c = 0;
-            if (skip < 3 && pay[3] >= 0) { b[c * kBlock] = pay[3]; c++; }
-            if (skip < 2 && pay[2] >= 0) { b[c * kBlock] = pay[2]; c++; }
-            if (skip < 1 && pay[1] >= 0) { b[c * kBlock] = pay[1]; c++; }
+            if (skip < 3 && pay[3] >= 0) { b[c * st.stride] = pay[3]; c++; }
+            if (skip < 2 && pay[2] >= 0) { b[c * st.stride] = pay[2]; c++; }
+            if (skip < 1 && pay[1] >= 0) { b[c * st.stride] = pay[1]; c++; }
             st.sp += c;
         } else {
             if (skip < 3 && pay[3] >= 0) st.push(pay[3]);
@@ -475,6 +486,205 @@ __device__ __forceinline__ bool packet_step(const DeviceTree& tree, RayRegs& r, 
     return bvh_packet_step<ANY>(tree, r, st, cur, retired, qm);
 }
 
+
+// ================================================================================================
+// Phase-split stepping (the default single-ray kernel).  ncu of the one-step-per-iteration kernel
+// (profiles/r2g_*): 14.7 of 32 lanes active per issued instruction, because every iteration ran
+// "node visit, then the triangles of its hit leaf slots" and ~20 % of the lanes had triangles —
+// the other ~80 % idled through one or more ~80-instruction triangle tests per visit.
+// Here a lane is in one of two phases — N: it holds a node to visit; T: it holds a leaf range with
+// triangles left — and the WARP picks per iteration the phase most of its lanes are in; the lanes
+// of the other phase wait one iteration.  A lane never visits a node while it still has triangles
+// pending: the reference shrinks ray.t with the candidates of a node before it pops the next node
+// (iter_indices.rs:292-309), and with its non-conservative boxes the set of visited
+// nodes — hence the result — depends on that, so the order per ray stays the reference's; only the
+// interleaving BETWEEN rays changes.
+// Leaf ranges found at a node beyond the first are parked on the traversal stack, above the inner
+// entries pushed at the same node (tagged by the sign bit), and `pend` counts them.
+// ================================================================================================
+#ifndef RTB_TRI_NUM
+#define RTB_TRI_NUM 1  // tri phase is chosen when lanes_T * RTB_TRI_NUM >= lanes_N * RTB_TRI_DEN
+#endif
+#ifndef RTB_TRI_DEN
+#define RTB_TRI_DEN 1
+#endif
+struct Lane {
+    int cur;               // node to visit next (-1: none in hand: pop)
+    int tri_pos, tri_end;  // leaf range in the leaf-ordered triangle records; T phase while tri_pos < tri_end
+    int pend;              // leaf ranges parked on the stack
+};
+constexpr int kLeafTag = (int)0x80000000u;
+// one word when count < 32 and first < 2^26, else three (escape word on top)
+__device__ __forceinline__ void push_leaf(Stack& st, int first, int count) {
+    if (count < 32 && first < (1 << 26)) {
+        st.push(kLeafTag | (count << 26) | first);
+    } else {
+        st.push(count);
+        st.push(first);
+        st.push(kLeafTag);
+    }
+}
+__device__ __forceinline__ void pop_leaf(Stack& st, int& first, int& end) {
+    const int v = st.pop();
+    int f, c;
+    if ((v & 0x7FFFFFFF) != 0) {
+        c = (v >> 26) & 31;
+        f = v & ((1 << 26) - 1);
+    } else {
+        f = st.pop();
+        c = st.pop();
+    }
+    first = f;
+    end = f + c;
+}
+// Called when the lane's current range is used up: next parked range, else the next node; true = ray finished.
+__device__ __forceinline__ bool lane_advance(Stack& st, Lane& L) {
+    if (L.pend > 0) {
+        pop_leaf(st, L.tri_pos, L.tri_end);
+        L.pend--;
+        return false;
+    }
+    if (L.cur < 0) {
+        if (st.sp == 0) return true;
+        L.cur = st.pop();
+    }
+    return false;
+}
+__device__ __forceinline__ void lane_take_leaf(Stack& st, Lane& L, int first, int count) {
+    if (count <= 0) return;
+    if (L.tri_pos >= L.tri_end) {
+        L.tri_pos = first;
+        L.tri_end = first + count;
+    } else {
+        push_leaf(st, first, count);
+        L.pend++;
+    }
+}
+
+// SpatialTriangle::intersect without early exits (same operations, same predicates, evaluated in full): in a T-phase
+// step nearly all lanes hold a triangle, so some lane needs every instruction anyway and branches only add
+// divergence bookkeeping.  Returns true when the candidate was accepted with t < ray.t.
+__device__ __forceinline__ bool tri_candidate_flat(const TriRec* __restrict__ tris, int pos, RayRegs& r) {
+    const F8 ab = ld256(&tris[pos].a);
+    const float4 A = ab.lo, E1 = ab.hi;
+    const float4 E2 = __ldg(&tris[pos].c);
+    const float hx = fsub(fmul(r.dy, E2.z), fmul(E2.y, r.dz));
+    const float hy = fsub(fmul(r.dz, E2.x), fmul(E2.z, r.dx));
+    const float hz = fsub(fmul(r.dx, E2.y), fmul(E2.x, r.dy));
+    const float a = fadd(fadd(fmul(E1.x, hx), fmul(E1.y, hy)), fmul(E1.z, hz));
+    const bool p_par = (a > -1e-5f && a < 1e-5f);  // spatial_sah.rs:140-142
+    const float f = fdiv(1.0f, a);
+    const float sx = fsub(r.ox, A.x), sy = fsub(r.oy, A.y), sz = fsub(r.oz, A.z);
+    const float u = fmul(f, fadd(fadd(fmul(sx, hx), fmul(sy, hy)), fmul(sz, hz)));
+    const bool p_u = (u >= 0.0f && u <= 1.0f);
+    const float qx = fsub(fmul(sy, E1.z), fmul(E1.y, sz));
+    const float qy = fsub(fmul(sz, E1.x), fmul(E1.z, sx));
+    const float qz = fsub(fmul(sx, E1.y), fmul(E1.x, sy));
+    const float v = fmul(f, fadd(fadd(fmul(r.dx, qx), fmul(r.dy, qy)), fmul(r.dz, qz)));
+    const bool p_v = !(v < 0.0f || fadd(u, v) > 1.0f);  // spatial_sah.rs:150-152
+    const float t = fmul(f, fadd(fadd(fmul(E2.x, qx), fmul(E2.y, qy)), fmul(E2.z, qz)));
+    const bool ok = !p_par && p_u && p_v && (t > r.t_min);
+    const uint32_t id = __float_as_uint(A.w);
+    const bool closer = ok && t < r.t;
+    const bool tie = ok && r.prim != kNoHit && t == r.t && id < r.prim;
+    if (closer) r.t = t;
+    if (closer || tie) r.prim = id;
+    return closer;
+}
+
+// N phase, Mbvh: MbvhNode::intersect at node entry; inner slots pushed in the reference's order with the entry that
+// would be popped next kept in L.cur; hit leaf slots become leaf ranges.
+__device__ __forceinline__ MNode mnode_load_shared(const float4* __restrict__ top_s, int slot) {
+    const float4* n = top_s + slot * kTopRow;
+    return MNode{n[0], n[1], n[2], n[3], n[4], n[5], as_int4(n[6]), as_int4(n[7])};
+}
+template <bool EXACT>
+__device__ __forceinline__ void mbvh_node_phase(const DeviceTree& tree, const float4* __restrict__ top_s, const RayRegs& r,
+                                                Stack& st, Lane& L) {
+    MNode nd;
+    if (kTopK > 0 && (L.cur & kTopFlag))  // a staged node: its child fields carry the flag for staged children
+        nd = mnode_load_shared(top_s, L.cur & ~kTopFlag);
+    else
+        nd = mnode_load_global(tree.nodes, L.cur);
+    float key[4];
+    const uint32_t mask = mbvh_slabs<EXACT>(nd.mnx, nd.mxx, nd.mny, nd.mxy, nd.mnz, nd.mxz, r, key);
+    const int4 ch = nd.ch, cn = nd.cn;
+    const uint32_t leafbits = (cn.x > -1 ? 1u : 0u) | (cn.y > -1 ? 2u : 0u) | (cn.z > -1 ? 4u : 0u) | (cn.w > -1 ? 8u : 0u);
+    const uint32_t childbits = (ch.x > -1 ? 1u : 0u) | (ch.y > -1 ? 2u : 0u) | (ch.z > -1 ? 4u : 0u) | (ch.w > -1 ? 8u : 0u);
+    const uint32_t leaves = mask & leafbits;
+    const uint32_t inner = mask & ~leafbits & childbits;
+    int next = -1;
+    if (inner) {
+        int pay[4] = {(inner & 1u) ? ch.x : -1, (inner & 2u) ? ch.y : -1, (inner & 4u) ? ch.z : -1, (inner & 8u) ? ch.w : -1};
+        RTB_CSWAP(0, 1)
+        RTB_CSWAP(2, 3)
+        RTB_CSWAP(0, 2)
+        RTB_CSWAP(1, 3)
+        if (key[2] > key[3]) {  // the last comparator swaps ids only (mbvh_node.rs:219-237)
+            int tp = pay[2];
+            pay[2] = pay[3];
+            pay[3] = tp;
+        }
+        next = pay[0] >= 0 ? pay[0] : (pay[1] >= 0 ? pay[1] : (pay[2] >= 0 ? pay[2] : pay[3]));
+        const int skip = pay[0] >= 0 ? 0 : (pay[1] >= 0 ? 1 : (pay[2] >= 0 ? 2 : 3));
+        if (st.sp + 3 <= kSmemStack) {
+            int* b = st.base + st.sp * st.stride;
+            int c = 0;
+            if (skip < 3 && pay[3] >= 0) { b[c * st.stride] = pay[3]; c++; }
+            if (skip < 2 && pay[2] >= 0) { b[c * st.stride] = pay[2]; c++; }
+            if (skip < 1 && pay[1] >= 0) { b[c * st.stride] = pay[1]; c++; }
+            st.sp += c;
+        } else {
+            if (skip < 3 && pay[3] >= 0) st.push(pay[3]);
+            if (skip < 2 && pay[2] >= 0) st.push(pay[2]);
+            if (skip < 1 && pay[1] >= 0) st.push(pay[1]);
+        }
+    }
+    L.cur = next;
+    if (leaves) {  // usually one slot: it becomes the lane's current range (the lane has none: it is in the N phase)
+        const int s0 = __ffs(leaves) - 1;
+        const int c0 = sel4(cn, s0), f0 = sel4(ch, s0);
+        L.tri_pos = f0;
+        L.tri_end = f0 + (c0 > 0 ? c0 : 0);
+        uint32_t rest = leaves & (leaves - 1);
+        while (rest) {  // further hit leaf slots of the same node: parked on the stack
+            const int s = __ffs(rest) - 1;
+            rest &= rest - 1;
+            lane_take_leaf(st, L, sel4(ch, s), sel4(cn, s));
+        }
+    }
+}
+// N phase, Bvh: one popped node (the root is popped without a box test, iter_indices.rs:32-46).
+__device__ __forceinline__ void bvh_node_phase(const DeviceTree& tree, const RayRegs& r, Stack& st, Lane& L) {
+    const float4* __restrict__ nodes = tree.nodes;
+    const F8 nd = ld256(nodes + (size_t)L.cur * 2);
+    const int count = __float_as_int(nd.lo.w), left_first = __float_as_int(nd.hi.w);
+    int next = -1;
+    if (count > -1) {
+        lane_take_leaf(st, L, left_first, count);
+    } else if (left_first > -1) {
+        const float4* c = nodes + (size_t)left_first * 2;
+        const F8 lc = ld256(c), rc = ld256(c + 2);
+        float kl = 0.f, kr = 0.f;
+        const bool hl = aabb_single(lc.lo, lc.hi, r, kl);
+        const bool hr = aabb_single(rc.lo, rc.hi, r, kr);
+        if (hl && hr) {  // BvhNode::sort_nodes (bvh_node.rs:150-177)
+            if (kl < kr) {
+                st.push(left_first);
+                next = left_first + 1;
+            } else {
+                st.push(left_first + 1);
+                next = left_first;
+            }
+        } else if (hl) {
+            next = left_first;
+        } else if (hr) {
+            next = left_first + 1;
+        }
+    }
+    L.cur = next;
+}
+
 // ================================================================================================
 // kernels
 // ================================================================================================
@@ -549,7 +759,7 @@ __global__ void __launch_bounds__(kBlock) trace_single_kernel(const DeviceTree t
     const size_t i = perm ? (size_t)perm[slot] : slot;  // sorted launch order -> original ray index
     RayRegs r;
     load_ray(rays, i, r);
-    Stack st{smem + threadIdx.x, deep, 0, overflow};
+    Stack st{smem + threadIdx.x, deep, 0, overflow, kBlock};
     if (tree.node_count != 0 && !r.nan) {
         int cur = 0;
         while (!single_step<TREE, ANY>(tree, r, st, cur)) {
@@ -564,8 +774,8 @@ __global__ void __launch_bounds__(kBlock) trace_single_kernel(const DeviceTree t
 // hands the idle lanes the next rays (ballot + prefix popcount).  Lanes therefore sit at different
 // depths of different rays, but all execute the same node-visit step, which keeps the SIMD lanes
 // busy when ray lengths differ (one missing ray no longer pins 31 idle lanes).
-template <int TREE, bool ANY>
-__global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent_kernel(const DeviceTree tree,
+template <int TREE, bool ANY, bool PHASED>
+__global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persistent_kernel(const DeviceTree tree,
                                                                          const RTRay* __restrict__ rays, size_t n,
                                                                          RTHit* __restrict__ hits,
                                                                          uint8_t* __restrict__ occluded,
@@ -573,15 +783,28 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                                                                          unsigned long long* __restrict__ counter,
                                                                          uint32_t* __restrict__ overflow,
                                                                          const PeerDests pd) {
-    __shared__ int smem[kSmemStack * kBlock];
+    // dynamic shared memory: the traversal stacks ([entry][thread]) and, behind them, the staged top of the tree
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    int* smem = reinterpret_cast<int*>(dyn_smem);
+    const float4* top_s = nullptr;
+    if constexpr (kTopK > 0 && PHASED && TREE == RT_TREE_MBVH) {
+        float4* t = reinterpret_cast<float4*>(dyn_smem + (size_t)kSmemStack * kPBlock * sizeof(int));
+        const uint32_t cnt = tree.top_count < (uint32_t)kTopK ? tree.top_count : (uint32_t)kTopK;
+        for (uint32_t i = threadIdx.x; i < cnt * 8; i += kPBlock) t[(i >> 3) * kTopRow + (i & 7)] = __ldg(tree.top + i);
+        __syncthreads();
+        top_s = t;
+    }
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     int deep[kSpillStack];
-    Stack st{smem + threadIdx.x, deep, 0, overflow};
+    Stack st{smem + threadIdx.x, deep, 0, overflow, kPBlock};
     RayRegs r;
     int cur = 0;
+    Lane L{-1, 0, 0, 0};
     size_t my = 0;
     bool active = false;
+    bool fin = false;  // the lane holds the record of a finished ray that is not stored yet (stored at the next refill, by
+                       // all finished lanes of the warp in the same instructions, instead of lane by lane as rays end)
     unsigned long long res_next = 0, res_end = 0;  // this warp's reserved index range (warp-uniform)
     bool exhausted = false;                        // the global counter ran past n (warp-uniform)
     for (;;) {
@@ -616,6 +839,10 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                 const unsigned want = __popc(idle);
                 const unsigned take = avail < want ? (unsigned)avail : want;
                 const unsigned rank = __popc(idle & lt_mask);
+                if (__any_sync(0xFFFFFFFFu, fin)) {
+                    if (fin) store_result<ANY>(r, my, hits, occluded, pd);
+                    fin = false;
+                }
                 if (!active && rank < take) {
                     my = (size_t)(res_next + rank);
                     if (perm) my = (size_t)perm[my];
@@ -627,23 +854,62 @@ __global__ void __launch_bounds__(kBlock, RTB_MINBLOCKS) trace_single_persistent
                         load_ray(rays, my, r);
                     st.reset();
                     cur = 0;
+                    L = Lane{(kTopK > 0 && PHASED && TREE == RT_TREE_MBVH && tree.top_count != 0) ? kTopFlag : 0, 0, 0, 0};
                     if (tree.node_count != 0 && !r.nan)
                         active = true;
                     else
-                        store_result<ANY>(r, my, hits, occluded, pd);
+                        fin = true;
                 }
                 res_next += take;
                 idle = __ballot_sync(0xFFFFFFFFu, !active);
             }
             if (idle == 0xFFFFFFFFu) break;  // nothing left to trace for this warp
         }
-        if (active) {
-            if (single_step<TREE, ANY>(tree, r, st, cur)) {
-                store_result<ANY>(r, my, hits, occluded, pd);
+        if constexpr (!PHASED) {
+            if (active) {
+                if (single_step<TREE, ANY>(tree, r, st, cur)) {
+                    fin = true;
+                    active = false;
+                }
+            }
+        } else {
+            const bool in_t = active && L.tri_pos < L.tri_end;
+            const bool in_n = active && !in_t;
+            const int n_t = __popc(__ballot_sync(0xFFFFFFFFu, in_t));
+            const int n_n = __popc(__ballot_sync(0xFFFFFFFFu, in_n));
+            bool done = false;
+            if (n_t * RTB_TRI_NUM >= n_n * RTB_TRI_DEN && n_t > 0) {
+                if (in_t) {
+                    const bool hit = tri_candidate_flat(tree.tris, L.tri_pos, r);
+                    L.tri_pos++;
+                    if (ANY && hit)
+                        done = true;
+                    else if (L.tri_pos >= L.tri_end)
+                        done = lane_advance(st, L);
+                }
+            } else {
+                // slabs with the SSE operand rule for the whole warp as soon as one visiting lane needs it (a zero /
+                // non-finite component): for every other ray both flavours give the same predicates and keys
+                const bool any_exact = TREE == RT_TREE_MBVH && __any_sync(0xFFFFFFFFu, in_n && r.exact) != 0;
+                if (in_n) {
+                    if (TREE == RT_TREE_MBVH) {
+                        if (any_exact)
+                            mbvh_node_phase<true>(tree, top_s, r, st, L);
+                        else
+                            mbvh_node_phase<false>(tree, top_s, r, st, L);
+                    } else {
+                        bvh_node_phase(tree, r, st, L);
+                    }
+                    if (L.tri_pos >= L.tri_end) done = lane_advance(st, L);
+                }
+            }
+            if (done) {
+                fin = true;
                 active = false;
             }
         }
     }
+    if (fin) store_result<ANY>(r, my, hits, occluded, pd);
 }
 
 // ---- lane-cooperative node fetch -------------------------------------------------------------------
@@ -687,7 +953,7 @@ __global__ void __launch_bounds__(kBlock, 6) trace_mbvh_coop_kernel(const Device
     float* warp_tile = tiles + (threadIdx.x >> 5) * 32 * kNodeRowWords;
     const float4* my_row = reinterpret_cast<const float4*>(warp_tile + lane * kNodeRowWords);
     int deep[kSpillStack];
-    Stack st{smem + threadIdx.x, deep, 0, overflow};
+    Stack st{smem + threadIdx.x, deep, 0, overflow, kBlock};
     RayRegs r;
     int cur = 0, fetched = -1;  // fetched: the node whose copy is in (or on its way to) this lane's row
     size_t my = 0;
@@ -732,7 +998,13 @@ __global__ void __launch_bounds__(kBlock, 6) trace_mbvh_coop_kernel(const Device
         }
         // rows that do not hold the node their lane is about to visit (fresh rays): fetch now
         const int want = (active && fetched != cur) ? cur : -1;
-        if (__any_sync(0xFFFFFFFFu, want >= 0)) coop_fetch(tree.nodes, want, warp_tile, lane);
+        if (__any_sync(0xFFFFFFFFu, want >= 0)) {
+            if (ANY) {  // a ray that ended on a hit may have left a prefetch in flight into a row that is re-targeted now
+                cp_async_wait_all();
+                __syncwarp();
+            }
+            coop_fetch(tree.nodes, want, warp_tile, lane);
+        }
         cp_async_wait_all();
         __syncwarp();
         MNode nd;
@@ -802,7 +1074,7 @@ __global__ void __launch_bounds__(kBlock) trace_packet_kernel(const DeviceTree t
     load_packet_lane(packets, p, ql, t_min, r);
     const uint32_t qm = quad_mask();
     int deep[kSpillStack];
-    Stack st{smem + threadIdx.x, deep, 0, overflow};
+    Stack st{smem + threadIdx.x, deep, 0, overflow, kBlock};
     bool retired = false;
     // BvhPacketIndexIterator rejects the packet when ANY lane has a NaN (iter_indices.rs:129-144);
     // MbvhPacketIndexIterator has no such check (the NaN lane just never passes a comparison).
@@ -830,7 +1102,7 @@ __global__ void __launch_bounds__(kBlock) trace_packet_persistent_kernel(const D
     const unsigned below = (1u << (lane & 28u)) - 1u;  // lanes of lower quads
     const uint32_t qm = quad_mask();
     int deep[kSpillStack];
-    Stack st{smem + threadIdx.x, deep, 0, overflow};
+    Stack st{smem + threadIdx.x, deep, 0, overflow, kBlock};
     RayRegs r;
     int cur = 0;
     size_t my = 0;
@@ -941,7 +1213,65 @@ __global__ void camera_rays_kernel(float3 pos, float3 p1, float3 right, float3 u
     o[1] = make_float4(fmul(dx, inv), fmul(dy, inv), fmul(dz, inv), 1e34f);
 }
 
+// Breadth-first copy of the top of an Mbvh (one warp): slot 0 = root; a child that also got a slot is addressed as
+// (slot | kTopFlag) in its parent's copy, every other field is the node's own.  Slot order inside a level is arbitrary.
+__global__ void build_top_table_kernel(const float4* __restrict__ nodes, uint32_t node_count, uint32_t cap,
+                                       float4* __restrict__ top, uint32_t* __restrict__ top_count) {
+    extern __shared__ int q[];  // node index per slot
+    __shared__ int tail;
+    const int lane = threadIdx.x;
+    if (node_count == 0 || cap == 0) {
+        if (lane == 0) *top_count = 0;
+        return;
+    }
+    if (lane == 0) {
+        q[0] = 0;
+        tail = 1;
+    }
+    __syncwarp();
+    int head = 0;
+    for (;;) {
+        const int end = tail;
+        if (head >= end) break;
+        __syncwarp();
+        for (int i = head + lane; i < end; i += 32) {
+            const float4* n = nodes + (size_t)q[i] * 8;
+            int4 ch = as_int4(n[6]);
+            const int4 cn = as_int4(n[7]);
+            int* c = &ch.x;
+            const int* k = &cn.x;
+            for (int s = 0; s < 4; s++) {
+                if (k[s] <= -1 && c[s] > -1) {  // inner child
+                    const int slot = atomicAdd(&tail, 1);
+                    if (slot < (int)cap) {
+                        q[slot] = c[s];
+                        c[s] = slot | kTopFlag;
+                    }
+                }
+            }
+            float4* o = top + (size_t)i * 8;
+            for (int j = 0; j < 6; j++) o[j] = n[j];
+            o[6] = make_float4(__int_as_float(ch.x), __int_as_float(ch.y), __int_as_float(ch.z), __int_as_float(ch.w));
+            o[7] = n[7];
+        }
+        head = end;
+        __syncwarp();
+        if (lane == 0 && tail > (int)cap) tail = (int)cap;
+        __syncwarp();
+    }
+    if (lane == 0) *top_count = (uint32_t)tail;
+}
+
 }  // namespace
+
+int top_table_capacity() { return kTopK; }
+
+cudaError_t launch_build_top_table(const float4* d_nodes, uint32_t node_count, float4* d_top, uint32_t* d_top_count,
+                                   cudaStream_t stream) {
+    if (kTopK == 0) return cudaSuccess;
+    build_top_table_kernel<<<1, 32, (size_t)kTopK * sizeof(int), stream>>>(d_nodes, node_count, (uint32_t)kTopK, d_top, d_top_count);
+    return cudaGetLastError();
+}
 
 // ---- launchers ----------------------------------------------------------------------------------
 // ---- optional ray sorting ----------------------------------------------------------------------------
@@ -974,20 +1304,28 @@ __global__ void ray_keys_kernel(const RTRay* __restrict__ rays, size_t n, float3
 
 // grid of a persistent kernel: resident blocks per SM x number of SMs (queried once per kernel)
 template <class K>
-static unsigned persistent_grid(K kernel) {
+static unsigned persistent_grid(K kernel, int block = kBlock, size_t dyn_smem = 0) {
     int dev = 0, sms = kSmCount, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0);
+    if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, dyn_smem);
     return (unsigned)(sms * (per_sm > 0 ? per_sm : 1));
+}
+// dynamic shared memory of the persistent single-ray kernel: stacks, plus the staged top of the tree where it is used
+template <int TREE, bool PHASED>
+constexpr size_t persistent_smem() {
+    return (size_t)kSmemStack * kPBlock * sizeof(int) +
+           ((kTopK > 0 && PHASED && TREE == RT_TREE_MBVH) ? (size_t)kTopK * kTopRow * sizeof(float4) : 0);
 }
 
 template <int TREE, bool ANY>
 static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, size_t n, RTHit* d_hits,
                                    uint8_t* d_occluded, const uint32_t* d_perm, unsigned long long* d_counter,
                                    uint32_t* d_overflow, int mode, const PeerDests& pd, cudaStream_t stream) {
-    if ((pd.count > 0 || pd.ready || pd.directions) && mode != kTracePersistent) return cudaErrorNotSupported;  // fused gather / input gate / split input live in the default kernel
+    if ((pd.count > 0 || pd.ready || pd.directions) && mode != kTracePersistent && mode != kTracePhased) return cudaErrorNotSupported;  // fused gather / input gate / split input live in the default kernel
     const size_t blocks_needed = ceil_div(n, kBlock);
+    const size_t pblocks_needed = ceil_div(n, kPBlock);
     const bool persistent = mode != kTraceStatic;
     if (TREE == RT_TREE_MBVH && mode == kTraceCoop) {
         static const unsigned machine = persistent_grid(trace_mbvh_coop_kernel<ANY>);
@@ -997,13 +1335,22 @@ static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, 
         trace_mbvh_coop_kernel<ANY><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_perm, d_counter, d_overflow);
         return cudaGetLastError();
     }
-    if (persistent) {
-        static const unsigned machine = persistent_grid(trace_single_persistent_kernel<TREE, ANY>);
-        const unsigned grid = (unsigned)(blocks_needed < machine ? blocks_needed : machine);
+    if (mode == kTracePhased) {
+        constexpr size_t smem = persistent_smem<TREE, true>();
+        static const unsigned machine = persistent_grid(trace_single_persistent_kernel<TREE, ANY, true>, kPBlock, smem);
+        const unsigned grid = (unsigned)(pblocks_needed < machine ? pblocks_needed : machine);
         cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
-        trace_single_persistent_kernel<TREE, ANY><<<grid, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_perm,
-                                                                              d_counter, d_overflow, pd);
+        trace_single_persistent_kernel<TREE, ANY, true><<<grid, kPBlock, smem, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_perm,
+                                                                                    d_counter, d_overflow, pd);
+    } else if (persistent) {
+        constexpr size_t smem = persistent_smem<TREE, false>();
+        static const unsigned machine = persistent_grid(trace_single_persistent_kernel<TREE, ANY, false>, kPBlock, smem);
+        const unsigned grid = (unsigned)(pblocks_needed < machine ? pblocks_needed : machine);
+        cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+        trace_single_persistent_kernel<TREE, ANY, false><<<grid, kPBlock, smem, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_perm,
+                                                                                     d_counter, d_overflow, pd);
     } else {
         trace_single_kernel<TREE, ANY><<<(unsigned)blocks_needed, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded,
                                                                                      d_perm, d_overflow);
@@ -1018,10 +1365,10 @@ cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any,
     if (n == 0) return cudaSuccess;
     PeerDests pd{};
     if (peers) pd = *peers;
-    if ((pd.ready || pd.directions) && (sort_bounds != nullptr || mode != kTracePersistent)) return cudaErrorNotSupported;  // gate / split input: default kernel, caller's order
+    if ((pd.ready || pd.directions) && (sort_bounds != nullptr || (mode != kTracePersistent && mode != kTracePhased))) return cudaErrorNotSupported;  // gate / split input: default kernel, caller's order
     uint32_t* d_perm = nullptr;
     void* scratch = nullptr;
-    if (sort_bounds != nullptr && n >= 4096 && n < (size_t(1) << 32)) {
+    if (sort_bounds != nullptr && n >= 4096 && n <= (size_t)0x7FFFFFFF) {  // CUB's num_items is an int; larger batches are traced unsorted
         // scratch from the stream-ordered pool: keys in/out (8 B), indices in/out (4 B), CUB temp
         size_t temp_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,

@@ -9,6 +9,7 @@ enum TraceMode {
     kTraceStatic = 0,      // one thread per ray, no refill (A/B only)
     kTracePersistent = 1,  // persistent warps + ray refill, every lane fetches its own node
     kTraceCoop = 2,        // same + lane-cooperative node fetch through shared memory (Mbvh; Bvh falls back to 1)
+    kTracePhased = 3,      // persistent warps + refill, node visits and triangle tests as separate warp-wide phases (default)
 };
 // d_counter: one 64-bit work counter owned by this launch (zeroed on `stream` by the launcher).
 // Destinations of the fused multi-GPU gather: up to 8 buffers (own + cudaIpc-mapped peers); record i goes to
@@ -36,6 +37,10 @@ cudaError_t launch_trace_single(const DeviceTree& tree, int tree_kind, bool any,
 cudaError_t launch_trace_packets(const DeviceTree& tree, int tree_kind, bool any, const RTRayPacket4* d_packets,
                                  size_t n_packets, float t_min, RTHitPacket4* d_hits, uint8_t* d_occluded,
                                  unsigned long long* d_counter, uint32_t* d_overflow, int mode, cudaStream_t stream);
+// Staged top of an Mbvh (DeviceTree::top): capacity in nodes (0: this build does not stage), and the one-warp builder.
+int top_table_capacity();
+cudaError_t launch_build_top_table(const float4* d_nodes, uint32_t node_count, float4* d_top, uint32_t* d_top_count,
+                                   cudaStream_t stream);
 cudaError_t launch_gather_tris(const float* d_verts, uint32_t stride_floats, const uint32_t* d_indices,
                                uint32_t index_count, uint32_t tri_count, TriRec* d_out, cudaStream_t stream);
 cudaError_t launch_camera_rays(const float pos[3], const float p1[3], const float right[3], const float up[3],

@@ -355,6 +355,44 @@ def test_host_pipeline_flavours_in_a_subprocess(A, mode):
     assert r.returncode == 0 and "gated ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_host_buffer_calls_return_under_synchronous_launches(A):
+    """CUDA_LAUNCH_BLOCKING=1 makes every kernel launch synchronous, as ncu and compute-sanitizer do.  The gated host
+    pipeline starts a launch before its rays have arrived; all its uploads and watermark writes must therefore be queued
+    BEFORE the launch call (round-1 defect: launch first, feed afterwards -> the launch never returned).  Runs smoke() and a
+    3 M-ray blocking + asynchronous call from pinned buffers in a subprocess with a hard timeout: a call that always
+    returns, like rtbvh_ffi/src/lib.rs:700-731."""
+    import subprocess
+    import sys
+    import os
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, '.')\n"
+        "import __graft_entry__ as G\n"
+        "G.smoke()\n"
+        "import torch\n"
+        "from rtbvh_b200 import api, workloads as W\n"
+        "from oracle import oracle as O\n"
+        "tris = W.soup(50_000)\n"
+        "aabbs, centers = O.prims_from_triangles(tris)\n"
+        "rc, bvh = O.build(O.BINNED_SAH, aabbs, centers, 1); m = bvh.collapse()\n"
+        "sc = api.Scene(tris, bvh=None, mbvh=api.Mbvh.from_arrays(m.nodes, m.indices))\n"
+        "rays = W.random_rays(3_000_000, *W.bounds(tris), seed=5)\n"
+        "want = O.trace(m, tris, rays, threads=8)[0]\n"
+        "hr = torch.from_numpy(rays.view(np.float32).reshape(-1).copy()).pin_memory()\n"
+        "hh = torch.zeros(6_000_000, dtype=torch.float32).pin_memory()\n"
+        "sc.intersect_ptr(hr.data_ptr(), 3_000_000, hh.data_ptr(), api.TREE_MBVH)\n"
+        "assert np.array_equal(hh.numpy().view(api.HIT_DTYPE).reshape(-1), want)\n"
+        "hh.zero_()\n"
+        "t = sc.intersect_async(hr.data_ptr(), 3_000_000, hh.data_ptr(), api.TREE_MBVH); sc.wait(t)\n"
+        "assert np.array_equal(hh.numpy().view(api.HIT_DTYPE).reshape(-1), want)\n"
+        "assert np.array_equal(sc.intersect(rays, api.TREE_MBVH), want)  # pageable input\n"
+        "print('blocking ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ({}, {"RTBVH_HOST_MODE": "gated"}):
+        env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1", **extra)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "blocking ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_split_origin_direction_input(A, O, W, teapot, teapot_trees):
     """rtbvh_gpu_intersect_od / _occluded_od / _od_async / _od_device: origins and directions as packed float3 arrays with a
     common t_min / t_max (the reference FFI's argument shape) give the records of the RTRay calls, bit for bit."""
