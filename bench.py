@@ -172,6 +172,10 @@ def run_gpu(args):
     sort_rays = os.environ.get("RTBVH_BENCH_SORT", "0") == "1"  # experiment knob; primary rays are coherent already
     scene.set_ray_sorting(sort_rays)
     info["ray_sorting"] = sort_rays
+    # work-order hint for image-ordered batches: 8x8 pixel tiles per warp instead of 64-pixel row segments (results unchanged)
+    tiling = os.environ.get("RTBVH_BENCH_TILING", "1") == "1"
+    scene.set_ray_tiling(WIDTH if tiling else 0)
+    info["ray_tiling"] = f"rtbvh_gpu_scene_set_ray_tiling({WIDTH})" if tiling else "off"
 
     fps = args.frames_per_step
     rays_per_step = fps * WIDTH * HEIGHT

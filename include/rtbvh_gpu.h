@@ -117,6 +117,13 @@ ResultCode rtbvh_gpu_scene_read_nodes(RTGpuScene scene, RTTreeKind tree, void *o
  * order of (origin, direction) and scatter the results back.  Results are unchanged, bit for bit; only the
  * order in which the device works through the batch changes.  Default 0 (camera rays are coherent already). */
 ResultCode rtbvh_gpu_scene_set_ray_sorting(RTGpuScene scene, int enable);
+/* Image-ordered batches (primary rays: ray i = pixel (i % row_length, i / row_length), any number of frames back to back):
+ * the device-pointer single-ray calls then hand the rays to the warps as 8x8 pixel tiles instead of 64-pixel row segments
+ * — a work-order hint like ray sorting, at no cost (index arithmetic in the kernel, no sort): neighbouring lanes walk
+ * neighbouring parts of the tree.  Results are unchanged, bit for bit, and stay at their rays' indices.  row_length must be
+ * a multiple of 8; rays beyond the last whole band of 8 rows keep the linear order; 0 switches the hint off.  Ignored while
+ * ray sorting is on and by the host-buffer calls (their rays arrive in index order). */
+ResultCode rtbvh_gpu_scene_set_ray_tiling(RTGpuScene scene, uint32_t row_length);
 
 /* ---- closest hit / any hit, host buffers (H2D + kernels + D2H inside the call) ------------------ */
 ResultCode rtbvh_gpu_intersect(RTGpuScene scene, RTTreeKind tree, const RTRay *rays, size_t ray_count, RTHit *hits);

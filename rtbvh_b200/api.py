@@ -46,7 +46,7 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_occluded_packets", "rtbvh_gpu_intersect_device", "rtbvh_gpu_occluded_device",
                "rtbvh_gpu_intersect_packets_device", "rtbvh_gpu_occluded_packets_device",
                "rtbvh_gpu_scene_stack_overflowed", "rtbvh_gpu_generate_camera_rays_device",
-               "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats", "rtbvh_gpu_scene_set_ray_sorting", "rtbvh_gpu_create_mbvh_from", "rtbvh_gpu_peer_buffer_create",
+               "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats", "rtbvh_gpu_scene_set_ray_sorting", "rtbvh_gpu_scene_set_ray_tiling", "rtbvh_gpu_create_mbvh_from", "rtbvh_gpu_peer_buffer_create",
                "rtbvh_gpu_peer_buffer_open", "rtbvh_gpu_peer_buffer_close", "rtbvh_gpu_peer_buffer_free",
                "rtbvh_gpu_intersect_device_scatter", "rtbvh_gpu_occluded_device_scatter", "rtbvh_gpu_peer_barrier",
                "rtbvh_gpu_intersect_async", "rtbvh_gpu_occluded_async", "rtbvh_gpu_wait", "rtbvh_gpu_host_alloc",
@@ -118,6 +118,8 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_scene_create.argtypes = [C.POINTER(RTBvh), C.POINTER(RTMbvh), vp, sz, sz, C.POINTER(u64)]
     L.rtbvh_gpu_scene_set_ray_sorting.restype = rc
     L.rtbvh_gpu_scene_set_ray_sorting.argtypes = [u64, C.c_int]
+    L.rtbvh_gpu_scene_set_ray_tiling.restype = rc
+    L.rtbvh_gpu_scene_set_ray_tiling.argtypes = [u64, C.c_uint32]
     L.rtbvh_gpu_scene_free.restype = rc
     L.rtbvh_gpu_scene_free.argtypes = [u64]
     L.rtbvh_gpu_intersect.restype = rc
@@ -413,6 +415,10 @@ class Scene:
     def set_ray_sorting(self, enable: bool = True):
         """Trace every single-ray batch in Morton order of (origin, direction); results are unchanged."""
         _check(lib().rtbvh_gpu_scene_set_ray_sorting(self.handle, int(enable)))
+
+    def set_ray_tiling(self, row_length: int = 0):
+        """Image-ordered batches: the device-pointer calls trace 8x8 pixel tiles (work order only; 0 = off)."""
+        _check(lib().rtbvh_gpu_scene_set_ray_tiling(self.handle, int(row_length)))
 
     def free(self):
         if self.handle.value:

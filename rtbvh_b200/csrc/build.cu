@@ -36,6 +36,8 @@
 #include <string>
 #include <vector>
 
+#include <atomic>
+
 #include "build.cuh"
 
 namespace rtb {
@@ -2483,6 +2485,18 @@ static ResultCode collapse_device(const float4* d_nodes, uint32_t n_nodes, DevBu
 // =================================================================================================
 // Host-facing entry points (host arrays in, host mirrors out)
 // =================================================================================================
+// The tree the last build of this thread left in the arena: create_mbvh right after create_bvh collapses it in place instead
+// of uploading the host mirror again.  Valid while the arena has not been reset (epoch) and the mirror is the same array.
+struct LastTree {
+    uint64_t serial = 0;
+    const void* d_nodes = nullptr;
+    uint32_t node_count = 0;
+    uint64_t epoch = 0;
+};
+static thread_local LastTree g_last_tree;
+static thread_local uint64_t g_arena_epoch = 1;
+static std::atomic<uint64_t> g_build_serial{0};
+
 static ResultCode need_device() {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -2492,15 +2506,18 @@ static ResultCode need_device() {
     // every builder entry point starts with an empty workspace (what earlier builds of this thread left in it is dead:
     // they synchronised before returning and copied their results out)
     const cudaError_t e = arena().reset();
+    g_arena_epoch++;
     if (e != cudaSuccess) return fail("builder workspace", e);
     return Ok;
 }
 
 static ResultCode download(const DeviceBvh& d, HostBvh* out) {
-    out->nodes.resize(d.node_count);
-    out->indices.resize(d.index_count);
-    if (d.node_count) RTB_CUDA(cudaMemcpy(out->nodes.data(), d.nodes.p, (size_t)d.node_count * 32, cudaMemcpyDeviceToHost));
-    if (d.index_count) RTB_CUDA(cudaMemcpy(out->indices.data(), d.indices.p, (size_t)d.index_count * 4, cudaMemcpyDeviceToHost));
+    if (!out->nodes.resize(d.node_count) || !out->indices.resize(d.index_count)) return fail("host mirror: out of memory");
+    if (d.node_count) RTB_CUDA(cudaMemcpyAsync(out->nodes.data(), d.nodes.p, (size_t)d.node_count * 32, cudaMemcpyDeviceToHost, 0));
+    if (d.index_count) RTB_CUDA(cudaMemcpyAsync(out->indices.data(), d.indices.p, (size_t)d.index_count * 4, cudaMemcpyDeviceToHost, 0));
+    RTB_CUDA(cudaStreamSynchronize(0));
+    out->serial = ++g_build_serial;
+    g_last_tree = LastTree{out->serial, d.nodes.p, d.node_count, g_arena_epoch};
     return Ok;
 }
 
@@ -2515,9 +2532,9 @@ ResultCode gpu_build_bvh(const RTAabb* aabbs, size_t prim_count, const float* ce
     DevBuf bb, cen;
     RTB_CUDA(bb.alloc((size_t)n * 32));
     RTB_CUDA(cen.alloc((size_t)n * center_stride));
-    RTB_CUDA(cudaMemcpy(cen.p, centers, (size_t)n * center_stride, cudaMemcpyHostToDevice));
+    RTB_CUDA(upload_from_user(cen.p, centers, (size_t)n * center_stride, 0));
     if (aabbs)
-        RTB_CUDA(cudaMemcpy(bb.p, aabbs, (size_t)n * 32, cudaMemcpyHostToDevice));
+        RTB_CUDA(upload_from_user(bb.p, aabbs, (size_t)n * 32, 0));
     dev.start();
     if (!aabbs) point_boxes_kernel<<<blocks(n, 256), 256>>>(cen.as<float>(), cstride, n, bb.as<float4>());
     DeviceBvh d;
@@ -2550,7 +2567,7 @@ ResultCode gpu_build_bvh_triangles(const float* vertices, size_t vertex_stride, 
     RTB_CUDA(verts.alloc((size_t)n * 3 * vertex_stride));
     RTB_CUDA(bb.alloc((size_t)n * 32));
     RTB_CUDA(cen.alloc((size_t)n * 12));
-    RTB_CUDA(cudaMemcpy(verts.p, vertices, (size_t)n * 3 * vertex_stride, cudaMemcpyHostToDevice));
+    RTB_CUDA(upload_from_user(verts.p, vertices, (size_t)n * 3 * vertex_stride, 0));
     dev.start();
     tri_prims_kernel<<<blocks(n, 256), 256>>>(verts.as<float>(), (uint32_t)(vertex_stride / 4), n, bb.as<float4>(), cen.as<float>());
     DeviceBvh d;
@@ -2577,25 +2594,40 @@ ResultCode gpu_build_bvh_triangles(const float* vertices, size_t vertex_stride, 
 }
 
 ResultCode gpu_collapse(const HostBvh& bvh, HostMbvh* out) {
-    if (need_device() != Ok) return Error;
-    out->nodes = bvh.nodes;      // Mbvh keeps clones of the binary nodes and of prim_indices (bvh.rs:399-403)
-    out->indices = bvh.indices;
     out->m_nodes.clear();
-    if (bvh.nodes.empty()) return Ok;
+    const uint32_t n_nodes = (uint32_t)bvh.nodes.size();
+    // the tree this thread built last may still sit in the builder workspace: collapse it where it is (no arena reset, the
+    // collapse's own buffers are taken behind it) instead of uploading the 32 B/node mirror again
+    const bool resident = n_nodes != 0 && bvh.serial != 0 && g_last_tree.serial == bvh.serial && g_last_tree.node_count == n_nodes &&
+                          g_last_tree.epoch == g_arena_epoch;
+    if (resident) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device: the builders run on the GPU only (no CPU fallback)");
+    } else if (need_device() != Ok) {
+        return Error;
+    }
+    if (n_nodes == 0) return Ok;
     Timer total, dev;
     total.start();
     DevBuf nodes, mnodes;
-    const uint32_t n_nodes = (uint32_t)bvh.nodes.size();
-    RTB_CUDA(nodes.alloc((size_t)n_nodes * 32));
-    RTB_CUDA(cudaMemcpy(nodes.p, bvh.nodes.data(), (size_t)n_nodes * 32, cudaMemcpyHostToDevice));
+    const float4* d_nodes = (const float4*)g_last_tree.d_nodes;
+    if (!resident) {
+        RTB_CUDA(nodes.alloc((size_t)n_nodes * 32));
+        RTB_CUDA(upload_from_user(nodes.p, bvh.nodes.data(), (size_t)n_nodes * 32, 0));
+        d_nodes = nodes.as<float4>();
+    }
     dev.start();
     uint32_t m_count = 0;
-    if (collapse_device(nodes.as<float4>(), n_nodes, &mnodes, &m_count) != Ok) return Error;
+    if (collapse_device(d_nodes, n_nodes, &mnodes, &m_count) != Ok) return Error;
     g_build_stats.device_ms = dev.stop();
-    out->m_nodes.resize(m_count);
-    if (m_count) RTB_CUDA(cudaMemcpy(out->m_nodes.data(), mnodes.p, (size_t)m_count * 128, cudaMemcpyDeviceToHost));
+    if (!out->m_nodes.resize(m_count)) return fail("host mirror: out of memory");
+    if (m_count) {
+        RTB_CUDA(cudaMemcpyAsync(out->m_nodes.data(), mnodes.p, (size_t)m_count * 128, cudaMemcpyDeviceToHost, 0));
+        RTB_CUDA(cudaStreamSynchronize(0));
+    }
     g_build_stats.total_ms = total.stop();
     g_build_stats.node_count = m_count;
+    g_build_stats.iterations = resident ? 1 : 0;  // 1: collapsed in place from the previous build's device copy
     return Ok;
 }
 
@@ -2611,9 +2643,9 @@ ResultCode gpu_refit(HostBvh* bvh, const RTAabb* aabbs) {
     RTB_CUDA(bb.alloc((size_t)n_idx * 32));
     RTB_CUDA(parent.alloc((size_t)n_nodes * 4));
     RTB_CUDA(arrived.alloc((size_t)n_nodes * 4));
-    RTB_CUDA(cudaMemcpy(nodes.p, bvh->nodes.data(), (size_t)n_nodes * 32, cudaMemcpyHostToDevice));
-    RTB_CUDA(cudaMemcpy(idx.p, bvh->indices.data(), (size_t)n_idx * 4, cudaMemcpyHostToDevice));
-    RTB_CUDA(cudaMemcpy(bb.p, aabbs, (size_t)n_idx * 32, cudaMemcpyHostToDevice));  // reads prim_count() aabbs (lib.rs:527-530)
+    RTB_CUDA(upload_from_user(nodes.p, bvh->nodes.data(), (size_t)n_nodes * 32, 0));
+    RTB_CUDA(upload_from_user(idx.p, bvh->indices.data(), (size_t)n_idx * 4, 0));
+    RTB_CUDA(upload_from_user(bb.p, aabbs, (size_t)n_idx * 32, 0));  // reads prim_count() aabbs (lib.rs:527-530)
     dev.start();
     RTB_CUDA(cudaMemset(arrived.p, 0, (size_t)n_nodes * 4));
     RTB_CUDA(cudaMemset(parent.p, 0xFF, (size_t)n_nodes * 4));
@@ -2622,7 +2654,8 @@ ResultCode gpu_refit(HostBvh* bvh, const RTAabb* aabbs) {
                                                 bb.as<float4>(), arrived.as<uint32_t>());
     RTB_CUDA(cudaGetLastError());
     g_build_stats.device_ms = dev.stop();
-    RTB_CUDA(cudaMemcpy(bvh->nodes.data(), nodes.p, (size_t)n_nodes * 32, cudaMemcpyDeviceToHost));
+    RTB_CUDA(cudaMemcpyAsync(bvh->nodes.data(), nodes.p, (size_t)n_nodes * 32, cudaMemcpyDeviceToHost, 0));
+    RTB_CUDA(cudaStreamSynchronize(0));
     g_build_stats.total_ms = total.stop();
     return Ok;
 }
@@ -2678,6 +2711,8 @@ ResultCode gpu_build_resident(const float* vertices, bool vertices_on_device, si
 
 ResultCode gpu_trim_workspace() {
     arena().release();
+    g_arena_epoch++;
+    HostPool::get().trim();
     return Ok;
 }
 

@@ -1,21 +1,28 @@
 // build.cuh — GPU builders behind create_bvh / create_mbvh / refit (build.cu).
 #pragma once
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "hostmem.cuh"
 
 namespace rtb {
 
-struct HostBvh {   // host mirror handed out through RTBvh (rtbvh::Bvh, src/bvh.rs:143-147)
-    std::vector<RTBvhNode> nodes;
-    std::vector<uint32_t> indices;
+struct HostBvh {   // host mirror handed out through RTBvh (rtbvh::Bvh, src/bvh.rs:143-147); pooled page-locked arrays
+    HostArray<RTBvhNode> nodes;
+    HostArray<uint32_t> indices;
     int build_type = 0;  // src/bvh.rs:18-23
+    uint64_t serial = 0;  // process-wide build number (identifies the device copy a collapse may reuse)
 };
-struct HostMbvh {  // rtbvh::Mbvh, src/bvh.rs:320-324
-    std::vector<RTBvhNode> nodes;
-    std::vector<RTMbvhNode> m_nodes;
-    std::vector<uint32_t> indices;
+// rtbvh::Mbvh (src/bvh.rs:320-324) keeps clones of the binary nodes and of prim_indices next to m_nodes.  Here the Mbvh shares
+// them with the Bvh it was collapsed from (`base`: both tables hold shared ownership, so free_bvh never invalidates the
+// pointers in an RTMbvh) instead of copying 68 MB per Mtri on the host; RTMbvh exposes only m_nodes and indices.
+struct HostMbvh {
+    std::shared_ptr<const HostBvh> base;
+    HostArray<RTMbvhNode> m_nodes;
+    const uint32_t* indices() const { return base ? base->indices.data() : nullptr; }
+    size_t index_count() const { return base ? base->indices.size() : 0; }
 };
 
 struct BuildStats {   // of the last build / collapse / refit on this thread
@@ -37,7 +44,7 @@ ResultCode gpu_build_bvh(const RTAabb* aabbs, size_t prim_count, const float* ce
 ResultCode gpu_build_bvh_triangles(const float* vertices, size_t vertex_stride, size_t tri_count, size_t prims_per_leaf,
                                    uint32_t bvh_type, HostBvh* out);
 // Mbvh::construct (src/bvh.rs:381-404) on the GPU.
-ResultCode gpu_collapse(const HostBvh& bvh, HostMbvh* out);
+ResultCode gpu_collapse(const HostBvh& bvh, HostMbvh* out);  // fills out->m_nodes (out->base is the caller's business)
 // Bvh::refit (src/bvh.rs:176-205) on the GPU.
 ResultCode gpu_refit(HostBvh* bvh, const RTAabb* aabbs);
 
@@ -53,7 +60,8 @@ struct ResidentTrees {
 ResultCode gpu_build_resident(const float* vertices, bool vertices_on_device, size_t vertex_stride, size_t tri_count,
                               size_t prims_per_leaf, uint32_t bvh_type, bool want_mbvh, ResidentTrees* out);
 
-// Frees the calling thread's builder workspace (it is otherwise kept between builds and only ever grows).
+// Frees the calling thread's builder workspace (it is otherwise kept between builds and only ever grows) and the cached
+// page-locked host blocks.
 ResultCode gpu_trim_workspace();
 
 // Dynamic scenes: refit of a device-resident Bvh (+ refresh of its Mbvh) from new vertex positions,

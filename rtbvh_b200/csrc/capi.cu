@@ -95,6 +95,16 @@ struct Scene {
     uint32_t* d_overflow = nullptr;
     float bounds[6] = {0, 0, 0, 1, 1, 1};  // root box (keys of the optional ray sort)
     std::atomic<int> sort_rays{0};
+    std::atomic<uint32_t> tile_w{0};  // rtbvh_gpu_scene_set_ray_tiling: row length of image-ordered batches (0 = off)
+    // work-order hint for the device-resident single-ray calls: 8x8 pixel tiles over the whole 8-row bands of the batch
+    void apply_tiling(PeerDests& pd, size_t n) const {
+        const uint32_t w = tile_w.load();
+        if (w == 0 || sort_rays.load()) return;
+        const unsigned long long band = 8ull * w;
+        pd.tile_w = w;
+        pd.tile_n = (unsigned long long)n / band * band;
+        if (pd.tile_n == 0) pd.tile_w = 0;
+    }
     const float* sort_bounds() const { return sort_rays.load() ? bounds : nullptr; }
     // work counters of the persistent kernels: every launch takes the next slot and zeroes it on its
     // own stream, so launches on different streams never share a counter
@@ -851,6 +861,14 @@ ResultCode rtbvh_gpu_scene_set_ray_sorting(RTGpuScene h, int enable) {
     return Ok;
 }
 
+ResultCode rtbvh_gpu_scene_set_ray_tiling(RTGpuScene h, uint32_t row_length) {
+    auto s = get_scene(h);
+    if (!s) return fail("unknown scene");
+    if (row_length % 8 != 0) return fail("rtbvh_gpu_scene_set_ray_tiling: the row length must be a multiple of 8 (0 = off)");
+    s->tile_w.store(row_length);
+    return Ok;
+}
+
 ResultCode rtbvh_gpu_scene_free(RTGpuScene h) {
     std::unique_lock<std::shared_mutex> lk(g_scenes.mu);
     if (h == 0 || h > g_scenes.scenes.size() || !g_scenes.scenes[h - 1]) return fail("unknown scene");
@@ -877,8 +895,10 @@ ResultCode rtbvh_gpu_intersect_device(RTGpuScene h, RTTreeKind tree, const RTRay
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
     if (!on_scene_device(*s)) return fail("the scene lives on another device than the current one (cudaSetDevice / rtbvh_gpu_set_device first)");
+    PeerDests pd{};
+    s->apply_tiling(pd, n);
     RTB_CUDA(launch_trace_single(*t, tree, false, d_rays, n, d_hits, nullptr, s->counter_slot(), s->d_overflow,
-                                 persistent_mode(), s->sort_bounds(), nullptr, (cudaStream_t)stream));
+                                 persistent_mode(), s->sort_bounds(), pd.tile_w ? &pd : nullptr, (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_occluded_device(RTGpuScene h, RTTreeKind tree, const RTRay* d_rays, size_t n, uint8_t* d_occ,
@@ -888,8 +908,10 @@ ResultCode rtbvh_gpu_occluded_device(RTGpuScene h, RTTreeKind tree, const RTRay*
     const DeviceTree* t = pick_tree(*s, tree);
     if (!t) return fail("scene has no such tree");
     if (!on_scene_device(*s)) return fail("the scene lives on another device than the current one (cudaSetDevice / rtbvh_gpu_set_device first)");
+    PeerDests pd{};
+    s->apply_tiling(pd, n);
     RTB_CUDA(launch_trace_single(*t, tree, true, d_rays, n, nullptr, d_occ, s->counter_slot(), s->d_overflow,
-                                 persistent_mode(), s->sort_bounds(), nullptr, (cudaStream_t)stream));
+                                 persistent_mode(), s->sort_bounds(), pd.tile_w ? &pd : nullptr, (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* d_packets, size_t n,
@@ -927,6 +949,7 @@ static ResultCode scatter_call(RTGpuScene h, RTTreeKind tree, bool any, const RT
     for (int k = 0; k < dest_count; k++) pd.p[k] = dests[k];
     pd.count = dest_count;
     pd.offset = dest_offset;
+    s->apply_tiling(pd, n);
     RTB_CUDA(launch_trace_single(*t, tree, any, d_rays, n, any ? nullptr : (RTHit*)d_local, any ? (uint8_t*)d_local : nullptr,
                                  s->counter_slot(), s->d_overflow, refill_mode(), s->sort_bounds(), &pd, (cudaStream_t)stream));
     return Ok;

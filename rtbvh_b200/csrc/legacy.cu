@@ -22,10 +22,10 @@ namespace hi = rtbvh_host;
 namespace {
 struct Manager {
     std::shared_mutex mu_bvh, mu_mbvh;
-    std::vector<std::unique_ptr<HostBvh>> bvhs;
+    std::vector<std::shared_ptr<HostBvh>> bvhs;  // shared: an Mbvh keeps the Bvh it was collapsed from alive (its indices)
     std::vector<std::unique_ptr<HostMbvh>> mbvhs;
 
-    RTBvh store(std::unique_ptr<HostBvh> b) {  // lib.rs:46-60
+    RTBvh store(std::shared_ptr<HostBvh> b) {  // lib.rs:46-60
         std::unique_lock<std::shared_mutex> lk(mu_bvh);
         bvhs.push_back(std::move(b));
         const HostBvh& s = *bvhs.back();
@@ -37,7 +37,7 @@ struct Manager {
         mbvhs.push_back(std::move(m));
         const HostMbvh& s = *mbvhs.back();
         return RTMbvh{(uint32_t)(mbvhs.size() - 1), (uint32_t)s.m_nodes.size(), s.m_nodes.data(),
-                      (uint32_t)s.indices.size(), s.indices.data()};
+                      (uint32_t)s.index_count(), s.indices()};
     }
 } g_manager;
 
@@ -70,7 +70,7 @@ ResultCode create_bvh(const RTAabb* aabbs, size_t prim_count, const float* cente
     if (center_stride != 12 && center_stride != 16)              // lib.rs:441-449: assert! (panic) in the reference
         return fail("create_bvh: center_stride must be 12 or 16 bytes");
     if (prim_count == 0) return NoPrimitives;                    // src/bvh.rs:88-90
-    auto b = std::make_unique<HostBvh>();
+    auto b = std::make_shared<HostBvh>();
     const ResultCode rc = gpu_build_bvh(aabbs, prim_count, centers, center_stride, prims_per_leaf, (uint32_t)bvh_type, b.get());
     if (rc != Ok) return rc;
     *result = g_manager.store(std::move(b));
@@ -83,7 +83,7 @@ ResultCode rtbvh_gpu_create_bvh_triangles(const float* vertices, size_t vertex_s
     if (!vertices || !result) return Error;
     if (vertex_stride != 12 && vertex_stride != 16) return fail("vertex_stride must be 12 or 16 bytes");
     if (triangle_count == 0) return NoPrimitives;
-    auto b = std::make_unique<HostBvh>();
+    auto b = std::make_shared<HostBvh>();
     const ResultCode rc = gpu_build_bvh_triangles(vertices, vertex_stride, triangle_count, prims_per_leaf, (uint32_t)bvh_type, b.get());
     if (rc != Ok) return rc;
     *result = g_manager.store(std::move(b));
@@ -94,12 +94,14 @@ ResultCode rtbvh_gpu_create_bvh_triangles(const float* vertices, size_t vertex_s
 // the struct's pointers are trusted like intersect() trusts them; the result is stored like create_mbvh's.
 ResultCode rtbvh_gpu_create_mbvh_from(const RTBvh* bvh, RTMbvh* mbvh) {
     if (!bvh || !mbvh || !bvh->nodes || !bvh->indices) return Error;
-    HostBvh copy;
-    copy.nodes.assign(bvh->nodes, bvh->nodes + bvh->node_count);
-    copy.indices.assign(bvh->indices, bvh->indices + bvh->index_count);
+    auto copy = std::make_shared<HostBvh>();  // the Mbvh's own clone of nodes and prim_indices (src/bvh.rs:399-403)
+    if (!copy->nodes.assign(bvh->nodes, bvh->nodes + bvh->node_count) ||
+        !copy->indices.assign(bvh->indices, bvh->indices + bvh->index_count))
+        return fail("rtbvh_gpu_create_mbvh_from: out of memory");
     auto m = std::make_unique<HostMbvh>();
-    const ResultCode rc = gpu_collapse(copy, m.get());
+    const ResultCode rc = gpu_collapse(*copy, m.get());
     if (rc != Ok) return rc;
+    m->base = copy;
     *mbvh = g_manager.store_mbvh(std::move(m));
     return Ok;
 }
@@ -119,6 +121,7 @@ ResultCode create_mbvh(RTBvh bvh, RTMbvh* mbvh) {
         if (bvh.id >= g_manager.bvhs.size()) return Error;       // MANAGER.get(..) == None
         const ResultCode rc = gpu_collapse(*g_manager.bvhs[bvh.id], m.get());
         if (rc != Ok) return rc;
+        m->base = g_manager.bvhs[bvh.id];
     }
     *mbvh = g_manager.store_mbvh(std::move(m));
     return Ok;
@@ -186,7 +189,7 @@ ResultCode intersect_mbvh_packet(RTMbvh bvh, const float* origin_x, const float*
 void free_bvh(RTBvh bvh) {                                        // lib.rs:838-842, :108-116
     std::unique_lock<std::shared_mutex> lk(g_manager.mu_bvh);
     if (bvh.id < g_manager.bvhs.size())
-        g_manager.bvhs[bvh.id] = std::make_unique<HostBvh>();
+        g_manager.bvhs[bvh.id] = std::make_shared<HostBvh>();
     else
         std::fprintf(stderr, "Could not free bvh with id: %u\n", bvh.id);
 }

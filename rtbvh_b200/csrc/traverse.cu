@@ -508,6 +508,9 @@ __device__ __forceinline__ bool packet_step(const DeviceTree& tree, RayRegs& r, 
 #ifndef RTB_TRI_DEN
 #define RTB_TRI_DEN 1
 #endif
+#ifndef RTB_PIPE
+#define RTB_PIPE 0  // 1: the node a lane visits next is fetched into registers as soon as it is known (end of the previous visit)
+#endif
 struct Lane {
     int cur;               // node to visit next (-1: none in hand: pop)
     int tri_pos, tri_end;  // leaf range in the leaf-ordered triangle records; T phase while tri_pos < tri_end
@@ -654,6 +657,61 @@ __device__ __forceinline__ void mbvh_node_phase(const DeviceTree& tree, const fl
         }
     }
 }
+// Software-pipelined flavour (RTB_PIPE): `nd` already holds node L.cur (loaded when L.cur became known); at the end the
+// NEXT node — the register hand-over or, without an inner hit, the popped entry — is fetched into `nd` right away, so its
+// L2 / L1 latency overlaps the pushes, the leaf bookkeeping, the loop overhead, a possible T phase and the other warps.
+template <bool EXACT>
+__device__ __forceinline__ void mbvh_node_phase_pipe(const DeviceTree& tree, MNode& nd, const RayRegs& r, Stack& st, Lane& L) {
+    float key[4];
+    const uint32_t mask = mbvh_slabs<EXACT>(nd.mnx, nd.mxx, nd.mny, nd.mxy, nd.mnz, nd.mxz, r, key);
+    const int4 ch = nd.ch, cn = nd.cn;
+    const uint32_t leafbits = (cn.x > -1 ? 1u : 0u) | (cn.y > -1 ? 2u : 0u) | (cn.z > -1 ? 4u : 0u) | (cn.w > -1 ? 8u : 0u);
+    const uint32_t childbits = (ch.x > -1 ? 1u : 0u) | (ch.y > -1 ? 2u : 0u) | (ch.z > -1 ? 4u : 0u) | (ch.w > -1 ? 8u : 0u);
+    const uint32_t leaves = mask & leafbits;
+    const uint32_t inner = mask & ~leafbits & childbits;
+    int pay[4] = {(inner & 1u) ? ch.x : -1, (inner & 2u) ? ch.y : -1, (inner & 4u) ? ch.z : -1, (inner & 8u) ? ch.w : -1};
+    RTB_CSWAP(0, 1)
+    RTB_CSWAP(2, 3)
+    RTB_CSWAP(0, 2)
+    RTB_CSWAP(1, 3)
+    if (key[2] > key[3]) {
+        int tp = pay[2];
+        pay[2] = pay[3];
+        pay[3] = tp;
+    }
+    int next = pay[0] >= 0 ? pay[0] : (pay[1] >= 0 ? pay[1] : (pay[2] >= 0 ? pay[2] : pay[3]));
+    const int skip = pay[0] >= 0 ? 0 : (pay[1] >= 0 ? 1 : (pay[2] >= 0 ? 2 : 3));
+    if (next < 0 && st.sp > 0) next = st.pop();  // no inner hit: the next node is the top of the stack (popped before the leaf entries of this node go on top)
+    if (next >= 0) nd = mnode_load_global(tree.nodes, next);
+    if (inner) {
+        if (skip < 3 && pay[3] >= 0) st.push(pay[3]);
+        if (skip < 2 && pay[2] >= 0) st.push(pay[2]);
+        if (skip < 1 && pay[1] >= 0) st.push(pay[1]);
+    }
+    L.cur = next;
+    if (leaves) {
+        const int s0 = __ffs(leaves) - 1;
+        const int c0 = sel4(cn, s0), f0 = sel4(ch, s0);
+        L.tri_pos = f0;
+        L.tri_end = f0 + (c0 > 0 ? c0 : 0);
+        uint32_t rest = leaves & (leaves - 1);
+        while (rest) {
+            const int s = __ffs(rest) - 1;
+            rest &= rest - 1;
+            lane_take_leaf(st, L, sel4(ch, s), sel4(cn, s));
+        }
+    }
+}
+// lane_advance of the pipelined flavour: L.cur is always the next node already (-1: none left)
+__device__ __forceinline__ bool lane_advance_pipe(Stack& st, Lane& L) {
+    if (L.pend > 0) {
+        pop_leaf(st, L.tri_pos, L.tri_end);
+        L.pend--;
+        return false;
+    }
+    return L.cur < 0;
+}
+
 // N phase, Bvh: one popped node (the root is popped without a box test, iter_indices.rs:32-46).
 __device__ __forceinline__ void bvh_node_phase(const DeviceTree& tree, const RayRegs& r, Stack& st, Lane& L) {
     const float4* __restrict__ nodes = tree.nodes;
@@ -789,7 +847,7 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
     const float4* top_s = nullptr;
     if constexpr (kTopK > 0 && PHASED && TREE == RT_TREE_MBVH) {
         float4* t = reinterpret_cast<float4*>(dyn_smem + (size_t)kSmemStack * kPBlock * sizeof(int));
-        const uint32_t cnt = tree.top_count < (uint32_t)kTopK ? tree.top_count : (uint32_t)kTopK;
+        const uint32_t cnt = min(tree.top_count, (uint32_t)kTopK);
         for (uint32_t i = threadIdx.x; i < cnt * 8; i += kPBlock) t[(i >> 3) * kTopRow + (i & 7)] = __ldg(tree.top + i);
         __syncthreads();
         top_s = t;
@@ -801,6 +859,8 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
     RayRegs r;
     int cur = 0;
     Lane L{-1, 0, 0, 0};
+    constexpr bool PIPE = RTB_PIPE && PHASED && TREE == RT_TREE_MBVH;
+    MNode nd;  // PIPE: the node L.cur, fetched ahead
     size_t my = 0;
     bool active = false;
     bool fin = false;  // the lane holds the record of a finished ray that is not stored yet (stored at the next refill, by
@@ -845,6 +905,13 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
                 }
                 if (!active && rank < take) {
                     my = (size_t)(res_next + rank);
+                    if (kRayChunk == 64 && pd.tile_w != 0 && my < pd.tile_n) {
+                        // chunk of 64 consecutive indices -> one 8x8 pixel tile of the same 8-row band (neighbouring lanes
+                        // then walk neighbouring parts of the tree: fewer distinct sectors per load instruction)
+                        const unsigned long long band = 8ull * pd.tile_w, b = my / band, rr = my % band;
+                        const unsigned tx = (unsigned)(rr >> 6), j = (unsigned)(rr & 63u);
+                        my = (size_t)(b * band + (unsigned long long)(j >> 3) * pd.tile_w + tx * 8u + (j & 7u));
+                    }
                     if (perm) my = (size_t)perm[my];
                     if (pd.directions)
                         load_ray_od(reinterpret_cast<const float*>(rays), pd, my, r);
@@ -855,10 +922,12 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
                     st.reset();
                     cur = 0;
                     L = Lane{(kTopK > 0 && PHASED && TREE == RT_TREE_MBVH && tree.top_count != 0) ? kTopFlag : 0, 0, 0, 0};
-                    if (tree.node_count != 0 && !r.nan)
+                    if (tree.node_count != 0 && !r.nan) {
                         active = true;
-                    else
+                        if constexpr (PIPE) nd = mnode_load_global(tree.nodes, 0);
+                    } else {
                         fin = true;
+                    }
                 }
                 res_next += take;
                 idle = __ballot_sync(0xFFFFFFFFu, !active);
@@ -885,13 +954,21 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
                     if (ANY && hit)
                         done = true;
                     else if (L.tri_pos >= L.tri_end)
-                        done = lane_advance(st, L);
+                        done = PIPE ? lane_advance_pipe(st, L) : lane_advance(st, L);
                 }
             } else {
                 // slabs with the SSE operand rule for the whole warp as soon as one visiting lane needs it (a zero /
                 // non-finite component): for every other ray both flavours give the same predicates and keys
                 const bool any_exact = TREE == RT_TREE_MBVH && __any_sync(0xFFFFFFFFu, in_n && r.exact) != 0;
-                if (in_n) {
+                if constexpr (PIPE) {
+                    if (in_n) {
+                        if (any_exact)
+                            mbvh_node_phase_pipe<true>(tree, nd, r, st, L);
+                        else
+                            mbvh_node_phase_pipe<false>(tree, nd, r, st, L);
+                        if (L.tri_pos >= L.tri_end) done = lane_advance_pipe(st, L);
+                    }
+                } else if (in_n) {
                     if (TREE == RT_TREE_MBVH) {
                         if (any_exact)
                             mbvh_node_phase<true>(tree, top_s, r, st, L);

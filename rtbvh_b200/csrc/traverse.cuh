@@ -27,6 +27,10 @@ struct PeerDests {
     // of direction per ray, and t_min / t_max apply to every ray — 24 instead of 32 bytes per ray across PCIe.
     const float* directions;
     float t_min, t_max;
+    // Image-ordered batches (rtbvh_gpu_scene_set_ray_tiling): rows of `tile_w` rays; the persistent kernels hand out the rays
+    // of the first `tile_n` indices as 8x8 pixel tiles instead of 64-ray row segments (work order only; 0 = off).
+    uint32_t tile_w;
+    unsigned long long tile_n;
 };
 // sort_bounds: null = trace in the caller's order; else {min xyz, max xyz} of the scene: the batch is traced in
 // Morton order of (origin, direction) and results are scattered back (same results, better coherence).

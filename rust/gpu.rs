@@ -170,6 +170,7 @@ pub mod sys {
         pub fn rtbvh_gpu_scene_refit_device(scene: RTGpuScene, d_vertices: *const f32, vertex_stride: usize, triangle_count: usize, stream: *mut c_void) -> ResultCode;
         pub fn rtbvh_gpu_scene_read_nodes(scene: RTGpuScene, tree: RTTreeKind, out: *mut c_void, bytes: usize) -> ResultCode;
         pub fn rtbvh_gpu_scene_set_ray_sorting(scene: RTGpuScene, enable: c_int) -> ResultCode;
+        pub fn rtbvh_gpu_scene_set_ray_tiling(scene: RTGpuScene, row_length: u32) -> ResultCode;
 
         // ---- closest hit / any hit, host buffers ---------------------------------------------------------------
         pub fn rtbvh_gpu_intersect(scene: RTGpuScene, tree: RTTreeKind, rays: *const RTRay, ray_count: usize, hits: *mut RTHit) -> ResultCode;
@@ -553,6 +554,12 @@ impl GpuScene {
     /// Trace incoherent batches (shadow / bounce rays) in Morton order of (origin, direction); results unchanged.
     pub fn set_ray_sorting(&mut self, enable: bool) -> Result<(), GpuError> {
         check(unsafe { sys::rtbvh_gpu_scene_set_ray_sorting(self.handle, enable as c_int) })
+    }
+
+    /// Image-ordered batches (primary rays, `row_length` pixels per row): the device-pointer calls trace 8x8 pixel tiles
+    /// (work order only; results unchanged; 0 = off).
+    pub fn set_ray_tiling(&mut self, row_length: u32) -> Result<(), GpuError> {
+        check(unsafe { sys::rtbvh_gpu_scene_set_ray_tiling(self.handle, row_length) })
     }
 
     /// The device copy of the binary tree (after `build` or `refit`), in the crate's format.
