@@ -45,7 +45,7 @@ WIDTH = HEIGHT = 1000
 N_TRIS = 1 << 20
 
 
-from bench_common import ClockSampler, host_threads, log, measured_peak_gbs, ncu_traffic  # noqa: E402,F401
+from bench_common import ClockSampler, bind_to_gpu_numa_node, host_threads, log, measured_peak_gbs, ncu_traffic  # noqa: E402,F401
 
 
 def build_scene_host():
@@ -152,9 +152,11 @@ def run_gpu(args):
     api.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    all_cpus = set(os.sched_getaffinity(0))
+    numa = bind_to_gpu_numa_node(local) if os.environ.get("RTBVH_BENCH_NUMA", "1") == "1" else "off"
 
     tris = build_scene_host()
-    info = {}
+    info = {"host_numa": numa}
     if world == 1:
         bvh, mbvh, info = build_trees(api, tris, info, rank)
     else:
@@ -320,11 +322,32 @@ def run_gpu(args):
                                d_hits[(e2e_steps - 1) % n_host].cpu().view(torch.int32)))
     # the host-buffer path must agree with the resident path on the same rays
     same = bool(torch.equal(h_hits[0].view(torch.int32), d_hits[0].cpu().view(torch.int32)))
+    # the same steps with the primary rays generated on the device (rtbvh_gpu_intersect_camera_async): only the records cross
+    # PCIe.  Step k re-creates ring slot k's frames (same seed, same frame numbers), so its records must equal that slot's.
+    def cam_submit(k):
+        b = k % n_host
+        g = (rank * (args.steps + args.warmup) + b) * fps
+        return scene.intersect_camera_async(cam, fps, h_hits[b].data_ptr(), api.TREE_MBVH, jitter_seed=W.SEED_SOUP, first_frame=g)
+    for b in range(n_host):
+        h_hits[b].zero_()
+    scene.wait(cam_submit(0))
+    barrier()
+    tickets = []
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        if k >= 2:
+            scene.wait(tickets[k - 2])
+        tickets.append(cam_submit(k))
+    scene.wait(0)
+    e2e_cam_ms = (time.perf_counter() - t0) * 1e3
+    same_cam = bool(torch.equal(h_hits[(e2e_steps - 1) % n_host].view(torch.int32),
+                                d_hits[(e2e_steps - 1) % n_host].cpu().view(torch.int32)))
 
-    t = torch.tensor([ms, e2e_ms, e2e_sync_ms, e2e_rtray_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_ms, e2e_sync_ms, e2e_rtray_ms, e2e_cam_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, e2e_sync_ms, e2e_rtray_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms, e2e_ms, e2e_sync_ms, e2e_rtray_ms, e2e_cam_ms = (float(x) for x in t)
+    os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every host core again
 
     if rank == 0:
         total_rays = world * args.steps * rays_per_step
@@ -377,7 +400,11 @@ def run_gpu(args):
             "clocks": clocks, "gpu_launches": args.steps,
             "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": rays_per_step * 24,
                     "d2h_bytes_per_step": rays_per_step * 8, "steps": e2e_steps,
-                    "host_equals_resident": same and same_async and same_od,
+                    "host_equals_resident": same and same_async and same_od and same_cam,
+                    "camera_value": world * e2e_steps * rays_per_step / e2e_cam_ms / 1e3,
+                    "camera_call": "rtbvh_gpu_intersect_camera_async + rtbvh_gpu_wait: primary rays generated on the device from the "
+                                   "camera (64 B of parameters per step), host hit records out every step, two steps in flight; "
+                                   f"h2d 0, d2h {rays_per_step * 8} B per step",
                     "call": "rtbvh_gpu_intersect_od_async + rtbvh_gpu_wait: pinned host origins[3n] + directions[3n] in (the "
                             "reference FFI's argument shape, 24 B per ray), host hit records out every step, two steps in "
                             "flight (double-buffered)",
@@ -412,8 +439,17 @@ def build_trees(api, tris, info, rank):
         st = api.last_build_stats()
         dev.append(st["device_ms"])
         tot.append(st["total_ms"])
-    mbvh = api.Mbvh.construct(bvh)
-    cst = api.last_build_stats()
+    # collapse through create_mbvh right behind create_bvh, like a caller of the reference's ABI: median of 3 (the first call
+    # also pins the host mirror's block, which later calls recycle — same warm-up rule as for the build above)
+    cdev, ctot, mbvh = [], [], None
+    for _ in range(4):
+        if mbvh is not None:
+            mbvh.free()
+        mbvh = api.Mbvh.construct(bvh)
+        cst = api.last_build_stats()
+        cdev.append(cst["device_ms"])
+        ctot.append(cst["total_ms"])
+    cst = {"device_ms": float(np.median(cdev[1:])), "total_ms": float(np.median(ctot[1:])), "first_call_total_ms": ctot[0]}
     # the same build straight into a device-resident scene (no host mirror): wall clock of the whole call from host
     # vertices, i.e. H2D of 36 MB of vertices + prims + binned SAH + collapse + triangle records
     api.Scene.build(tris, api.BINNED_SAH, 1, mbvh=True).free()
@@ -442,7 +478,8 @@ def build_trees(api, tris, info, rank):
                        "roofline": build_roofline,
                        "binned_sah_ms_per_mtri_incl_h2d_d2h": float(np.median(tot)) / mtri,
                        "binned_sah_device_ms_runs": dev, "collapse_device_ms": cst["device_ms"],
-                       "collapse_ms_incl_h2d_d2h": cst["total_ms"], "bvh_nodes": int(bvh.rt.node_count),
+                       "collapse_ms_incl_h2d_d2h": cst["total_ms"], "collapse_first_call_ms_incl_h2d_d2h": cst["first_call_total_ms"],
+                       "bvh_nodes": int(bvh.rt.node_count),
                        "mbvh_nodes": int(mbvh.rt.node_count),
                        "resident_scene_build_wall_ms": float(np.median(res_wall)),
                        "resident_scene_build_device_ms": float(np.median(res_dev)),

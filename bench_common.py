@@ -87,3 +87,27 @@ def host_threads():
         return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
         return max(1, os.cpu_count() or 1)
+
+
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Pins this process (and with it the first-touch placement of the pinned host buffers it allocates afterwards) to the CPUs
+    of the NUMA node its GPU hangs off.  torchrun sets no affinity: without this, a rank's staging buffers may sit on the other
+    socket and every H2D / D2H crosses the inter-socket link.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return f"gpu {bus}: no NUMA node reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return f"gpu {bus}: NUMA node {node} has no allowed CPU"
+        os.sched_setaffinity(0, allowed)
+        return f"gpu {bus}: bound to NUMA node {node} ({len(allowed)} CPUs)"
+    except Exception as e:  # never fatal: the bench runs unbound
+        return f"not bound ({type(e).__name__}: {e})"

@@ -220,6 +220,22 @@ ResultCode rtbvh_gpu_create_mbvh_from(const RTBvh *bvh, RTMbvh *mbvh);
  * inputs and the D2H of the host mirror; iterations = LOCB clustering iterations. */
 ResultCode rtbvh_gpu_last_build_stats(double *device_ms, double *total_ms, uint32_t *iterations);
 
+/* ---- primary rays generated on the device: nothing but the records crosses PCIe ------------------- */
+/* `frames` frames of width x height camera rays — the rays rtbvh_gpu_generate_camera_rays_device writes for frames
+ * first_frame .. first_frame + frames - 1, frame after frame, row-major — are generated in the staging slots, traced (in 8x8
+ * pixel tiles when width is a multiple of 8) and their records copied to the HOST buffer (hits: width*height*frames RTHit;
+ * occluded: as many bytes), chunk by chunk on the scene's pipeline streams.  Returns a ticket at once; rtbvh_gpu_wait as for
+ * the *_async calls.  This is the loop of examples/benchmark.rs (generate_ray per pixel, then traverse) without the 24-32
+ * bytes per ray of upload the host-ray calls pay: what remains on the bus is 8 bytes (1 byte) per ray of results. */
+ResultCode rtbvh_gpu_intersect_camera_async(RTGpuScene scene, RTTreeKind tree, const float pos[3], const float p1[3],
+                                            const float right[3], const float up[3], uint32_t width, uint32_t height,
+                                            uint64_t jitter_seed, uint64_t first_frame, uint32_t frames, RTHit *hits,
+                                            uint64_t *ticket);
+ResultCode rtbvh_gpu_occluded_camera_async(RTGpuScene scene, RTTreeKind tree, const float pos[3], const float p1[3],
+                                           const float right[3], const float up[3], uint32_t width, uint32_t height,
+                                           uint64_t jitter_seed, uint64_t first_frame, uint32_t frames, uint8_t *occluded,
+                                           uint64_t *ticket);
+
 /* ---- workload helper: CameraView3D::generate_ray on the device (shared/src/lib.rs:157-165) ----- */
 /* Writes width*rows rays for pixel rows [row0, row0+rows): u = (x + jx) / width, v = (y + jy) / height,
  * direction = normalize(p1 + u*right + v*up - pos); (jx, jy) = 0 when jitter_seed == 0, else

@@ -45,7 +45,7 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_scene_free", "rtbvh_gpu_intersect", "rtbvh_gpu_occluded", "rtbvh_gpu_intersect_packets",
                "rtbvh_gpu_occluded_packets", "rtbvh_gpu_intersect_device", "rtbvh_gpu_occluded_device",
                "rtbvh_gpu_intersect_packets_device", "rtbvh_gpu_occluded_packets_device",
-               "rtbvh_gpu_scene_stack_overflowed", "rtbvh_gpu_generate_camera_rays_device",
+               "rtbvh_gpu_scene_stack_overflowed", "rtbvh_gpu_generate_camera_rays_device", "rtbvh_gpu_intersect_camera_async", "rtbvh_gpu_occluded_camera_async",
                "rtbvh_gpu_create_bvh_triangles", "rtbvh_gpu_last_build_stats", "rtbvh_gpu_scene_set_ray_sorting", "rtbvh_gpu_scene_set_ray_tiling", "rtbvh_gpu_create_mbvh_from", "rtbvh_gpu_peer_buffer_create",
                "rtbvh_gpu_peer_buffer_open", "rtbvh_gpu_peer_buffer_close", "rtbvh_gpu_peer_buffer_free",
                "rtbvh_gpu_intersect_device_scatter", "rtbvh_gpu_occluded_device_scatter", "rtbvh_gpu_peer_barrier",
@@ -195,6 +195,9 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_last_build_stats.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u32)]
     L.rtbvh_gpu_generate_camera_rays_device.restype = rc
     L.rtbvh_gpu_generate_camera_rays_device.argtypes = [vp, vp, vp, vp, u32, u32, u32, u32, u64, u64, vp, vp]
+    for fn in (L.rtbvh_gpu_intersect_camera_async, L.rtbvh_gpu_occluded_camera_async):
+        fn.restype = rc
+        fn.argtypes = [u64, C.c_int, vp, vp, vp, vp, u32, u32, u64, u64, u32, vp, C.POINTER(u64)]
     _lib = L
     return L
 
@@ -510,6 +513,17 @@ class Scene:
                             t_max: float = 1e34, stream: int = 0):
         _check(lib().rtbvh_gpu_intersect_od_device(self.handle, tree, _dev_ptr(d_origins), _dev_ptr(d_directions), n, t_min,
                                                    t_max, _dev_ptr(d_hits), C.c_void_p(stream)))
+
+    def intersect_camera_async(self, cam: dict, frames: int, hits_ptr: int, tree: int = TREE_MBVH, jitter_seed: int = 0,
+                               first_frame: int = 0, any_hit: bool = False) -> int:
+        """rtbvh_gpu_intersect_camera_async / _occluded_camera_async: primary rays generated on the device, records to the
+        host buffer at `hits_ptr`; returns a ticket."""
+        keep = [np.ascontiguousarray(cam[k], dtype=np.float32) for k in ("pos", "p1", "right", "up")]
+        t = C.c_uint64(0)
+        fn = lib().rtbvh_gpu_occluded_camera_async if any_hit else lib().rtbvh_gpu_intersect_camera_async
+        _check(fn(self.handle, tree, _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]), cam["width"], cam["height"], jitter_seed,
+                  first_frame, frames, C.c_void_p(hits_ptr), C.byref(t)))
+        return t.value
 
     def wait(self, ticket: int = 0):
         _check(lib().rtbvh_gpu_wait(self.handle, ticket))

@@ -2034,6 +2034,16 @@ struct Arena {
         for (auto& c : chunks) c.used = 0;
         return cudaSuccess;
     }
+    // Position of the bump pointer, to rewind to later (what was handed out before the mark stays valid).
+    struct Mark {
+        size_t chunks = 0, used = 0;
+    };
+    Mark mark() const { return Mark{chunks.size(), chunks.empty() ? 0 : chunks.back().used}; }
+    void rewind(const Mark& m) {
+        if (m.chunks == 0 || m.chunks > chunks.size()) return;
+        for (size_t i = m.chunks; i < chunks.size(); i++) chunks[i].used = 0;
+        chunks[m.chunks - 1].used = m.used;
+    }
     cudaError_t grow(size_t cap) {
         Chunk c{nullptr, cap, 0};
         const auto t0 = std::chrono::steady_clock::now();
@@ -2044,6 +2054,7 @@ struct Arena {
     }
     cudaError_t take(size_t bytes, void** out) {
         bytes = (bytes + 255) & ~size_t(255);
+        // (after a rewind the bump pointer may sit in an earlier chunk: allocation always continues in the last one)
         if (chunks.empty() || chunks.back().cap - chunks.back().used < bytes) {
             const size_t last = chunks.empty() ? 0 : chunks.back().cap;
             const cudaError_t e = grow(std::max({bytes, last, size_t(64) << 20}));
@@ -2492,6 +2503,7 @@ struct LastTree {
     const void* d_nodes = nullptr;
     uint32_t node_count = 0;
     uint64_t epoch = 0;
+    Arena::Mark mark;  // end of the build's allocations: every in-place collapse starts from here again
 };
 static thread_local LastTree g_last_tree;
 static thread_local uint64_t g_arena_epoch = 1;
@@ -2517,7 +2529,7 @@ static ResultCode download(const DeviceBvh& d, HostBvh* out) {
     if (d.index_count) RTB_CUDA(cudaMemcpyAsync(out->indices.data(), d.indices.p, (size_t)d.index_count * 4, cudaMemcpyDeviceToHost, 0));
     RTB_CUDA(cudaStreamSynchronize(0));
     out->serial = ++g_build_serial;
-    g_last_tree = LastTree{out->serial, d.nodes.p, d.node_count, g_arena_epoch};
+    g_last_tree = LastTree{out->serial, d.nodes.p, d.node_count, g_arena_epoch, arena().mark()};
     return Ok;
 }
 
@@ -2601,6 +2613,7 @@ ResultCode gpu_collapse(const HostBvh& bvh, HostMbvh* out) {
     const bool resident = n_nodes != 0 && bvh.serial != 0 && g_last_tree.serial == bvh.serial && g_last_tree.node_count == n_nodes &&
                           g_last_tree.epoch == g_arena_epoch;
     if (resident) {
+        arena().rewind(g_last_tree.mark);  // repeated collapses of the same tree reuse the same workspace
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device: the builders run on the GPU only (no CPU fallback)");
     } else if (need_device() != Ok) {

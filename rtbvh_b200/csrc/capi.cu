@@ -1119,6 +1119,80 @@ ResultCode rtbvh_gpu_intersect_od_device(RTGpuScene h, RTTreeKind tree, const fl
     RTB_CUDA(launch_od(*s, *t, tree, false, d_origins, d_directions, n, t_min, t_max, d_hits, nullptr, (cudaStream_t)stream));
     return Ok;
 }
+// ---- primary rays generated on the device: no ray upload at all ---------------------------------------------------------
+// The batch is `frames` frames of width x height camera rays (CameraView3D::generate_ray, shared/src/lib.rs:157-165; the
+// arithmetic of rtbvh_gpu_generate_camera_rays_device).  Per chunk of whole frames (or of rows, when one frame exceeds a
+// staging slot): ray generation -> traversal in 8x8 tiles -> D2H of the records, on the pipeline streams, so consecutive
+// chunks and consecutive submissions overlap like the host-ray calls do.  Only the records cross PCIe.
+static ResultCode camera_call(RTGpuScene h, RTTreeKind tree, bool any, const float pos[3], const float p1[3], const float right[3],
+                              const float up[3], uint32_t width, uint32_t height, uint64_t seed, uint64_t first_frame,
+                              uint32_t frames, void* out, uint64_t* ticket) {
+    auto sp = get_scene(h);
+    if (!sp) return fail("unknown scene");
+    Scene& s = *sp;
+    const DeviceTree* t = pick_tree(s, tree);
+    if (!t) return fail("scene has no such tree");
+    if (!pos || !p1 || !right || !up || !ticket) return fail("null argument");
+    const size_t per_frame = (size_t)width * height, total = per_frame * frames;
+    if (total != 0 && !out) return fail("null host buffer");
+    std::unique_lock<std::mutex> lk(s.pipe_mutex);
+    DeviceGuard dg(s.device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
+    if (ensure_pipeline(s, gated_slot_rays(total)) != Ok) return Error;
+    const uint64_t id = s.next_ticket++;
+    Scene::Ticket& tk = s.tickets[id % kTickets];
+    if (tk.id != 0)
+        for (int i = 0; i < kPipeStreams; i++) RTB_CUDA(cudaEventSynchronize(tk.ev[i]));
+    const size_t unit_out = any ? 1 : sizeof(RTHit);
+    if (total != 0) {
+        // rows per chunk: whole frames while they fit a slot, else a multiple of 8 rows (tile bands)
+        size_t rows_per_chunk = s.slot_rays / width;
+        if (rows_per_chunk == 0) return fail("camera batch: a single row exceeds the staging slot");
+        if (rows_per_chunk >= height) rows_per_chunk = rows_per_chunk / height * height;
+        else if (rows_per_chunk >= 8) rows_per_chunk &= ~size_t(7);
+        const size_t total_rows = (size_t)height * frames;
+        for (size_t row = 0; row < total_rows; row += rows_per_chunk) {
+            const size_t rows = std::min(rows_per_chunk, total_rows - row);
+            const int k = (int)(s.chunk_seq++ % kPipeStreams);
+            cudaStream_t st = s.streams[k];
+            RTRay* d_rays = (RTRay*)s.d_in[k];
+            for (size_t r0 = row; r0 < row + rows;) {  // one generator launch per frame segment
+                const size_t f = r0 / height, y0 = r0 % height;
+                const size_t seg = std::min((size_t)height - y0, row + rows - r0);
+                RTB_CUDA(launch_camera_rays(pos, p1, right, up, width, height, (uint32_t)y0, (uint32_t)seg, seed, first_frame + f,
+                                            d_rays + (r0 - row) * width, st));
+                r0 += seg;
+            }
+            const size_t m = rows * width;
+            PeerDests pd{};
+            if (width % 8 == 0 && !s.sort_rays.load()) {
+                pd.tile_w = width;
+                pd.tile_n = (unsigned long long)(m / (8ull * width) * (8ull * width));
+                if (pd.tile_n == 0) pd.tile_w = 0;
+            }
+            RTB_CUDA(launch_trace_single(*t, tree, any, d_rays, m, any ? nullptr : (RTHit*)s.d_out[k], any ? (uint8_t*)s.d_out[k] : nullptr,
+                                         s.counter_slot(), s.d_overflow, persistent_mode(), s.sort_bounds(), pd.tile_w ? &pd : nullptr, st));
+            RTB_CUDA(cudaMemcpyAsync((char*)out + row * width * unit_out, s.d_out[k], m * unit_out, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int i = 0; i < kPipeStreams; i++) {
+        if (!tk.ev[i]) RTB_CUDA(cudaEventCreateWithFlags(&tk.ev[i], cudaEventDisableTiming));
+        RTB_CUDA(cudaEventRecord(tk.ev[i], s.streams[i]));
+    }
+    tk.id = id;
+    *ticket = id;
+    return Ok;
+}
+ResultCode rtbvh_gpu_intersect_camera_async(RTGpuScene h, RTTreeKind tree, const float pos[3], const float p1[3], const float right[3],
+                                            const float up[3], uint32_t width, uint32_t height, uint64_t jitter_seed,
+                                            uint64_t first_frame, uint32_t frames, RTHit* hits, uint64_t* ticket) {
+    return camera_call(h, tree, false, pos, p1, right, up, width, height, jitter_seed, first_frame, frames, hits, ticket);
+}
+ResultCode rtbvh_gpu_occluded_camera_async(RTGpuScene h, RTTreeKind tree, const float pos[3], const float p1[3], const float right[3],
+                                           const float up[3], uint32_t width, uint32_t height, uint64_t jitter_seed,
+                                           uint64_t first_frame, uint32_t frames, uint8_t* occluded, uint64_t* ticket) {
+    return camera_call(h, tree, true, pos, p1, right, up, width, height, jitter_seed, first_frame, frames, occluded, ticket);
+}
 ResultCode rtbvh_gpu_wait(RTGpuScene h, uint64_t ticket) {
     auto s = get_scene(h);
     if (!s) return fail("unknown scene");

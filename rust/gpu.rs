@@ -210,6 +210,8 @@ pub mod sys {
         pub fn rtbvh_gpu_last_build_stats(device_ms: *mut f64, total_ms: *mut f64, iterations: *mut u32) -> ResultCode;
 
         // ---- workload helper --------------------------------------------------------------------------------------
+        pub fn rtbvh_gpu_intersect_camera_async(scene: RTGpuScene, tree: RTTreeKind, pos: *const f32, p1: *const f32, right: *const f32, up: *const f32, width: u32, height: u32, jitter_seed: u64, first_frame: u64, frames: u32, hits: *mut RTHit, ticket: *mut u64) -> ResultCode;
+        pub fn rtbvh_gpu_occluded_camera_async(scene: RTGpuScene, tree: RTTreeKind, pos: *const f32, p1: *const f32, right: *const f32, up: *const f32, width: u32, height: u32, jitter_seed: u64, first_frame: u64, frames: u32, occluded: *mut u8, ticket: *mut u64) -> ResultCode;
         pub fn rtbvh_gpu_generate_camera_rays_device(pos: *const f32, p1: *const f32, right: *const f32, up: *const f32, width: u32, height: u32, row0: u32, rows: u32, jitter_seed: u64, frame: u64, d_rays: *mut RTRay, stream: *mut c_void) -> ResultCode;
     }
 }

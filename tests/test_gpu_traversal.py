@@ -175,6 +175,60 @@ def test_device_resident_api_and_camera_rays(A, O, W, teapot, teapot_trees):
     sc.free()
 
 
+def test_ray_tiling_and_camera_calls(A, O, W, teapot, teapot_trees):
+    """rtbvh_gpu_scene_set_ray_tiling is a work-order hint: 8x8 pixel tiles per warp, every record unchanged and at its
+    ray's index (whole 8-row bands are tiled, the tail keeps the linear order).  rtbvh_gpu_intersect_camera_async /
+    _occluded_camera_async generate the frames on the device and must deliver exactly the records of
+    generate_camera_rays_device + intersect_device, which in turn equal the oracle's on the very same rays."""
+    import torch
+    bvh, m = teapot_trees["sah"]
+    tris = teapot["tris"]
+    sc = _scene(A, tris, bvh, m)
+    stream = torch.cuda.current_stream().cuda_stream
+    try:
+        for (w, h, frames) in ((400, 400, 2), (200, 52, 3), (8, 8, 1), (1000, 24, 1)):
+            cam = W.benchmark_camera(w, h)
+            n = w * h * frames
+            d_rays = torch.empty(n * 8, dtype=torch.float32, device="cuda")
+            for f in range(frames):
+                A.generate_camera_rays_device(cam, 0, h, d_rays[f * w * h * 8:], jitter_seed=77, frame=5 + f, stream=stream)
+            torch.cuda.synchronize()
+            rays = d_rays.cpu().numpy().view(A.RAY_DTYPE).reshape(-1)
+            for tree, otree in ((A.TREE_MBVH, m), (A.TREE_BVH, bvh)):
+                want = O.trace(otree, tris, rays)[0]
+                want_occ = O.trace(otree, tris, rays, mode="any")[0]
+                d_hits = torch.zeros(n * 2, dtype=torch.float32, device="cuda")
+                d_occ = torch.zeros(n, dtype=torch.uint8, device="cuda")
+                sc.set_ray_tiling(w)
+                sc.intersect_device(d_rays, n, d_hits, tree, stream=stream)
+                sc.occluded_device(d_rays, n, d_occ, tree, stream=stream)
+                torch.cuda.synchronize()
+                sc.set_ray_tiling(0)
+                assert np.array_equal(d_hits.cpu().numpy().view(A.HIT_DTYPE).reshape(-1), want), (w, h, frames, tree)
+                assert np.array_equal(d_occ.cpu().numpy(), want_occ), (w, h, frames, tree)
+                # a batch that is not a whole number of bands: the tail is traced in linear order
+                sc.set_ray_tiling(w)
+                d_hits.zero_()
+                sc.intersect_device(d_rays, n - 3, d_hits, tree, stream=stream)
+                torch.cuda.synchronize()
+                sc.set_ray_tiling(0)
+                assert np.array_equal(d_hits.cpu().numpy().view(A.HIT_DTYPE).reshape(-1)[: n - 3], want[: n - 3])
+                # frames generated on the device inside the call, records straight to the host
+                hh = torch.zeros(n * 2, dtype=torch.float32).pin_memory()
+                ho = torch.zeros(n, dtype=torch.uint8).pin_memory()
+                t1 = sc.intersect_camera_async(cam, frames, hh.data_ptr(), tree, jitter_seed=77, first_frame=5)
+                t2 = sc.intersect_camera_async(cam, frames, ho.data_ptr(), tree, jitter_seed=77, first_frame=5, any_hit=True)
+                sc.wait(t2)
+                sc.wait(t1)
+                assert np.array_equal(hh.numpy().view(A.HIT_DTYPE).reshape(-1), want), (w, h, frames, tree)
+                assert np.array_equal(ho.numpy(), want_occ), (w, h, frames, tree)
+        with pytest.raises(A.RtbvhError):
+            sc.set_ray_tiling(12)  # not a multiple of 8
+        assert not sc.stack_overflowed()
+    finally:
+        sc.free()
+
+
 def test_full_size_properties_soup_1m(A, O, W):
     """BASELINE config 2 at full geometry size: oracle parity on a sample plus size-independent properties
     (any-hit == closest-hit predicate; a closest hit re-traced with t = t_hit*(1+1e-3) finds the same t)."""

@@ -94,7 +94,7 @@ def rust_functions():
 
 def test_extern_block_matches_the_headers():
     c, r = c_functions(), rust_functions()
-    assert len(c) == 55
+    assert len(c) == 57
     assert sorted(c) == sorted(r), f"only in headers: {sorted(set(c) - set(r))}; only in gpu.rs: {sorted(set(r) - set(c))}"
     for name in sorted(c):
         assert c[name][1] == r[name][1], f"{name}: return type {r[name][1]} vs C {c[name][1]}"
