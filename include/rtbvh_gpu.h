@@ -186,6 +186,22 @@ ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene scene, uint32_t *overflow
  * finishes to dests[k][dest_offset + i] for every k — P2P stores over NVLink / NVSwitch, overlapped with the traversal,
  * no collective afterwards.  d_hits / d_occluded (local copy in ray order) may be null.  Synchronise the ranks (a
  * barrier after the stream has drained) before reading a gather buffer. */
+/* Scene replication (the tree is replicated, rays are sharded).  The scene is built or uploaded ONCE,
+ * on one GPU; every other GPU gets a byte-identical replica copied device to device over NVLink / NVSwitch — the trees
+ * never travel through host memory or a collective library.
+ *   one process per GPU:  rank 0 calls _export (cudaIpc handles of the scene's device arrays + sizes, a 512-byte POD the
+ *     caller ships out of band: MPI, torch.distributed, a pipe); every other rank calls _import with its own device
+ *     current: the handles are opened, the arrays copied into allocations of the importing rank, the handles closed.  The
+ *     exporting scene must stay alive (and must not be refitted) until every importer has returned — one barrier.
+ *   one process, several GPUs:  _clone copies the scene onto `device` with cudaMemcpyPeer.
+ * The replica is a full scene (traversal, refit, read-back), independent of the original afterwards. */
+typedef struct RTGpuSceneExport {
+  unsigned char bytes[512];
+} RTGpuSceneExport;
+ResultCode rtbvh_gpu_scene_export(RTGpuScene scene, RTGpuSceneExport *out);
+ResultCode rtbvh_gpu_scene_import(const RTGpuSceneExport *exported, RTGpuScene *scene);
+ResultCode rtbvh_gpu_scene_clone(RTGpuScene scene, int device, RTGpuScene *clone);
+
 ResultCode rtbvh_gpu_peer_buffer_create(size_t bytes, void **d_ptr, unsigned char *handle64);
 ResultCode rtbvh_gpu_peer_buffer_open(const unsigned char *handle64, void **d_ptr);
 ResultCode rtbvh_gpu_peer_buffer_close(void *d_ptr);

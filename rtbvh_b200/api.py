@@ -52,7 +52,8 @@ GPU_SYMBOLS = ("rtbvh_gpu_device_count", "rtbvh_gpu_set_device", "rtbvh_gpu_last
                "rtbvh_gpu_intersect_async", "rtbvh_gpu_occluded_async", "rtbvh_gpu_wait", "rtbvh_gpu_host_alloc",
                "rtbvh_gpu_host_free", "rtbvh_gpu_scene_refit", "rtbvh_gpu_scene_refit_device", "rtbvh_gpu_scene_read_nodes",
                "rtbvh_gpu_intersect_od", "rtbvh_gpu_occluded_od", "rtbvh_gpu_intersect_od_async", "rtbvh_gpu_occluded_od_async",
-               "rtbvh_gpu_intersect_od_device", "rtbvh_gpu_trim_workspace", "rtbvh_gpu_scene_build", "rtbvh_gpu_scene_build_device", "rtbvh_gpu_scene_tree_size", "rtbvh_gpu_scene_read_indices")
+               "rtbvh_gpu_intersect_od_device", "rtbvh_gpu_trim_workspace", "rtbvh_gpu_scene_build", "rtbvh_gpu_scene_build_device", "rtbvh_gpu_scene_tree_size", "rtbvh_gpu_scene_read_indices",
+               "rtbvh_gpu_scene_export", "rtbvh_gpu_scene_import", "rtbvh_gpu_scene_clone")
 
 
 class RTBvh(C.Structure):  # rtbvh_ffi/src/lib.rs:210-220
@@ -144,6 +145,12 @@ def lib() -> C.CDLL:
     L.rtbvh_gpu_create_bvh_triangles.argtypes = [vp, sz, sz, sz, u32, C.POINTER(RTBvh)]
     L.rtbvh_gpu_peer_buffer_create.restype = rc
     L.rtbvh_gpu_peer_buffer_create.argtypes = [sz, C.POINTER(vp), vp]
+    L.rtbvh_gpu_scene_export.restype = rc
+    L.rtbvh_gpu_scene_export.argtypes = [u64, vp]
+    L.rtbvh_gpu_scene_import.restype = rc
+    L.rtbvh_gpu_scene_import.argtypes = [vp, C.POINTER(u64)]
+    L.rtbvh_gpu_scene_clone.restype = rc
+    L.rtbvh_gpu_scene_clone.argtypes = [u64, C.c_int, C.POINTER(u64)]
     L.rtbvh_gpu_peer_buffer_open.restype = rc
     L.rtbvh_gpu_peer_buffer_open.argtypes = [vp, C.POINTER(vp)]
     L.rtbvh_gpu_peer_buffer_close.restype = rc
@@ -407,6 +414,38 @@ class Scene:
             _check(lib().rtbvh_gpu_scene_tree_size(self.handle, TREE_MBVH, C.byref(nn), None))
             self.n_mnodes = nn.value
         return self
+
+    def _adopt_sizes(self):
+        nn, ni = C.c_uint32(0), C.c_uint32(0)
+        self.n_nodes = self.n_indices = self.n_mnodes = 0
+        if lib().rtbvh_gpu_scene_tree_size(self.handle, TREE_BVH, C.byref(nn), C.byref(ni)) == 0:
+            self.n_nodes, self.n_indices = nn.value, ni.value
+        if lib().rtbvh_gpu_scene_tree_size(self.handle, TREE_MBVH, C.byref(nn), C.byref(ni)) == 0:
+            self.n_mnodes, self.n_indices = nn.value, ni.value
+        return self
+
+    def export_bytes(self) -> bytes:
+        """rtbvh_gpu_scene_export: 512 bytes (cudaIpc handles + sizes) another process turns into a replica with
+        Scene.import_bytes.  Keep this scene alive until every importer has returned."""
+        blob = C.create_string_buffer(512)
+        _check(lib().rtbvh_gpu_scene_export(self.handle, blob))
+        return blob.raw
+
+    @classmethod
+    def import_bytes(cls, blob: bytes) -> "Scene":
+        """rtbvh_gpu_scene_import: replica on the current device, copied device to device from the exporting process's GPU."""
+        self = cls.__new__(cls)
+        self.handle = C.c_uint64(0)
+        buf = C.create_string_buffer(bytes(blob), 512)
+        _check(lib().rtbvh_gpu_scene_import(buf, C.byref(self.handle)))
+        return self._adopt_sizes()
+
+    def clone(self, device: int) -> "Scene":
+        """rtbvh_gpu_scene_clone: replica on another GPU of this process (cudaMemcpyPeer)."""
+        other = Scene.__new__(Scene)
+        other.handle = C.c_uint64(0)
+        _check(lib().rtbvh_gpu_scene_clone(self.handle, int(device), C.byref(other.handle)))
+        return other._adopt_sizes()
 
     def read_indices(self, tree: int = TREE_BVH) -> np.ndarray:
         ni = C.c_uint32(0)

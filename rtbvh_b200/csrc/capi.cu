@@ -50,9 +50,13 @@ constexpr size_t kMinChunkRays = size_t(1) << 17;  // gated pipeline: smallest l
 constexpr int kReadySlots = 64;
 constexpr int kMarkSlots = 4096;
 
-// RTBVH_TRACE_MODE selects the single-ray kernel variant (A/B measurements); default: see kDefaultTraceMode
+// RTBVH_TRACE_MODE selects the single-ray kernel variant (A/B measurements).  Measured on B200, config 2 (1 Mi-triangle
+// soup, 8 M primary rays per launch, scripts/trace_ab.py, profiles/r5_trace_ab.md): persistent (one node visit + its leaf
+// slots per iteration) 1 887-1 889 Mrays/s; phased (warp-wide node / triangle phases) 1 780 with the majority rule, 1 862-1 877
+// with a triangle phase as soon as a third as many lanes wait for it; staged tree top (RTB_TOPK = 21 / 85 / 341 nodes in shared
+// memory) 1 844-1 860; software-pipelined node fetch 1 460.  Configs 4 / 5 (incoherent): 390 / 94 persistent, 393 / 90 phased.
 #ifndef RTB_DEFAULT_TRACE_MODE
-#define RTB_DEFAULT_TRACE_MODE kTracePhased
+#define RTB_DEFAULT_TRACE_MODE kTracePersistent
 #endif
 constexpr int kDefaultTraceMode = RTB_DEFAULT_TRACE_MODE;
 int persistent_mode() {
@@ -876,15 +880,168 @@ ResultCode rtbvh_gpu_scene_free(RTGpuScene h) {
     return Ok;
 }
 
-// Packets: measured (profiles/r1q_matrix.json vs r1h_matrix.json) the static quad-per-packet kernel beats the
-// persistent one by 2-35 % on every scene (coherent packets finish together, the refill bookkeeping only costs),
-// so it is the default; RTBVH_PACKET_MODE=persistent selects the refill kernel.
-int packet_mode() {
-    static const int v = [] {
+// ---- scene replication: build once, copy device to device ------------------------------------
+// The six device arrays of a scene, in this order: Bvh nodes, Bvh prim_indices, Bvh-order triangle records, Mbvh nodes,
+// Mbvh prim_indices, Mbvh-order triangle records (the last two usually alias the Bvh's: kSharedLeafOrder).
+namespace {
+constexpr uint32_t kExportMagic = 0x52544258u;  // "RTBX"
+constexpr uint32_t kHasBvh = 1u, kHasMbvh = 2u, kSharedLeafOrder = 4u;
+struct SceneBlob {
+    uint32_t magic, version;
+    int32_t device;
+    uint32_t flags, tri_count;
+    uint32_t bvh_nodes, bvh_indices, mbvh_nodes, mbvh_indices;
+    float bounds[6];
+    cudaIpcMemHandle_t handles[6];
+};
+static_assert(sizeof(SceneBlob) <= sizeof(RTGpuSceneExport), "export blob must fit the public POD");
+
+void scene_describe(const Scene& s, SceneBlob& b, const void* src[6], size_t bytes[6]) {
+    std::memset(&b, 0, sizeof(b));
+    b.magic = kExportMagic;
+    b.version = 1;
+    b.device = s.device;
+    b.tri_count = s.tri_count;
+    if (s.d_bvh_nodes) b.flags |= kHasBvh;
+    if (s.d_mbvh_nodes) b.flags |= kHasMbvh;
+    if (s.d_bvh_nodes && s.d_mbvh_nodes && s.d_tris_mbvh == s.d_tris_bvh) b.flags |= kSharedLeafOrder;
+    b.bvh_nodes = s.bvh.node_count;
+    b.bvh_indices = s.bvh.index_count;
+    b.mbvh_nodes = s.mbvh.node_count;
+    b.mbvh_indices = s.mbvh.index_count;
+    std::memcpy(b.bounds, s.bounds, sizeof(b.bounds));
+    const bool own_m = (b.flags & kHasMbvh) && !(b.flags & kSharedLeafOrder);
+    src[0] = s.d_bvh_nodes;   bytes[0] = (b.flags & kHasBvh) ? (size_t)b.bvh_nodes * 32 : 0;
+    src[1] = s.d_idx_bvh;     bytes[1] = (b.flags & kHasBvh) ? (size_t)b.bvh_indices * 4 : 0;
+    src[2] = s.d_tris_bvh;    bytes[2] = (b.flags & kHasBvh) ? (size_t)b.bvh_indices * sizeof(TriRec) : 0;
+    src[3] = s.d_mbvh_nodes;  bytes[3] = (b.flags & kHasMbvh) ? (size_t)b.mbvh_nodes * 128 : 0;
+    src[4] = s.d_idx_mbvh;    bytes[4] = own_m ? (size_t)b.mbvh_indices * 4 : 0;
+    src[5] = s.d_tris_mbvh;   bytes[5] = own_m ? (size_t)b.mbvh_indices * sizeof(TriRec) : 0;
+}
+
+// New scene on the CURRENT device from six source arrays that are readable from it: `src_device` >= 0 selects
+// cudaMemcpyPeer (clone inside one process), -1 a plain device-to-device copy (cudaIpc-mapped peer memory).
+ResultCode scene_replicate(const SceneBlob& b, const void* const src[6], const size_t bytes[6], int src_device, RTGpuScene* out) {
+    auto s = std::make_shared<Scene>();
+    RTB_CUDA(cudaGetDevice(&s->device));
+    RTB_CUDA(cudaMalloc(&s->d_overflow, sizeof(uint32_t)));
+    RTB_CUDA(cudaMemset(s->d_overflow, 0, sizeof(uint32_t)));
+    RTB_CUDA(cudaMalloc(&s->d_counters, kCounterSlots * sizeof(unsigned long long)));
+    void* dst[6] = {};
+    for (int k = 0; k < 6; k++) {
+        if (bytes[k] == 0) continue;
+        cudaError_t e = cudaMalloc(&dst[k], bytes[k]);
+        if (e == cudaSuccess)
+            e = src_device >= 0 ? cudaMemcpyPeer(dst[k], s->device, src[k], src_device, bytes[k])
+                                : cudaMemcpy(dst[k], src[k], bytes[k], cudaMemcpyDeviceToDevice);
+        // the scene owns whatever has been allocated so far (freed by ~Scene on the error path)
+        if (k == 0) s->d_bvh_nodes = dst[k];
+        if (k == 1) s->d_idx_bvh = (uint32_t*)dst[k];
+        if (k == 2) s->d_tris_bvh = (TriRec*)dst[k];
+        if (k == 3) s->d_mbvh_nodes = dst[k];
+        if (k == 4) s->d_idx_mbvh = (uint32_t*)dst[k];
+        if (k == 5) s->d_tris_mbvh = (TriRec*)dst[k];
+        if (e != cudaSuccess) return fail("scene replication: device-to-device copy failed", e);
+    }
+    s->tri_count = b.tri_count;
+    std::memcpy(s->bounds, b.bounds, sizeof(b.bounds));
+    if (b.flags & kHasBvh)
+        s->bvh = DeviceTree{(const float4*)s->d_bvh_nodes, b.bvh_nodes, s->d_tris_bvh, b.bvh_indices, nullptr, 0};
+    if (b.flags & kHasMbvh) {
+        if (b.flags & kSharedLeafOrder) {
+            s->d_idx_mbvh = s->d_idx_bvh;
+            s->d_tris_mbvh = s->d_tris_bvh;
+        }
+        s->mbvh = DeviceTree{(const float4*)s->d_mbvh_nodes, b.mbvh_nodes, s->d_tris_mbvh, b.mbvh_indices, nullptr, 0};
+        if (scene_build_top(*s, 0, true) != Ok) return Error;
+    }
+    RTB_CUDA(cudaDeviceSynchronize());
+    std::unique_lock<std::shared_mutex> lk(g_scenes.mu);
+    g_scenes.scenes.push_back(s);
+    *out = (RTGpuScene)g_scenes.scenes.size();
+    return Ok;
+}
+}  // namespace
+
+ResultCode rtbvh_gpu_scene_export(RTGpuScene h, RTGpuSceneExport* out) {
+    auto s = get_scene(h);
+    if (!s || !out) return fail("rtbvh_gpu_scene_export: unknown scene / null argument");
+    DeviceGuard dg(s->device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
+    SceneBlob b;
+    const void* src[6];
+    size_t bytes[6];
+    scene_describe(*s, b, src, bytes);
+    RTB_CUDA(cudaDeviceSynchronize());  // builds / refits enqueued on the scene have finished before a peer reads it
+    for (int k = 0; k < 6; k++)
+        if (bytes[k]) RTB_CUDA(cudaIpcGetMemHandle(&b.handles[k], const_cast<void*>(src[k])));
+    std::memset(out, 0, sizeof(*out));
+    std::memcpy(out->bytes, &b, sizeof(b));
+    return Ok;
+}
+
+ResultCode rtbvh_gpu_scene_import(const RTGpuSceneExport* exported, RTGpuScene* scene) {
+    if (!exported || !scene) return fail("rtbvh_gpu_scene_import: null argument");
+    if (rtbvh_gpu_device_count() == 0) return fail("no CUDA device: the traversal path has no CPU fallback");
+    SceneBlob b;
+    std::memcpy(&b, exported->bytes, sizeof(b));
+    if (b.magic != kExportMagic || b.version != 1 || !(b.flags & (kHasBvh | kHasMbvh)))
+        return fail("rtbvh_gpu_scene_import: not a scene export of this library version");
+    const size_t want[6] = {(b.flags & kHasBvh) ? (size_t)b.bvh_nodes * 32 : 0,
+                            (b.flags & kHasBvh) ? (size_t)b.bvh_indices * 4 : 0,
+                            (b.flags & kHasBvh) ? (size_t)b.bvh_indices * sizeof(TriRec) : 0,
+                            (b.flags & kHasMbvh) ? (size_t)b.mbvh_nodes * 128 : 0,
+                            ((b.flags & kHasMbvh) && !(b.flags & kSharedLeafOrder)) ? (size_t)b.mbvh_indices * 4 : 0,
+                            ((b.flags & kHasMbvh) && !(b.flags & kSharedLeafOrder)) ? (size_t)b.mbvh_indices * sizeof(TriRec) : 0};
+    void* mapped[6] = {};
+    ResultCode rc = Ok;
+    for (int k = 0; k < 6 && rc == Ok; k++) {
+        if (!want[k]) continue;
+        const cudaError_t e = cudaIpcOpenMemHandle(&mapped[k], b.handles[k], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            mapped[k] = nullptr;
+            rc = fail("rtbvh_gpu_scene_import: cudaIpcOpenMemHandle (exports are opened by ANOTHER process; peer access needed)", e);
+        }
+    }
+    if (rc == Ok) rc = scene_replicate(b, mapped, want, -1, scene);
+    for (int k = 0; k < 6; k++)
+        if (mapped[k]) cudaIpcCloseMemHandle(mapped[k]);
+    return rc;
+}
+
+ResultCode rtbvh_gpu_scene_clone(RTGpuScene h, int device, RTGpuScene* clone) {
+    auto s = get_scene(h);
+    if (!s || !clone) return fail("rtbvh_gpu_scene_clone: unknown scene / null argument");
+    if (device < 0 || device >= rtbvh_gpu_device_count()) return fail("rtbvh_gpu_scene_clone: no such device");
+    SceneBlob b;
+    const void* src[6];
+    size_t bytes[6];
+    scene_describe(*s, b, src, bytes);
+    {
+        DeviceGuard dg(s->device);
+        if (!dg.ok()) return fail("cudaSetDevice", dg.err);
+        RTB_CUDA(cudaDeviceSynchronize());
+    }
+    DeviceGuard dg(device);
+    if (!dg.ok()) return fail("cudaSetDevice", dg.err);
+    return scene_replicate(b, src, bytes, s->device, clone);
+}
+
+// Packet kernels (RTBVH_PACKET_MODE = static | persistent | lane).  Measured on config 2's frames as packets of four
+// x-adjacent pixels (scripts/trace_ab.py --packets, profiles/r5_trace_ab.md): Mbvh closest hit static quad 1 135, persistent
+// quad 1 288, one lane per packet see there; Bvh static 406, persistent 360.  Default: Mbvh = lane, Bvh = static.
+int packet_mode(RTTreeKind tree) {
+    static const int forced = [] {
         const char* e = std::getenv("RTBVH_PACKET_MODE");
-        return (e && std::string(e) == "persistent") ? (int)kTracePersistent : (int)kTraceStatic;
+        if (!e) return -1;
+        const std::string m(e);
+        if (m == "persistent") return (int)kTracePersistent;
+        if (m == "static") return (int)kTraceStatic;
+        if (m == "lane") return (int)kTraceLane;
+        return -1;
     }();
-    return v;
+    if (forced >= 0) return forced;
+    return tree == RT_TREE_MBVH ? (int)kTraceLane : (int)kTraceStatic;
 }
 
 // ---- device-resident, asynchronous ---------------------------------------------------------------
@@ -922,7 +1079,7 @@ ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene h, RTTreeKind tree, con
     if (!t) return fail("scene has no such tree");
     if (!on_scene_device(*s)) return fail("the scene lives on another device than the current one (cudaSetDevice / rtbvh_gpu_set_device first)");
     RTB_CUDA(launch_trace_packets(*t, tree, false, d_packets, n, t_min, d_hits, nullptr, s->counter_slot(), s->d_overflow,
-                                  packet_mode(), (cudaStream_t)stream));
+                                  packet_mode(tree), (cudaStream_t)stream));
     return Ok;
 }
 ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* d_packets, size_t n,
@@ -933,7 +1090,7 @@ ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene h, RTTreeKind tree, cons
     if (!t) return fail("scene has no such tree");
     if (!on_scene_device(*s)) return fail("the scene lives on another device than the current one (cudaSetDevice / rtbvh_gpu_set_device first)");
     RTB_CUDA(launch_trace_packets(*t, tree, true, d_packets, n, t_min, nullptr, d_occ, s->counter_slot(), s->d_overflow,
-                                  packet_mode(), (cudaStream_t)stream));
+                                  packet_mode(tree), (cudaStream_t)stream));
     return Ok;
 }
 // ---- multi-GPU: gather fused into the traversal kernel (P2P stores into cudaIpc-mapped peer buffers) -----------
@@ -1218,7 +1375,7 @@ ResultCode rtbvh_gpu_intersect_packets(RTGpuScene h, RTTreeKind tree, const RTRa
                           [&](void* din, size_t m, void* dout, const unsigned long long*, cudaStream_t st) {
                               return launch_trace_packets(*t, tree, false, (const RTRayPacket4*)din, m, t_min,
                                                           (RTHitPacket4*)dout, nullptr, s->counter_slot(), s->d_overflow,
-                                                          packet_mode(), st);
+                                                          packet_mode(tree), st);
                           });
 }
 ResultCode rtbvh_gpu_occluded_packets(RTGpuScene h, RTTreeKind tree, const RTRayPacket4* packets, size_t n,
@@ -1230,7 +1387,7 @@ ResultCode rtbvh_gpu_occluded_packets(RTGpuScene h, RTTreeKind tree, const RTRay
     return run_host_batch(*s, packets, n, sizeof(RTRayPacket4), 4, 4, occluded,
                           [&](void* din, size_t m, void* dout, const unsigned long long*, cudaStream_t st) {
                               return launch_trace_packets(*t, tree, true, (const RTRayPacket4*)din, m, t_min, nullptr,
-                                                          (uint8_t*)dout, s->counter_slot(), s->d_overflow, packet_mode(), st);
+                                                          (uint8_t*)dout, s->counter_slot(), s->d_overflow, packet_mode(tree), st);
                           });
 }
 

@@ -499,69 +499,53 @@ __device__ __forceinline__ bool packet_step(const DeviceTree& tree, RayRegs& r, 
 // (iter_indices.rs:292-309), and with its non-conservative boxes the set of visited
 // nodes — hence the result — depends on that, so the order per ray stays the reference's; only the
 // interleaving BETWEEN rays changes.
-// Leaf ranges found at a node beyond the first are parked on the traversal stack, above the inner
-// entries pushed at the same node (tagged by the sign bit), and `pend` counts them.
+// Hit leaf slots of a node beyond the first stay with the lane as a 4-bit mask + the node's index
+// (Lane::pmask / pnode); their ranges are re-read from the node when the current range is used up.
 // ================================================================================================
 #ifndef RTB_TRI_NUM
-#define RTB_TRI_NUM 1  // tri phase is chosen when lanes_T * RTB_TRI_NUM >= lanes_N * RTB_TRI_DEN
+#define RTB_TRI_NUM 3  // tri phase is chosen when lanes_T * RTB_TRI_NUM >= lanes_N * RTB_TRI_DEN
+#endif
+#ifndef RTB_TRI_FLAT
+#define RTB_TRI_FLAT 1  // T phase: the triangle test without early exits (0: the branching test of the other kernels)
 #endif
 #ifndef RTB_TRI_DEN
 #define RTB_TRI_DEN 1
 #endif
-#ifndef RTB_PIPE
-#define RTB_PIPE 0  // 1: the node a lane visits next is fetched into registers as soon as it is known (end of the previous visit)
-#endif
 struct Lane {
     int cur;               // node to visit next (-1: none in hand: pop)
     int tri_pos, tri_end;  // leaf range in the leaf-ordered triangle records; T phase while tri_pos < tri_end
-    int pend;              // leaf ranges parked on the stack
+    int pnode;             // Mbvh: the node whose further hit leaf slots (pmask) are still to be tested
+    uint32_t pmask;
 };
-constexpr int kLeafTag = (int)0x80000000u;
-// one word when count < 32 and first < 2^26, else three (escape word on top)
-__device__ __forceinline__ void push_leaf(Stack& st, int first, int count) {
-    if (count < 32 && first < (1 << 26)) {
-        st.push(kLeafTag | (count << 26) | first);
+// Next pending leaf slot of node L.pnode: its (first, count) words are read again from the node (two scalar loads that hit L1:
+// the lane fetched this line a few instructions ago) instead of keeping eight registers alive or parking ranges on the stack.
+__device__ __forceinline__ void lane_next_leaf(const DeviceTree& tree, const float4* __restrict__ top_s, Lane& L) {
+    const int s = __ffs(L.pmask) - 1;
+    L.pmask &= L.pmask - 1;
+    int first, count;
+    if (kTopK > 0 && (L.pnode & kTopFlag)) {
+        const int* w = reinterpret_cast<const int*>(top_s + (L.pnode & ~kTopFlag) * kTopRow + 6);
+        first = w[s];
+        count = w[4 + s];
     } else {
-        st.push(count);
-        st.push(first);
-        st.push(kLeafTag);
+        const int* w = reinterpret_cast<const int*>(tree.nodes + (size_t)L.pnode * 8 + 6);
+        first = __ldg(w + s);
+        count = __ldg(w + 4 + s);
     }
+    L.tri_pos = first;
+    L.tri_end = first + count;
 }
-__device__ __forceinline__ void pop_leaf(Stack& st, int& first, int& end) {
-    const int v = st.pop();
-    int f, c;
-    if ((v & 0x7FFFFFFF) != 0) {
-        c = (v >> 26) & 31;
-        f = v & ((1 << 26) - 1);
-    } else {
-        f = st.pop();
-        c = st.pop();
-    }
-    first = f;
-    end = f + c;
-}
-// Called when the lane's current range is used up: next parked range, else the next node; true = ray finished.
-__device__ __forceinline__ bool lane_advance(Stack& st, Lane& L) {
-    if (L.pend > 0) {
-        pop_leaf(st, L.tri_pos, L.tri_end);
-        L.pend--;
-        return false;
+// Called when the lane's current range is used up: next pending leaf slot, else the next node; true = ray finished.
+__device__ __forceinline__ bool lane_advance(const DeviceTree& tree, const float4* __restrict__ top_s, Stack& st, Lane& L) {
+    while (L.pmask != 0) {
+        lane_next_leaf(tree, top_s, L);
+        if (L.tri_pos < L.tri_end) return false;
     }
     if (L.cur < 0) {
         if (st.sp == 0) return true;
         L.cur = st.pop();
     }
     return false;
-}
-__device__ __forceinline__ void lane_take_leaf(Stack& st, Lane& L, int first, int count) {
-    if (count <= 0) return;
-    if (L.tri_pos >= L.tri_end) {
-        L.tri_pos = first;
-        L.tri_end = first + count;
-    } else {
-        push_leaf(st, first, count);
-        L.pend++;
-    }
 }
 
 // SpatialTriangle::intersect without early exits (same operations, same predicates, evaluated in full): in a T-phase
@@ -643,75 +627,17 @@ __device__ __forceinline__ void mbvh_node_phase(const DeviceTree& tree, const fl
             if (skip < 1 && pay[1] >= 0) st.push(pay[1]);
         }
     }
+    const int node = L.cur;
     L.cur = next;
     if (leaves) {  // usually one slot: it becomes the lane's current range (the lane has none: it is in the N phase)
         const int s0 = __ffs(leaves) - 1;
         const int c0 = sel4(cn, s0), f0 = sel4(ch, s0);
         L.tri_pos = f0;
-        L.tri_end = f0 + (c0 > 0 ? c0 : 0);
-        uint32_t rest = leaves & (leaves - 1);
-        while (rest) {  // further hit leaf slots of the same node: parked on the stack
-            const int s = __ffs(rest) - 1;
-            rest &= rest - 1;
-            lane_take_leaf(st, L, sel4(ch, s), sel4(cn, s));
-        }
+        L.tri_end = f0 + c0;
+        L.pmask = leaves & (leaves - 1);  // further hit leaf slots of the same node: fetched when this range is used up
+        L.pnode = node;
     }
 }
-// Software-pipelined flavour (RTB_PIPE): `nd` already holds node L.cur (loaded when L.cur became known); at the end the
-// NEXT node — the register hand-over or, without an inner hit, the popped entry — is fetched into `nd` right away, so its
-// L2 / L1 latency overlaps the pushes, the leaf bookkeeping, the loop overhead, a possible T phase and the other warps.
-template <bool EXACT>
-__device__ __forceinline__ void mbvh_node_phase_pipe(const DeviceTree& tree, MNode& nd, const RayRegs& r, Stack& st, Lane& L) {
-    float key[4];
-    const uint32_t mask = mbvh_slabs<EXACT>(nd.mnx, nd.mxx, nd.mny, nd.mxy, nd.mnz, nd.mxz, r, key);
-    const int4 ch = nd.ch, cn = nd.cn;
-    const uint32_t leafbits = (cn.x > -1 ? 1u : 0u) | (cn.y > -1 ? 2u : 0u) | (cn.z > -1 ? 4u : 0u) | (cn.w > -1 ? 8u : 0u);
-    const uint32_t childbits = (ch.x > -1 ? 1u : 0u) | (ch.y > -1 ? 2u : 0u) | (ch.z > -1 ? 4u : 0u) | (ch.w > -1 ? 8u : 0u);
-    const uint32_t leaves = mask & leafbits;
-    const uint32_t inner = mask & ~leafbits & childbits;
-    int pay[4] = {(inner & 1u) ? ch.x : -1, (inner & 2u) ? ch.y : -1, (inner & 4u) ? ch.z : -1, (inner & 8u) ? ch.w : -1};
-    RTB_CSWAP(0, 1)
-    RTB_CSWAP(2, 3)
-    RTB_CSWAP(0, 2)
-    RTB_CSWAP(1, 3)
-    if (key[2] > key[3]) {
-        int tp = pay[2];
-        pay[2] = pay[3];
-        pay[3] = tp;
-    }
-    int next = pay[0] >= 0 ? pay[0] : (pay[1] >= 0 ? pay[1] : (pay[2] >= 0 ? pay[2] : pay[3]));
-    const int skip = pay[0] >= 0 ? 0 : (pay[1] >= 0 ? 1 : (pay[2] >= 0 ? 2 : 3));
-    if (next < 0 && st.sp > 0) next = st.pop();  // no inner hit: the next node is the top of the stack (popped before the leaf entries of this node go on top)
-    if (next >= 0) nd = mnode_load_global(tree.nodes, next);
-    if (inner) {
-        if (skip < 3 && pay[3] >= 0) st.push(pay[3]);
-        if (skip < 2 && pay[2] >= 0) st.push(pay[2]);
-        if (skip < 1 && pay[1] >= 0) st.push(pay[1]);
-    }
-    L.cur = next;
-    if (leaves) {
-        const int s0 = __ffs(leaves) - 1;
-        const int c0 = sel4(cn, s0), f0 = sel4(ch, s0);
-        L.tri_pos = f0;
-        L.tri_end = f0 + (c0 > 0 ? c0 : 0);
-        uint32_t rest = leaves & (leaves - 1);
-        while (rest) {
-            const int s = __ffs(rest) - 1;
-            rest &= rest - 1;
-            lane_take_leaf(st, L, sel4(ch, s), sel4(cn, s));
-        }
-    }
-}
-// lane_advance of the pipelined flavour: L.cur is always the next node already (-1: none left)
-__device__ __forceinline__ bool lane_advance_pipe(Stack& st, Lane& L) {
-    if (L.pend > 0) {
-        pop_leaf(st, L.tri_pos, L.tri_end);
-        L.pend--;
-        return false;
-    }
-    return L.cur < 0;
-}
-
 // N phase, Bvh: one popped node (the root is popped without a box test, iter_indices.rs:32-46).
 __device__ __forceinline__ void bvh_node_phase(const DeviceTree& tree, const RayRegs& r, Stack& st, Lane& L) {
     const float4* __restrict__ nodes = tree.nodes;
@@ -719,7 +645,8 @@ __device__ __forceinline__ void bvh_node_phase(const DeviceTree& tree, const Ray
     const int count = __float_as_int(nd.lo.w), left_first = __float_as_int(nd.hi.w);
     int next = -1;
     if (count > -1) {
-        lane_take_leaf(st, L, left_first, count);
+        L.tri_pos = left_first;
+        L.tri_end = left_first + count;
     } else if (left_first > -1) {
         const float4* c = nodes + (size_t)left_first * 2;
         const F8 lc = ld256(c), rc = ld256(c + 2);
@@ -858,9 +785,7 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
     Stack st{smem + threadIdx.x, deep, 0, overflow, kPBlock};
     RayRegs r;
     int cur = 0;
-    Lane L{-1, 0, 0, 0};
-    constexpr bool PIPE = RTB_PIPE && PHASED && TREE == RT_TREE_MBVH;
-    MNode nd;  // PIPE: the node L.cur, fetched ahead
+    Lane L{-1, 0, 0, 0, 0u};
     size_t my = 0;
     bool active = false;
     bool fin = false;  // the lane holds the record of a finished ray that is not stored yet (stored at the next refill, by
@@ -921,13 +846,11 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
                         load_ray(rays, my, r);
                     st.reset();
                     cur = 0;
-                    L = Lane{(kTopK > 0 && PHASED && TREE == RT_TREE_MBVH && tree.top_count != 0) ? kTopFlag : 0, 0, 0, 0};
-                    if (tree.node_count != 0 && !r.nan) {
+                    L = Lane{(kTopK > 0 && PHASED && TREE == RT_TREE_MBVH && tree.top_count != 0) ? kTopFlag : 0, 0, 0, 0, 0u};
+                    if (tree.node_count != 0 && !r.nan)
                         active = true;
-                        if constexpr (PIPE) nd = mnode_load_global(tree.nodes, 0);
-                    } else {
+                    else
                         fin = true;
-                    }
                 }
                 res_next += take;
                 idle = __ballot_sync(0xFFFFFFFFu, !active);
@@ -942,33 +865,31 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
                 }
             }
         } else {
+            // phase vote: T = lanes holding a triangle range, N = the other active lanes
+            const unsigned act_m = ~idle;  // idle was re-balloted by the refill; otherwise it is this iteration's ballot
             const bool in_t = active && L.tri_pos < L.tri_end;
+            const unsigned t_m = __ballot_sync(0xFFFFFFFFu, in_t);
+            const int n_t = __popc(t_m), n_n = __popc(act_m & ~t_m);
             const bool in_n = active && !in_t;
-            const int n_t = __popc(__ballot_sync(0xFFFFFFFFu, in_t));
-            const int n_n = __popc(__ballot_sync(0xFFFFFFFFu, in_n));
             bool done = false;
             if (n_t * RTB_TRI_NUM >= n_n * RTB_TRI_DEN && n_t > 0) {
                 if (in_t) {
+#if RTB_TRI_FLAT
                     const bool hit = tri_candidate_flat(tree.tris, L.tri_pos, r);
+#else
+                    const bool hit = tri_candidate<false>(tree.tris, L.tri_pos, r);
+#endif
                     L.tri_pos++;
                     if (ANY && hit)
                         done = true;
                     else if (L.tri_pos >= L.tri_end)
-                        done = PIPE ? lane_advance_pipe(st, L) : lane_advance(st, L);
+                        done = lane_advance(tree, top_s, st, L);
                 }
             } else {
                 // slabs with the SSE operand rule for the whole warp as soon as one visiting lane needs it (a zero /
                 // non-finite component): for every other ray both flavours give the same predicates and keys
                 const bool any_exact = TREE == RT_TREE_MBVH && __any_sync(0xFFFFFFFFu, in_n && r.exact) != 0;
-                if constexpr (PIPE) {
-                    if (in_n) {
-                        if (any_exact)
-                            mbvh_node_phase_pipe<true>(tree, nd, r, st, L);
-                        else
-                            mbvh_node_phase_pipe<false>(tree, nd, r, st, L);
-                        if (L.tri_pos >= L.tri_end) done = lane_advance_pipe(st, L);
-                    }
-                } else if (in_n) {
+                if (in_n) {
                     if (TREE == RT_TREE_MBVH) {
                         if (any_exact)
                             mbvh_node_phase<true>(tree, top_s, r, st, L);
@@ -977,7 +898,7 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
                     } else {
                         bvh_node_phase(tree, r, st, L);
                     }
-                    if (L.tri_pos >= L.tri_end) done = lane_advance(st, L);
+                    if (L.tri_pos >= L.tri_end) done = lane_advance(tree, top_s, st, L);
                 }
             }
             if (done) {
@@ -1230,6 +1151,262 @@ __global__ void __launch_bounds__(kBlock) trace_packet_persistent_kernel(const D
             }
         }
     }
+}
+
+// ================================================================================================
+// Mbvh packets, ONE LANE PER PACKET (the default Mbvh packet kernel).
+// With four lanes per packet every lane repeats the packet's control flow (stack, slot loop, leaf
+// bookkeeping) and the packet pays the union of its four rays' node visits in every lane.  Here one
+// lane owns the whole RayPacket4: the 16 ray x slot slab tests of a visit are 16 independent
+// dependency chains in ONE thread (instruction-level parallelism instead of occupancy), the control
+// flow is paid once per packet, and a node fetch (4 x LDG.256) is shared by four rays — a quarter of
+// the L1 data-pipe wavefronts per ray of the single-ray kernel.  Persistent warps, refill and the
+// warp-wide node / triangle phases are those of the phased single-ray kernel.
+// Semantics are MbvhPacketIndexIterator's (iter_indices.rs:370-414) + intersect4 (mbvh_node.rs:243-295,
+// spatial_sah.rs:165-244): a slot is entered when ANY ray passes `t_max > t_min && t_min < packet.t[i]`
+// with the packet.t of node entry, no ordering (inner slots pushed 3, 2, 1, 0), leaf slots yield every
+// primitive to the four-ray triangle test (eps 1e-6, t >= t_min).
+// ================================================================================================
+#ifndef RTB_LBLOCK
+#define RTB_LBLOCK 128
+#endif
+#ifndef RTB_LMINBLOCKS
+#define RTB_LMINBLOCKS 5  // 96 registers: measured 4 blocks (128 regs) 1 781-1 806, 5 blocks 2 008, 6 blocks (80 regs, spills) 1 795, 7 blocks 1 454 Mrays/s
+#endif
+constexpr int kLBlock = RTB_LBLOCK;
+#ifndef RTB_LKEEPDIR
+#define RTB_LKEEPDIR 0  // 1: keep the four directions in registers instead of re-reading them in the triangle phase
+#endif
+struct Packet {
+    float ox[4], oy[4], oz[4];
+#if RTB_LKEEPDIR
+    float dx[4], dy[4], dz[4];
+#endif
+    float ix[4], iy[4], iz[4];  // node visits need the inverse directions only; the triangle phase re-reads the directions
+    float t[4];                 // from the packet record (3 x LDG.128 per tested triangle: 12 registers less per lane)
+    uint32_t prim[4];
+};
+__device__ __forceinline__ void load_packet(const RTRayPacket4* __restrict__ packets, size_t p, Packet& k, bool& exact) {
+    const float4* q = reinterpret_cast<const float4*>(packets + p);  // 112-byte records: 16-byte aligned
+    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5),
+                 g = __ldg(q + 6);
+    k.ox[0] = a.x; k.ox[1] = a.y; k.ox[2] = a.z; k.ox[3] = a.w;
+    k.oy[0] = b.x; k.oy[1] = b.y; k.oy[2] = b.z; k.oy[3] = b.w;
+    k.oz[0] = c.x; k.oz[1] = c.y; k.oz[2] = c.z; k.oz[3] = c.w;
+    const float dx[4] = {d.x, d.y, d.z, d.w}, dy[4] = {e.x, e.y, e.z, e.w}, dz[4] = {f.x, f.y, f.z, f.w};
+    k.t[0] = g.x; k.t[1] = g.y; k.t[2] = g.z; k.t[3] = g.w;
+    bool fin = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        k.ix[i] = fdiv(1.0f, dx[i]);  // RayPacket4::new: inv_direction = 1 / direction (src/ray.rs:64-148)
+        k.iy[i] = fdiv(1.0f, dy[i]);
+        k.iz[i] = fdiv(1.0f, dz[i]);
+#if RTB_LKEEPDIR
+        k.dx[i] = dx[i]; k.dy[i] = dy[i]; k.dz[i] = dz[i];
+#endif
+        k.prim[i] = kNoHit;
+        fin = fin && isfinite(k.ox[i]) && isfinite(k.oy[i]) && isfinite(k.oz[i]) && isfinite(dx[i]) && isfinite(dy[i]) &&
+              isfinite(dz[i]) && isfinite(k.ix[i]) && isfinite(k.iy[i]) && isfinite(k.iz[i]);
+    }
+    exact = !fin;
+}
+// MbvhNode::intersect4 (mbvh_node.rs:243-281): `result |= ...` over the four rays; returns the 4-bit slot mask
+template <bool EXACT>
+__device__ __forceinline__ uint32_t mbvh_slabs_packet(const MNode& nd, const Packet& k) {
+    const float a_mnx[4] = {nd.mnx.x, nd.mnx.y, nd.mnx.z, nd.mnx.w}, a_mxx[4] = {nd.mxx.x, nd.mxx.y, nd.mxx.z, nd.mxx.w};
+    const float a_mny[4] = {nd.mny.x, nd.mny.y, nd.mny.z, nd.mny.w}, a_mxy[4] = {nd.mxy.x, nd.mxy.y, nd.mxy.z, nd.mxy.w};
+    const float a_mnz[4] = {nd.mnz.x, nd.mnz.y, nd.mnz.z, nd.mnz.w}, a_mxz[4] = {nd.mxz.x, nd.mxz.y, nd.mxz.z, nd.mxz.w};
+    uint32_t mask = 0;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float t1 = fmul(fsub(a_mnx[s], k.ox[i]), k.ix[i]), t2 = fmul(fsub(a_mxx[s], k.ox[i]), k.ix[i]);
+            float tmin = vmin<EXACT>(t1, t2), tmax = vmax<EXACT>(t1, t2);
+            t1 = fmul(fsub(a_mny[s], k.oy[i]), k.iy[i]);
+            t2 = fmul(fsub(a_mxy[s], k.oy[i]), k.iy[i]);
+            tmin = vmax<EXACT>(tmin, vmin<EXACT>(t1, t2));
+            tmax = vmin<EXACT>(tmax, vmax<EXACT>(t1, t2));
+            t1 = fmul(fsub(a_mnz[s], k.oz[i]), k.iz[i]);
+            t2 = fmul(fsub(a_mxz[s], k.oz[i]), k.iz[i]);
+            tmin = vmax<EXACT>(tmin, vmin<EXACT>(t1, t2));
+            tmax = vmin<EXACT>(tmax, vmax<EXACT>(t1, t2));
+            any = any || (tmax > tmin && tmin < k.t[i]);
+        }
+        if (any) mask |= 1u << s;
+    }
+    return mask;
+}
+// SpatialTriangle::intersect4 (spatial_sah.rs:165-244) for the four rays of the lane's packet, without early exits.
+// Returns the 4-bit mask of rays that accepted the candidate with t < packet.t[i].
+__device__ __forceinline__ uint32_t tri_candidate_packet(const TriRec* __restrict__ tris, int pos, float t_min,
+                                                         const RTRayPacket4* __restrict__ rec, Packet& k) {
+    const F8 ab = ld256(&tris[pos].a);
+    const float4 A = ab.lo, E1 = ab.hi;
+    const float4 E2 = __ldg(&tris[pos].c);
+    const uint32_t id = __float_as_uint(A.w);
+#if RTB_LKEEPDIR
+    const float* dx = k.dx; const float* dy = k.dy; const float* dz = k.dz;
+#else
+    const float4* q = reinterpret_cast<const float4*>(rec);
+    const float4 d = __ldg(q + 3), e = __ldg(q + 4), f4 = __ldg(q + 5);
+    const float dx[4] = {d.x, d.y, d.z, d.w}, dy[4] = {e.x, e.y, e.z, e.w}, dz[4] = {f4.x, f4.y, f4.z, f4.w};
+#endif
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float hx = fsub(fmul(dy[i], E2.z), fmul(E2.y, dz[i]));
+        const float hy = fsub(fmul(dz[i], E2.x), fmul(E2.z, dx[i]));
+        const float hz = fsub(fmul(dx[i], E2.y), fmul(E2.x, dy[i]));
+        const float a = fadd(fadd(fmul(E1.x, hx), fmul(E1.y, hy)), fmul(E1.z, hz));
+        const bool p_a = (a <= -1e-6f || a >= 1e-6f);  // spatial_sah.rs:191-196
+        const float f = fdiv(1.0f, a);
+        const float sx = fsub(k.ox[i], A.x), sy = fsub(k.oy[i], A.y), sz = fsub(k.oz[i], A.z);
+        const float u = fmul(f, fadd(fadd(fmul(sx, hx), fmul(sy, hy)), fmul(sz, hz)));
+        const bool p_u = (u >= 0.0f && u <= 1.0f);
+        const float qx = fsub(fmul(sy, E1.z), fmul(E1.y, sz));
+        const float qy = fsub(fmul(sz, E1.x), fmul(E1.z, sx));
+        const float qz = fsub(fmul(sx, E1.y), fmul(E1.x, sy));
+        const float v = fmul(f, fadd(fadd(fmul(dx[i], qx), fmul(dy[i], qy)), fmul(dz[i], qz)));
+        const bool p_v = (v >= 0.0f && fadd(u, v) <= 1.0f);  // spatial_sah.rs:218-222
+        const float t = fmul(f, fadd(fadd(fmul(E2.x, qx), fmul(E2.y, qy)), fmul(E2.z, qz)));
+        const bool ok = p_a && p_u && p_v && (t >= t_min);
+        const bool closer = ok && t < k.t[i];
+        const bool tie = ok && k.prim[i] != kNoHit && t == k.t[i] && id < k.prim[i];
+        if (closer) k.t[i] = t;
+        if (closer || tie) k.prim[i] = id;
+        if (closer) acc |= 1u << i;
+    }
+    return acc;
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(kLBlock, RTB_LMINBLOCKS) trace_mbvh_packet_lane_kernel(
+    const DeviceTree tree, const RTRayPacket4* __restrict__ packets, size_t n_packets, float t_min,
+    RTHitPacket4* __restrict__ hits, uint8_t* __restrict__ occluded, unsigned long long* __restrict__ counter,
+    uint32_t* __restrict__ overflow) {
+    __shared__ int smem[kSmemStack * kLBlock];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int deep[kSpillStack];
+    Stack st{smem + threadIdx.x, deep, 0, overflow, kLBlock};
+    Packet k;
+    bool exact = false;
+    uint32_t retired = 0;  // any hit: rays of the packet that are done (their t is -1e34, see rtbvh_gpu.h)
+    Lane L{-1, 0, 0, 0, 0u};
+    size_t my = 0;
+    bool active = false, fin = false;
+    unsigned long long res_next = 0, res_end = 0;
+    bool exhausted = false;
+    constexpr unsigned kPacketChunk = 32;  // packets a warp reserves per global atomic: one full refill
+    auto store = [&]() {
+        if (ANY) {
+            const uint32_t v = (retired & 1u) | ((retired & 2u) << 7) | ((retired & 4u) << 14) | ((retired & 8u) << 21);
+            reinterpret_cast<uint32_t*>(occluded)[my] = v;
+        } else {
+            float4* o = reinterpret_cast<float4*>(hits + my);
+            o[0] = make_float4(k.t[0], k.t[1], k.t[2], k.t[3]);
+            o[1] = make_float4(__uint_as_float(k.prim[0]), __uint_as_float(k.prim[1]), __uint_as_float(k.prim[2]),
+                               __uint_as_float(k.prim[3]));
+        }
+    };
+    for (;;) {
+        unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (idle == 0xFFFFFFFFu || (!exhausted && __popc(idle) >= kRefillIdle)) {
+            while (idle != 0 && !exhausted) {
+                if (res_next >= res_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(counter, (unsigned long long)kPacketChunk);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (base >= n_packets) {
+                        exhausted = true;
+                        break;
+                    }
+                    res_next = base;
+                    res_end = base + kPacketChunk < n_packets ? base + kPacketChunk : n_packets;
+                }
+                const unsigned long long avail = res_end - res_next;
+                const unsigned want = __popc(idle);
+                const unsigned take = avail < want ? (unsigned)avail : want;
+                const unsigned rank = __popc(idle & lt_mask);
+                if (__any_sync(0xFFFFFFFFu, fin)) {
+                    if (fin) store();
+                    fin = false;
+                }
+                if (!active && rank < take) {
+                    my = (size_t)(res_next + rank);
+                    load_packet(packets, my, k, exact);
+                    st.reset();
+                    retired = 0;
+                    L = Lane{0, 0, 0, 0, 0u};
+                    if (tree.node_count != 0)  // MbvhPacketIndexIterator has no NaN check (iter_indices.rs:327-352)
+                        active = true;
+                    else
+                        fin = true;
+                }
+                res_next += take;
+                idle = __ballot_sync(0xFFFFFFFFu, !active);
+            }
+            if (idle == 0xFFFFFFFFu) break;
+        }
+        const unsigned act_m = ~idle;
+        const bool in_t = active && L.tri_pos < L.tri_end;
+        const unsigned t_m = __ballot_sync(0xFFFFFFFFu, in_t);
+        const int n_t = __popc(t_m), n_n = __popc(act_m & ~t_m);
+        const bool in_n = active && !in_t;
+        bool done = false;
+        if (n_t * RTB_TRI_NUM >= n_n * RTB_TRI_DEN && n_t > 0) {
+            if (in_t) {
+                const uint32_t acc = tri_candidate_packet(tree.tris, L.tri_pos, t_min, packets + my, k);
+                L.tri_pos++;
+                if (ANY && acc) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (acc & (1u << i)) k.t[i] = -1e34f;
+                    retired |= acc;
+                    if (retired == 0xFu) done = true;
+                }
+                if (!done && L.tri_pos >= L.tri_end) done = lane_advance(tree, nullptr, st, L);
+            }
+        } else {
+            const bool any_exact = __any_sync(0xFFFFFFFFu, in_n && exact) != 0;
+            if (in_n) {
+                const int node = L.cur;
+                const MNode nd = mnode_load_global(tree.nodes, node);
+                const uint32_t mask = any_exact ? mbvh_slabs_packet<true>(nd, k) : mbvh_slabs_packet<false>(nd, k);
+                const int4 ch = nd.ch, cn = nd.cn;
+                const uint32_t leafbits = (cn.x > -1 ? 1u : 0u) | (cn.y > -1 ? 2u : 0u) | (cn.z > -1 ? 4u : 0u) | (cn.w > -1 ? 8u : 0u);
+                const uint32_t childbits = (ch.x > -1 ? 1u : 0u) | (ch.y > -1 ? 2u : 0u) | (ch.z > -1 ? 4u : 0u) | (ch.w > -1 ? 8u : 0u);
+                const uint32_t leaves = mask & leafbits;
+                const uint32_t inner = mask & ~leafbits & childbits;
+                // inner slots are pushed 3, 2, 1, 0 (iter_indices.rs:390): the lowest hit slot is popped next and stays in a register
+                int next = -1;
+                if (inner) {
+                    const int lowest = __ffs(inner) - 1;
+                    if ((inner & 8u) && lowest != 3) st.push(ch.w);
+                    if ((inner & 4u) && lowest != 2) st.push(ch.z);
+                    if ((inner & 2u) && lowest != 1) st.push(ch.y);
+                    next = sel4(ch, lowest);
+                }
+                L.cur = next;
+                if (leaves) {
+                    const int s0 = __ffs(leaves) - 1;
+                    const int c0 = sel4(cn, s0), f0 = sel4(ch, s0);
+                    L.tri_pos = f0;
+                    L.tri_end = f0 + c0;
+                    L.pmask = leaves & (leaves - 1);
+                    L.pnode = node;
+                }
+                if (L.tri_pos >= L.tri_end) done = lane_advance(tree, nullptr, st, L);
+            }
+        }
+        if (done) {
+            fin = true;
+            active = false;
+        }
+    }
+    if (fin) store();
 }
 
 // ---- scene upload helpers ---------------------------------------------------------------------
@@ -1487,7 +1664,15 @@ static cudaError_t launch_packets_t(const DeviceTree& tree, const RTRayPacket4* 
                                     RTHitPacket4* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
                                     uint32_t* d_overflow, int mode, cudaStream_t stream) {
     const size_t blocks_needed = ceil_div(n_packets * 4, kBlock);
-    if (mode != kTraceStatic) {
+    if (mode == kTraceLane && TREE == RT_TREE_MBVH) {  // one lane per packet
+        static const unsigned machine = persistent_grid(trace_mbvh_packet_lane_kernel<ANY>, kLBlock);
+        const size_t need = ceil_div(n_packets, kLBlock);
+        const unsigned grid = (unsigned)(need < machine ? need : machine);
+        cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+        trace_mbvh_packet_lane_kernel<ANY><<<grid, kLBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded,
+                                                                        d_counter, d_overflow);
+    } else if (mode != kTraceStatic) {
         static const unsigned machine = persistent_grid(trace_packet_persistent_kernel<TREE, ANY>);
         const unsigned grid = (unsigned)(blocks_needed < machine ? blocks_needed : machine);
         cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);

@@ -9,6 +9,7 @@ enum TraceMode {
     kTraceStatic = 0,      // one thread per ray, no refill (A/B only)
     kTracePersistent = 1,  // persistent warps + ray refill, every lane fetches its own node
     kTraceCoop = 2,        // same + lane-cooperative node fetch through shared memory (Mbvh; Bvh falls back to 1)
+    kTraceLane = 4,        // Mbvh packets: one lane per RayPacket4 (phased, persistent); other trees fall back to 1
     kTracePhased = 3,      // persistent warps + refill, node visits and triangle tests as separate warp-wide phases (default)
 };
 // d_counter: one 64-bit work counter owned by this launch (zeroed on `stream` by the launcher).

@@ -136,6 +136,14 @@ pub mod sys {
     }
 
     pub type RTGpuScene = u64;
+
+    /// What `rtbvh_gpu_scene_export` fills and `rtbvh_gpu_scene_import` reads: cudaIpc handles + sizes, shipped between the
+    /// per-GPU processes by whatever the application already uses (MPI, a pipe).
+    #[repr(C)]
+    #[derive(Copy, Clone)]
+    pub struct RTGpuSceneExport {
+        pub bytes: [u8; 512],
+    }
     /// `(prim_id, inout t, user_data) -> stop` (`rtbvh_ffi/src/lib.rs:541-558`).
     pub type RTIntersectCallback = Option<unsafe extern "C" fn(u32, *mut f32, *mut c_void) -> bool>;
 
@@ -196,6 +204,9 @@ pub mod sys {
         pub fn rtbvh_gpu_scene_stack_overflowed(scene: RTGpuScene, overflowed: *mut u32) -> ResultCode;
 
         // ---- multi-GPU gather fused into the traversal kernel ---------------------------------------------------
+        pub fn rtbvh_gpu_scene_export(scene: RTGpuScene, out: *mut RTGpuSceneExport) -> ResultCode;
+        pub fn rtbvh_gpu_scene_import(exported: *const RTGpuSceneExport, scene: *mut RTGpuScene) -> ResultCode;
+        pub fn rtbvh_gpu_scene_clone(scene: RTGpuScene, device: c_int, clone: *mut RTGpuScene) -> ResultCode;
         pub fn rtbvh_gpu_peer_buffer_create(bytes: usize, d_ptr: *mut *mut c_void, handle64: *mut c_uchar) -> ResultCode;
         pub fn rtbvh_gpu_peer_buffer_open(handle64: *const c_uchar, d_ptr: *mut *mut c_void) -> ResultCode;
         pub fn rtbvh_gpu_peer_buffer_close(d_ptr: *mut c_void) -> ResultCode;
