@@ -45,7 +45,7 @@ WIDTH = HEIGHT = 1000
 N_TRIS = 1 << 20
 
 
-from bench_common import ClockSampler, bind_to_gpu_numa_node, host_threads, log, measured_peak_gbs, ncu_traffic  # noqa: E402,F401
+from bench_common import ClockSampler, bind_to_gpu_numa_node, host_threads, log, measured_peak_gbs, ncu_traffic, nvlink_kib  # noqa: E402,F401
 
 
 def build_scene_host():
@@ -159,18 +159,46 @@ def run_gpu(args):
     info = {"host_numa": numa}
     if world == 1:
         bvh, mbvh, info = build_trees(api, tris, info, rank)
+        scene = api.Scene(tris, bvh=None, mbvh=mbvh)
     else:
-        # the tree is built once (rank 0) and replicated: one broadcast per scene over NCCL
-        from rtbvh_b200 import multigpu as MG
-        arrays = None
+        # the tree is built once (rank 0) and replicated through the C ABI: rank 0 exports its resident
+        # scene (cudaIpc handles, 512 bytes over the process group), every other rank copies it device to device over NVLink
+        # (rtbvh_gpu_scene_export / rtbvh_gpu_scene_import) — no host hop, no collective
+        scene, blob = None, [None]
         if rank == 0:
             bvh, mbvh, info = build_trees(api, tris, info, rank)
-            arrays = {"mnodes": mbvh.nodes, "indices": mbvh.indices}
-        arrays = MG.broadcast_arrays(arrays, src=0, device="cuda")
+            scene = api.Scene(tris, bvh=None, mbvh=mbvh)
+            try:
+                blob[0] = scene.export_bytes()
+            except api.RtbvhError as e:
+                log(f"[bench] scene export failed: {e}")
+        dist.broadcast_object_list(blob, src=0)
+        ok = 1
+        t_rep = time.perf_counter()
         if rank != 0:
-            mbvh = api.Mbvh.from_arrays(arrays["mnodes"], arrays["indices"])
-        info["replication"] = "tree built on rank 0, broadcast over NCCL, one replica per GPU"
-    scene = api.Scene(tris, bvh=None, mbvh=mbvh)
+            try:
+                if blob[0] is None:
+                    raise api.RtbvhError(1, "no export")
+                scene = api.Scene.import_bytes(blob[0])
+            except api.RtbvhError as e:
+                log(f"[bench] scene import failed on rank {rank}: {e}")
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # also the barrier that keeps rank 0's scene alive until all imports are done
+        rep_ms = (time.perf_counter() - t_rep) * 1e3
+        if int(flag[0]) == 1:
+            info["replication"] = ("tree built on rank 0; rtbvh_gpu_scene_export -> rtbvh_gpu_scene_import on every other rank: "
+                                   f"device-to-device copies over NVLink, {rep_ms:.1f} ms for all ranks")
+        else:  # no cudaIpc / peer access on this box: replicate through the process group instead
+            from rtbvh_b200 import multigpu as MG
+            if rank != 0 and scene is not None:
+                scene.free()
+            arrays = {"mnodes": mbvh.nodes, "indices": mbvh.indices} if rank == 0 else None
+            arrays = MG.broadcast_arrays(arrays, src=0, device="cuda")
+            if rank != 0:
+                mbvh = api.Mbvh.from_arrays(arrays["mnodes"], arrays["indices"])
+                scene = api.Scene(tris, bvh=None, mbvh=mbvh)
+            info["replication"] = "tree built on rank 0, broadcast over NCCL (cudaIpc import unavailable), one replica per GPU"
     sort_rays = os.environ.get("RTBVH_BENCH_SORT", "0") == "1"  # experiment knob; primary rays are coherent already
     scene.set_ray_sorting(sort_rays)
     info["ray_sorting"] = sort_rays
@@ -184,6 +212,8 @@ def run_gpu(args):
     cam = W.soup_camera(WIDTH, HEIGHT)
     free_b, _ = torch.cuda.mem_get_info()
     ring = int(max(2, min(args.steps + args.warmup, (free_b * 0.6) // (rays_per_step * 40))))
+    if os.environ.get("RTBVH_BENCH_RING"):  # experiment knob: fewer distinct ray buffers (still larger than L2 together)
+        ring = max(2, min(ring, int(os.environ["RTBVH_BENCH_RING"])))
     stream = torch.cuda.current_stream().cuda_stream
     d_rays = [torch.empty(rays_per_step * 8, dtype=torch.float32, device="cuda") for _ in range(ring)]
     d_hits = [torch.empty(rays_per_step * 2, dtype=torch.float32, device="cuda") for _ in range(ring)]
@@ -240,20 +270,38 @@ def run_gpu(args):
 
     for k in range(args.warmup):
         step(k)
-    barrier()
+    # rank-0-only host work (sub-processes: tens of milliseconds) goes BEFORE the barrier: with a cross-rank step barrier inside
+    # the timed region, a rank that starts its loop late makes every other rank's first step wait inside ITS timed region
     sampler = ClockSampler(local)
-    if rank == 0:
+    nvl0 = nvlink_kib(local) if (rank == 0 and world > 1) else None
+    if rank == 0 and os.environ.get("RTBVH_BENCH_NOSAMPLER") != "1":
         sampler.start()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if os.environ.get("RTBVH_BENCH_STEPTIMES") == "1" else None
     ev0.record()
     for k in range(args.steps):
         step(args.warmup + k)
+        if step_ev is not None:
+            step_ev[k].record()
     for w in works[-2:]:
         w.wait()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    if step_ev is not None:
+        ts = [ev0.elapsed_time(e) for e in step_ev]
+        log(f"[bench] rank {rank} step end times (ms): " + " ".join(f"{t:.2f}" for t in ts))
     clocks = sampler.stop() if rank == 0 else None
+    if nvl0 is not None:
+        nvl1 = nvlink_kib(local)
+        if nvl1 is not None:
+            # the fused gather sends every record of this rank to each of the world-1 peers and receives theirs
+            expect = args.steps * rays_per_step * 8 * (world - 1) if gather != "none" else 0
+            info["nvlink_gpu0"] = {"tx_bytes": (nvl1[0] - nvl0[0]) * 1024, "rx_bytes": (nvl1[1] - nvl0[1]) * 1024,
+                                   "expected_payload_bytes_each_way": expect,
+                                   "how": "nvidia-smi nvlink -gt d around the timed region (all links of GPU 0; counters include "
+                                          "protocol overhead and the step barriers' flag traffic)"}
     if scene.stack_overflowed():
         raise RuntimeError("traversal stack overflow")
     if fused is not None:

@@ -37,6 +37,22 @@ def ncu_traffic():
         return None
 
 
+def nvlink_kib(index: int):
+    """Sum of the NVLink data counters of GPU `index` over all links: (tx KiB, rx KiB), or None when nvidia-smi cannot
+    report them (`nvidia-smi nvlink -gt d`)."""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True,
+                             timeout=20).stdout
+        tx = [int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+        rx = [int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+        if not tx and not rx:
+            return None
+        return sum(tx), sum(rx)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"

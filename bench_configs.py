@@ -76,10 +76,10 @@ class Ctx:
         torch = self.torch
         for k in range(warmup):
             step(k)
-        self.barrier()
         sampler = ClockSampler(self.local)
         if self.rank == 0:
-            sampler.start()
+            sampler.start()  # before the barrier: the sub-process start must not skew rank 0's loop against the other ranks'
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for k in range(steps):

@@ -1107,6 +1107,12 @@ static ResultCode scatter_call(RTGpuScene h, RTTreeKind tree, bool any, const RT
     pd.count = dest_count;
     pd.offset = dest_offset;
     s->apply_tiling(pd, n);
+    // chunk-wise push (default; RTBVH_GATHER_PUSH=0 stores every record to every destination as its ray finishes)
+    static const bool push = [] {
+        const char* e = std::getenv("RTBVH_GATHER_PUSH");
+        return !(e && e[0] == '0');
+    }();
+    pd.push = (push && dest_count > 0 && d_local != nullptr) ? 1 : 0;
     RTB_CUDA(launch_trace_single(*t, tree, any, d_rays, n, any ? nullptr : (RTHit*)d_local, any ? (uint8_t*)d_local : nullptr,
                                  s->counter_slot(), s->d_overflow, refill_mode(), s->sort_bounds(), &pd, (cudaStream_t)stream));
     return Ok;

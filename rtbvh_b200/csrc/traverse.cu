@@ -673,9 +673,16 @@ __device__ __forceinline__ void bvh_node_phase(const DeviceTree& tree, const Ray
 // ================================================================================================
 // kernels
 // ================================================================================================
+#ifndef RTB_STREAM
+#define RTB_STREAM 1  // rays are read once and records written once: streaming (evict-first) accesses keep the tree in L2
+#endif
 __device__ __forceinline__ void load_ray(const RTRay* __restrict__ rays, size_t i, RayRegs& r) {
+#if RTB_STREAM
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(rays) + i * 2), b = __ldcs(reinterpret_cast<const float4*>(rays) + i * 2 + 1);
+#else
     const F8 ab = ld256(reinterpret_cast<const float4*>(rays) + i * 2);
     const float4 a = ab.lo, b = ab.hi;
+#endif
     r.ox = a.x; r.oy = a.y; r.oz = a.z; r.t_min = a.w;
     r.dx = b.x; r.dy = b.y; r.dz = b.z; r.t = b.w;
     finish_ray_setup(r);
@@ -700,6 +707,14 @@ __device__ __forceinline__ void load_ray_od(const float* __restrict__ origins, c
     r.t = pd.t_max;
     finish_ray_setup(r);
 }
+template <class T>
+__device__ __forceinline__ void st_stream(T* p, T v) {
+#if RTB_STREAM
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 // Result store.  With peer destinations (multi-GPU gather fused into the kernel) the record is also written,
 // the moment its ray finishes, into the gather buffer of every peer GPU (P2P stores over NVLink / NVSwitch to
 // cudaIpc-mapped memory): the transfer overlaps the traversal ray by ray and no collective follows the kernel.
@@ -708,13 +723,13 @@ __device__ __forceinline__ void store_result(const RayRegs& r, size_t i, RTHit* 
                                              uint8_t* __restrict__ occluded, const PeerDests& pd) {
     if (ANY) {
         const uint8_t v = r.prim != kNoHit ? 1 : 0;
-        if (occluded) occluded[i] = v;
+        if (occluded) st_stream(occluded + i, v);
 #pragma unroll
         for (int k = 0; k < 8; k++)  // unrolled: pd stays in the constant bank (no local copy for dynamic indexing)
             if (k < pd.count) static_cast<uint8_t*>(pd.p[k])[pd.offset + i] = v;
     } else {
         const float2 v = make_float2(r.t, __uint_as_float(r.prim));
-        if (hits) reinterpret_cast<float2*>(hits)[i] = v;
+        if (hits) st_stream(reinterpret_cast<float2*>(hits) + i, v);
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (k < pd.count) static_cast<float2*>(pd.p[k])[pd.offset + i] = v;
@@ -724,9 +739,128 @@ template <bool ANY>
 __device__ __forceinline__ void store_result(const RayRegs& r, size_t i, RTHit* __restrict__ hits,
                                              uint8_t* __restrict__ occluded) {
     if (ANY)
-        occluded[i] = r.prim != kNoHit ? 1 : 0;
+        st_stream(occluded + i, (uint8_t)(r.prim != kNoHit ? 1 : 0));
     else
-        reinterpret_cast<float2*>(hits)[i] = make_float2(r.t, __uint_as_float(r.prim));
+        st_stream(reinterpret_cast<float2*>(hits) + i, make_float2(r.t, __uint_as_float(r.prim)));
+}
+
+// Position in reservation order -> ray index: 8x8 pixel tiles inside the tiled part of the batch (see the refill code).
+__device__ __forceinline__ size_t tiled_index(const PeerDests& pd, unsigned long long pos) {
+    if (kRayChunk == 64 && pd.tile_w != 0 && pos < pd.tile_n) {
+        const unsigned long long band = 8ull * pd.tile_w, b = pos / band, rr = pos % band;
+        const unsigned tx = (unsigned)(rr >> 6), j = (unsigned)(rr & 63u);
+        return (size_t)(b * band + (unsigned long long)(j >> 3) * pd.tile_w + tx * 8u + (j & 7u));
+    }
+    return (size_t)pos;
+}
+// Fused multi-GPU gather, chunk-wise.  Every chunk of kRayChunk rays is reserved — and therefore traced — by ONE warp, so
+// the bookkeeping is warp-local: a four-entry table per warp in shared memory (chunk id, rays still running); finished rays
+// store their record into the LOCAL result buffer, and when the last ray of a chunk has finished the warp copies the
+// chunk's records to every destination — lane l moves records 2l, 2l+1 (one 16-byte load from L2, one 16-byte store per
+// destination; any hit: two bytes), 64 contiguous bytes per tile row — instead of one 8-byte P2P store per ray and
+// destination scattered over the refills.  No global atomics, no device-scope fence: writer and reader are the same warp.
+// A chunk that finds the table full (a warp with more than four chunks in flight: very long rays) falls back to per-ray stores.
+constexpr int kPushSlots = 4;
+template <bool ANY>
+__device__ __forceinline__ void push_chunk(unsigned c, size_t n, const RTHit* __restrict__ hits,
+                                           const uint8_t* __restrict__ occluded, const PeerDests& pd, unsigned lane) {
+    __threadfence_block();  // the records were stored by lanes of this warp
+    const unsigned long long lo = (unsigned long long)c * kRayChunk;
+    const unsigned size = (unsigned)((n - lo) < (unsigned long long)kRayChunk ? (n - lo) : (unsigned long long)kRayChunk);
+    const unsigned j = 2u * lane;
+    if (j >= size) return;
+    const size_t idx = tiled_index(pd, lo + j);  // even, and idx + 1 is the next position's index (same tile row)
+    const bool two = j + 1 < size;
+    if (ANY) {
+        const uint8_t* src = occluded + idx;
+        unsigned short v2 = 0;
+        if (two) {
+            asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v2) : "l"(src) : "memory");
+        } else {
+            asm volatile("ld.global.cg.u8 %0, [%1];" : "=h"(v2) : "l"(src) : "memory");
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k < pd.count) {
+                uint8_t* d = static_cast<uint8_t*>(pd.p[k]) + pd.offset + idx;
+                if (two)
+                    *reinterpret_cast<unsigned short*>(d) = v2;
+                else
+                    *d = (uint8_t)v2;
+            }
+        }
+    } else {
+        const float2* src = reinterpret_cast<const float2*>(hits) + idx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (two) {
+            asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src) : "memory");
+        } else {
+            asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(src) : "memory");
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k < pd.count) {
+                float2* d = static_cast<float2*>(pd.p[k]) + pd.offset + idx;
+                if (two)
+                    *reinterpret_cast<float4*>(d) = v;
+                else
+                    *d = make_float2(v.x, v.y);
+            }
+        }
+    }
+}
+// A warp registers the chunk it has just reserved: false when its table is full (that chunk's rays then scatter one by one).
+__device__ __forceinline__ void push_register(unsigned* tab, unsigned c, unsigned size, unsigned lane) {
+    __syncwarp();
+    int e = -1;
+#pragma unroll
+    for (int k = 0; k < kPushSlots; k++)
+        if (e < 0 && tab[kPushSlots + k] == 0) e = k;  // warp-uniform (broadcast reads)
+    __syncwarp();
+    if (e >= 0 && lane == 0) {
+        tab[e] = c;
+        tab[kPushSlots + e] = size;
+    }
+    __syncwarp();
+}
+// Result flush of the finished lanes of a warp (all lanes call it).  PUSH: local store, the chunk table counts the rays
+// down, completed chunks are copied to the destinations; otherwise the plain (or per-ray scattered) store.
+template <bool ANY, bool PUSH>
+__device__ __forceinline__ void flush_finished(bool& fin, const RayRegs& r, size_t my, unsigned slot, size_t n,
+                                               RTHit* __restrict__ hits, uint8_t* __restrict__ occluded, const PeerDests& pd,
+                                               unsigned* tab, unsigned lane) {
+    unsigned pending = __ballot_sync(0xFFFFFFFFu, fin);
+    if (pending == 0) return;
+    if (!PUSH) {
+        if (fin) store_result<ANY>(r, my, hits, occluded, pd);
+        fin = false;
+        return;
+    }
+    const unsigned cid = slot / kRayChunk;
+    if (fin) store_result<ANY>(r, my, hits, occluded);
+    while (pending) {
+        const unsigned c = __shfl_sync(0xFFFFFFFFu, cid, __ffs(pending) - 1);
+        const unsigned grp = __ballot_sync(0xFFFFFFFFu, fin && cid == c);
+        pending &= ~grp;
+        int e = -1;
+#pragma unroll
+        for (int k = 0; k < kPushSlots; k++)
+            if (tab[k] == c && tab[kPushSlots + k] != 0) e = k;
+        __syncwarp();
+        if (e < 0) {  // unregistered chunk: one store per ray and destination
+            if (fin && cid == c) {
+                PeerDests q = pd;
+                store_result<ANY>(r, my, nullptr, nullptr, q);
+            }
+            continue;
+        }
+        const unsigned left = tab[kPushSlots + e] - __popc(grp);
+        __syncwarp();
+        if (lane == 0) tab[kPushSlots + e] = left;
+        __syncwarp();
+        if (left == 0) push_chunk<ANY>(c, n, hits, occluded, pd, lane);
+    }
+    fin = false;
 }
 
 // Static assignment: thread i traces ray i.  Kept for A/B runs (RTBVH_TRACE_MODE=static) and for
@@ -759,7 +893,7 @@ __global__ void __launch_bounds__(kBlock) trace_single_kernel(const DeviceTree t
 // hands the idle lanes the next rays (ballot + prefix popcount).  Lanes therefore sit at different
 // depths of different rays, but all execute the same node-visit step, which keeps the SIMD lanes
 // busy when ray lengths differ (one missing ray no longer pins 31 idle lanes).
-template <int TREE, bool ANY, bool PHASED>
+template <int TREE, bool ANY, bool PHASED, bool PUSH>
 __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persistent_kernel(const DeviceTree tree,
                                                                          const RTRay* __restrict__ rays, size_t n,
                                                                          RTHit* __restrict__ hits,
@@ -771,6 +905,12 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
     // dynamic shared memory: the traversal stacks ([entry][thread]) and, behind them, the staged top of the tree
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     int* smem = reinterpret_cast<int*>(dyn_smem);
+    __shared__ unsigned push_tab[PUSH ? (kPBlock / 32) * 2 * kPushSlots : 1];  // per warp: chunk ids, rays still running
+    unsigned* tab = push_tab + (PUSH ? (threadIdx.x >> 5) * 2 * kPushSlots : 0);
+    if (PUSH) {
+        if ((threadIdx.x & 31u) < 2 * kPushSlots) tab[threadIdx.x & 31u] = 0;
+        __syncwarp();
+    }
     const float4* top_s = nullptr;
     if constexpr (kTopK > 0 && PHASED && TREE == RT_TREE_MBVH) {
         float4* t = reinterpret_cast<float4*>(dyn_smem + (size_t)kSmemStack * kPBlock * sizeof(int));
@@ -787,6 +927,7 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
     int cur = 0;
     Lane L{-1, 0, 0, 0, 0u};
     size_t my = 0;
+    unsigned slot = 0;  // PUSH: the ray's position in reservation order (its chunk = slot / kRayChunk)
     bool active = false;
     bool fin = false;  // the lane holds the record of a finished ray that is not stored yet (stored at the next refill, by
                        // all finished lanes of the warp in the same instructions, instead of lane by lane as rays end)
@@ -806,6 +947,7 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
                     }
                     res_next = base;
                     res_end = base + kRayChunk < n ? base + kRayChunk : n;
+                    if (PUSH) push_register(tab, (unsigned)(base / kRayChunk), (unsigned)(res_end - res_next), lane);
                     if (pd.ready) {  // host-buffer pipeline: wait until the copy engine has delivered this range
                         if (lane == 0) {
                             unsigned long long have;
@@ -824,19 +966,12 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
                 const unsigned want = __popc(idle);
                 const unsigned take = avail < want ? (unsigned)avail : want;
                 const unsigned rank = __popc(idle & lt_mask);
-                if (__any_sync(0xFFFFFFFFu, fin)) {
-                    if (fin) store_result<ANY>(r, my, hits, occluded, pd);
-                    fin = false;
-                }
+                flush_finished<ANY, PUSH>(fin, r, my, slot, n, hits, occluded, pd, tab, lane);
                 if (!active && rank < take) {
-                    my = (size_t)(res_next + rank);
-                    if (kRayChunk == 64 && pd.tile_w != 0 && my < pd.tile_n) {
-                        // chunk of 64 consecutive indices -> one 8x8 pixel tile of the same 8-row band (neighbouring lanes
-                        // then walk neighbouring parts of the tree: fewer distinct sectors per load instruction)
-                        const unsigned long long band = 8ull * pd.tile_w, b = my / band, rr = my % band;
-                        const unsigned tx = (unsigned)(rr >> 6), j = (unsigned)(rr & 63u);
-                        my = (size_t)(b * band + (unsigned long long)(j >> 3) * pd.tile_w + tx * 8u + (j & 7u));
-                    }
+                    // chunk of 64 consecutive positions -> one 8x8 pixel tile of the same 8-row band (neighbouring lanes then
+                    // walk neighbouring parts of the tree: fewer distinct sectors per load instruction)
+                    if (PUSH) slot = (unsigned)(res_next + rank);
+                    my = tiled_index(pd, res_next + rank);
                     if (perm) my = (size_t)perm[my];
                     if (pd.directions)
                         load_ray_od(reinterpret_cast<const float*>(rays), pd, my, r);
@@ -907,7 +1042,7 @@ __global__ void __launch_bounds__(kPBlock, RTB_MINBLOCKS) trace_single_persisten
             }
         }
     }
-    if (fin) store_result<ANY>(r, my, hits, occluded, pd);
+    flush_finished<ANY, PUSH>(fin, r, my, slot, n, hits, occluded, pd, tab, lane);
 }
 
 // ---- lane-cooperative node fetch -------------------------------------------------------------------
@@ -1591,20 +1726,29 @@ static cudaError_t launch_single_t(const DeviceTree& tree, const RTRay* d_rays, 
     }
     if (mode == kTracePhased) {
         constexpr size_t smem = persistent_smem<TREE, true>();
-        static const unsigned machine = persistent_grid(trace_single_persistent_kernel<TREE, ANY, true>, kPBlock, smem);
+        static const unsigned machine = persistent_grid(trace_single_persistent_kernel<TREE, ANY, true, false>, kPBlock, smem);
         const unsigned grid = (unsigned)(pblocks_needed < machine ? pblocks_needed : machine);
         cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
-        trace_single_persistent_kernel<TREE, ANY, true><<<grid, kPBlock, smem, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_perm,
+        trace_single_persistent_kernel<TREE, ANY, true, false><<<grid, kPBlock, smem, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_perm,
                                                                                     d_counter, d_overflow, pd);
     } else if (persistent) {
         constexpr size_t smem = persistent_smem<TREE, false>();
-        static const unsigned machine = persistent_grid(trace_single_persistent_kernel<TREE, ANY, false>, kPBlock, smem);
-        const unsigned grid = (unsigned)(pblocks_needed < machine ? pblocks_needed : machine);
         cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
-        trace_single_persistent_kernel<TREE, ANY, false><<<grid, kPBlock, smem, stream>>>(tree, d_rays, n, d_hits, d_occluded, d_perm,
-                                                                                     d_counter, d_overflow, pd);
+        const bool push = pd.push != 0 && pd.count > 0 && d_perm == nullptr && (pd.offset & 1) == 0 &&
+                          n < 0xFFFFFFFFull && (ANY ? d_occluded != nullptr : d_hits != nullptr);
+        if (push) {
+            static const unsigned machine = persistent_grid(trace_single_persistent_kernel<TREE, ANY, false, true>, kPBlock, smem);
+            const unsigned grid = (unsigned)(pblocks_needed < machine ? pblocks_needed : machine);
+            trace_single_persistent_kernel<TREE, ANY, false, true><<<grid, kPBlock, smem, stream>>>(tree, d_rays, n, d_hits, d_occluded,
+                                                                                        d_perm, d_counter, d_overflow, pd);
+        } else {
+            static const unsigned machine = persistent_grid(trace_single_persistent_kernel<TREE, ANY, false, false>, kPBlock, smem);
+            const unsigned grid = (unsigned)(pblocks_needed < machine ? pblocks_needed : machine);
+            trace_single_persistent_kernel<TREE, ANY, false, false><<<grid, kPBlock, smem, stream>>>(tree, d_rays, n, d_hits, d_occluded,
+                                                                                         d_perm, d_counter, d_overflow, pd);
+        }
     } else {
         trace_single_kernel<TREE, ANY><<<(unsigned)blocks_needed, kBlock, 0, stream>>>(tree, d_rays, n, d_hits, d_occluded,
                                                                                      d_perm, d_overflow);

@@ -19,6 +19,10 @@ struct PeerDests {
     void* p[8];
     int count;
     size_t offset;
+    // Chunk-wise push (0: every record is stored to every destination as its ray finishes).  Finished rays store their
+    // record locally; the warp that traced a chunk of kRayChunk rays copies the chunk to all destinations with full-width
+    // stores once its last ray has finished (needs a local result buffer, an even `offset`, the caller's ray order).
+    int push;
     // Input gate of the host-buffer pipeline (null: all rays are resident).  *ready = number of rays of this launch
     // whose H2D copy has completed (written by the copy engine, stream-ordered behind each sub-chunk): a warp that
     // reserves rays [a, b) waits until *ready >= b, so ONE launch can start while its input is still arriving.

@@ -23,8 +23,9 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_per_rank, steps, any_hit, out_dir):
+def _worker(rank, world, port, n_per_rank, steps, any_hit, out_dir, push=True, tile_w=0):
     import sys
+    os.environ["RTBVH_GATHER_PUSH"] = "1" if push else "0"  # chunk-wise push (default) / one store per ray and destination
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import torch
     import torch.distributed as dist
@@ -41,6 +42,7 @@ def _worker(rank, world, port, n_per_rank, steps, any_hit, out_dir):
     rc, bvh = O.build(O.BINNED_SAH, aabbs, centers, 1)
     m = bvh.collapse()
     scene = api.Scene(tris, bvh=None, mbvh=api.Mbvh.from_arrays(m.nodes, m.indices))
+    scene.set_ray_tiling(tile_w)  # work-order hint: 8x8 tiles inside whole bands of 8 rows of tile_w rays (results unchanged)
     rec = 1 if any_hit else 8
     fg = MG.FusedGather(n_per_rank, rec)
     stream = torch.cuda.current_stream().cuda_stream
@@ -65,11 +67,14 @@ def _worker(rank, world, port, n_per_rank, steps, any_hit, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("any_hit", [False, True])
-def test_fused_gather_equals_single_process(O, W, teapot, teapot_trees, tmp_path, any_hit):
+@pytest.mark.parametrize("any_hit,push,n_per_rank,tile_w", [(False, True, 50_000, 0), (True, True, 50_000, 0),
+                                                            (False, False, 50_000, 0), (False, True, 50_030, 40),
+                                                            (True, True, 50_062, 48)])
+def test_fused_gather_equals_single_process(O, W, teapot, teapot_trees, tmp_path, any_hit, push, n_per_rank, tile_w):
     import torch.multiprocessing as mp
-    world, n_per_rank, steps = 2, 50_000, 4
-    mp.spawn(_worker, args=(world, _free_port(), n_per_rank, steps, any_hit, str(tmp_path)), nprocs=world, join=True)
+    world, steps = 2, 4
+    mp.spawn(_worker, args=(world, _free_port(), n_per_rank, steps, any_hit, str(tmp_path), push, tile_w), nprocs=world,
+             join=True)
     for k in range(steps):
         rays = W.random_rays(world * n_per_rank, *W.bounds(teapot["tris"]), seed=0xF00D + k)
         want, _, _ = O.trace(teapot_trees["sah"][1], teapot["tris"], rays, mode="any" if any_hit else "closest")
