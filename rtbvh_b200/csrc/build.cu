@@ -27,6 +27,7 @@
 //     parallel; the result is bit-identical to the reference algorithm, node for node.
 //   * collapse and refit are pointer-chasing kernels over the finished binary tree.
 #include <cub/cub.cuh>
+#include <mutex>
 
 #include <algorithm>
 #include <cfloat>
@@ -2088,7 +2089,7 @@ struct DevBuf {  // a view into the arena: nothing to free
 // A cudaMalloc'ed copy of an arena buffer, owned by the caller (the resident scene path).
 static cudaError_t detach(const DevBuf& b, size_t bytes, void** out) {
     *out = nullptr;
-    cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+    cudaError_t e = dev_block_alloc(out, bytes ? bytes : 16);
     if (e != cudaSuccess) return e;
     return bytes ? cudaMemcpyAsync(*out, b.p, bytes, cudaMemcpyDeviceToDevice, 0) : cudaSuccess;
 }
@@ -2726,7 +2727,104 @@ ResultCode gpu_trim_workspace() {
     arena().release();
     g_arena_epoch++;
     HostPool::get().trim();
+    dev_block_trim();
     return Ok;
+}
+
+// ---- device block cache of the resident scenes (build.cuh) ---------------------------------------------------------
+namespace {
+constexpr size_t kDevCacheBlocks = 24;
+struct DevBlock {
+    void* p;
+    size_t bytes;
+    int device;
+};
+struct DevCache {
+    std::mutex mu;
+    std::vector<DevBlock> live, idle;
+    size_t limit() {
+        static const size_t v = [] {
+            const char* e = std::getenv("RTBVH_SCENE_CACHE_MB");
+            return (size_t)(e ? std::strtoull(e, nullptr, 10) : 24576ull) << 20;
+        }();
+        return v;
+    }
+} g_dev_cache;
+}  // namespace
+
+cudaError_t dev_block_alloc(void** p, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (bytes == 0) bytes = 16;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_cache.mu);
+        // best fit among the idle blocks of this device that waste at most a quarter (small blocks: at most 1 MiB)
+        int best = -1;
+        for (size_t i = 0; i < g_dev_cache.idle.size(); i++) {
+            const DevBlock& b = g_dev_cache.idle[i];
+            if (b.device != dev || b.bytes < bytes || b.bytes > bytes + bytes / 4 + (size_t(1) << 20)) continue;
+            if (best < 0 || b.bytes < g_dev_cache.idle[best].bytes) best = (int)i;
+        }
+        if (best >= 0) {
+            const DevBlock b = g_dev_cache.idle[best];
+            g_dev_cache.idle.erase(g_dev_cache.idle.begin() + best);
+            g_dev_cache.live.push_back(b);
+            *p = b.p;
+            return cudaSuccess;
+        }
+    }
+    e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {  // out of memory with blocks parked in the cache: give them back and try once more
+        cudaGetLastError();
+        dev_block_trim();
+        e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    std::lock_guard<std::mutex> lk(g_dev_cache.mu);
+    g_dev_cache.live.push_back(DevBlock{*p, bytes, dev});
+    return cudaSuccess;
+}
+
+void dev_block_free(void* p) {
+    if (!p) return;
+    DevBlock blk{nullptr, 0, 0};
+    std::vector<void*> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_cache.mu);
+        for (size_t i = 0; i < g_dev_cache.live.size(); i++)
+            if (g_dev_cache.live[i].p == p) {
+                blk = g_dev_cache.live[i];
+                g_dev_cache.live.erase(g_dev_cache.live.begin() + i);
+                break;
+            }
+        if (blk.p && blk.bytes >= (size_t(1) << 20)) {  // only blocks worth keeping
+            g_dev_cache.idle.push_back(blk);
+            size_t total = 0;
+            for (const DevBlock& b : g_dev_cache.idle) total += b.bytes;
+            while (!g_dev_cache.idle.empty() && (g_dev_cache.idle.size() > kDevCacheBlocks || total > g_dev_cache.limit())) {
+                total -= g_dev_cache.idle.front().bytes;  // oldest first
+                drop.push_back(g_dev_cache.idle.front().p);
+                g_dev_cache.idle.erase(g_dev_cache.idle.begin());
+            }
+            p = nullptr;
+        }
+    }
+    // A cached block may still be read by kernels the caller enqueued before freeing the scene; the next owner's work is
+    // stream-ordered behind them only on the legacy default stream, so drain the device once here (cudaFree would have).
+    if (!p) cudaDeviceSynchronize();
+    for (void* d : drop) cudaFree(d);
+    if (p) cudaFree(p);
+}
+
+void dev_block_trim() {
+    std::vector<void*> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_cache.mu);
+        for (const DevBlock& b : g_dev_cache.idle) drop.push_back(b.p);
+        g_dev_cache.idle.clear();
+    }
+    for (void* d : drop) cudaFree(d);
 }
 
 // ---- dynamic scenes: refit of device-resident trees ---------------------------------------------

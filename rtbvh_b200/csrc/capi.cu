@@ -157,13 +157,13 @@ struct Scene {
         if (ev_refit_done) cudaEventDestroy(ev_refit_done);
         cudaFree(d_ready);
         if (h_marks) cudaFreeHost(h_marks);
-        cudaFree(d_bvh_nodes);
-        cudaFree(d_mbvh_nodes);
-        if (d_tris_mbvh != d_tris_bvh) cudaFree(d_tris_mbvh);
-        cudaFree(d_tris_bvh);
-        if (d_idx_mbvh != d_idx_bvh) cudaFree(d_idx_mbvh);
-        cudaFree(d_idx_bvh);
-        cudaFree(d_refit_verts);
+        dev_block_free(d_bvh_nodes);  // the large blocks go back to the scene block cache (build.cuh)
+        dev_block_free(d_mbvh_nodes);
+        if (d_tris_mbvh != d_tris_bvh) dev_block_free(d_tris_mbvh);
+        dev_block_free(d_tris_bvh);
+        if (d_idx_mbvh != d_idx_bvh) dev_block_free(d_idx_mbvh);
+        dev_block_free(d_idx_bvh);
+        dev_block_free(d_refit_verts);
         cudaFree(d_top);
         cudaFree(d_top_count);
         cudaFree(d_overflow);
@@ -710,7 +710,7 @@ static ResultCode scene_build_common(const float* vertices, bool on_device, size
     if (rc != Ok) return rc;
     s->tri_count = (uint32_t)triangle_count;
     const float* d_verts = on_device ? vertices : rt.d_vertices;
-    RTB_CUDA(cudaMalloc((void**)&s->d_tris_bvh, (size_t)rt.index_count * sizeof(TriRec)));
+    RTB_CUDA(dev_block_alloc((void**)&s->d_tris_bvh, (size_t)rt.index_count * sizeof(TriRec)));
     RTB_CUDA(launch_gather_tris(d_verts, (uint32_t)(vertex_stride / 4), rt.d_indices, rt.index_count, (uint32_t)triangle_count,
                                 s->d_tris_bvh, 0));
     s->bvh = DeviceTree{(const float4*)s->d_bvh_nodes, rt.node_count, s->d_tris_bvh, rt.index_count, nullptr, 0};
@@ -826,10 +826,10 @@ ResultCode rtbvh_gpu_scene_refit(RTGpuScene h, const float* vertices, size_t ver
     const size_t bytes = triangle_count * 3 * vertex_stride;
     if (bytes > s->refit_verts_bytes) {
         RTB_CUDA(cudaDeviceSynchronize());  // an earlier refit_device may still read the old staging buffer
-        cudaFree(s->d_refit_verts);
+        dev_block_free(s->d_refit_verts);
         s->d_refit_verts = nullptr;
         s->refit_verts_bytes = 0;
-        RTB_CUDA(cudaMalloc(&s->d_refit_verts, bytes ? bytes : 16));
+        RTB_CUDA(dev_block_alloc((void**)&s->d_refit_verts, bytes ? bytes : 16));
         s->refit_verts_bytes = bytes;
     }
     if (refit_order_begin(*s, 0) != Ok) return Error;
@@ -930,7 +930,7 @@ ResultCode scene_replicate(const SceneBlob& b, const void* const src[6], const s
     void* dst[6] = {};
     for (int k = 0; k < 6; k++) {
         if (bytes[k] == 0) continue;
-        cudaError_t e = cudaMalloc(&dst[k], bytes[k]);
+        cudaError_t e = dev_block_alloc(&dst[k], bytes[k]);
         if (e == cudaSuccess)
             e = src_device >= 0 ? cudaMemcpyPeer(dst[k], s->device, src[k], src_device, bytes[k])
                                 : cudaMemcpy(dst[k], src[k], bytes[k], cudaMemcpyDeviceToDevice);
@@ -1107,11 +1107,15 @@ static ResultCode scatter_call(RTGpuScene h, RTTreeKind tree, bool any, const RT
     pd.count = dest_count;
     pd.offset = dest_offset;
     s->apply_tiling(pd, n);
-    // chunk-wise push (default; RTBVH_GATHER_PUSH=0 stores every record to every destination as its ray finishes)
-    static const bool push = [] {
+    // Store shape of the fused gather (RTBVH_GATHER_PUSH=1 / 0 forces one).  Measured, 8 M rays per step and rank
+    // (profiles/r5k_gather_ab_n2.txt, r5n_gather_ab.txt): per-ray stores cost +0.2 % for the own buffer and +2.4 % for 7 peers;
+    // the chunk-wise push halves the peer part (+1.1 %) but its bookkeeping costs +1.7 % whatever the peer count:
+    // 2 GPUs 4.26 vs 4.33 ms per step, 8 GPUs 4.42 vs 4.41.  Default: push only beyond 4 destinations.
+    static const int push_mode = [] {
         const char* e = std::getenv("RTBVH_GATHER_PUSH");
-        return !(e && e[0] == '0');
+        return e ? (e[0] == '0' ? 0 : 1) : -1;
     }();
+    const bool push = push_mode < 0 ? dest_count > 4 : push_mode == 1;
     pd.push = (push && dest_count > 0 && d_local != nullptr) ? 1 : 0;
     RTB_CUDA(launch_trace_single(*t, tree, any, d_rays, n, any ? nullptr : (RTHit*)d_local, any ? (uint8_t*)d_local : nullptr,
                                  s->counter_slot(), s->d_overflow, refill_mode(), s->sort_bounds(), &pd, (cudaStream_t)stream));
