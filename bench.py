@@ -68,6 +68,17 @@ def oracle_tree(tris):
     return O, bvh, m, build_s
 
 
+def oracle_threaded_build_ms(O, tris):
+    """The CPU builder with the reference's threaded scheduling (subtrees > 1024 primitives on other threads, src/utils.rs:
+    189-289) on every host core: the honest CPU figure next to the GPU builder's ms per Mtri.  None on any failure."""
+    try:
+        aabbs, centers = O.prims_from_triangles(tris)
+        rc, b = O.build(O.BINNED_SAH, aabbs, centers, 1, parallel=True)
+        return b.build_ms if rc == 0 else None
+    except Exception:
+        return None
+
+
 def cpu_sample_rate(O, m, tris, rays, target_s=10.0):
     """Times the oracle on a bounded sample; returns (Mrays/s, n_sample, counters per ray)."""
     threads = host_threads()
@@ -128,6 +139,9 @@ def run_reference(args):
                          "single_thread_value": one},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "oracle_build_ms_per_mtri": build_s * 1e3 / (N_TRIS / 1e6),
+        "oracle_build_ms_per_mtri_all_cores": (lambda v: v / (N_TRIS / 1e6) if v else None)(oracle_threaded_build_ms(O, tris)),
+        "oracle_build_note": "binned SAH, 1 Mi triangles: one thread (deterministic numbering) and the reference's threaded "
+                             f"scheduling on {threads} threads (subtrees > 1024 primitives run on other threads)",
     }))
 
 
@@ -417,6 +431,10 @@ def run_gpu(args):
                    "sample": f"first {n_s} rays of the timed workload (the very rays the GPU steps trace), Mbvh single-ray "
                              f"closest hit, OpenMP dynamic chunks of 1000",
                    "single_thread_value": cpu_single_thread_rate(O, otree, tris, host_rays)}
+            tb = oracle_threaded_build_ms(O, tris)
+            cpu["binned_sah_build_ms_per_mtri"] = tb / (N_TRIS / 1e6) if tb else None
+            cpu["binned_sah_build_note"] = (f"the port's binned-SAH builder on this scene with the reference's threaded scheduling "
+                                            f"(subtrees > 1024 primitives on other threads, src/utils.rs:189-289), {threads} threads")
             # parity spot check inside the bench: oracle vs GPU on the sample
             want, _, _ = O.trace(otree, tris, host_rays[:200_000], threads=threads)
             got = d_hits[0][: 200_000 * 2].cpu().numpy().view(api.HIT_DTYPE).reshape(-1)

@@ -348,6 +348,13 @@ def config3_gpu(args):
         host_step()
     e2e_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)[0]
     # the reference's own ABI (create_bvh-shaped call with host mirrors + create_mbvh)
+    # (first call: the pooled page-locked host mirrors are pinned — once per size class and process; second call: recycled)
+    b = api.build_triangles(tris, kind, 1)
+    abi_first = api.last_build_stats()
+    m = api.Mbvh.construct(b)
+    abi_c_first = api.last_build_stats()
+    m.free()
+    b.free()
     b = api.build_triangles(tris, kind, 1)
     abi = api.last_build_stats()
     m = api.Mbvh.construct(b)
@@ -356,7 +363,9 @@ def config3_gpu(args):
         from oracle import oracle as O
         info = {"bvh_nodes": int(b.rt.node_count), "mbvh_nodes": int(m.rt.node_count), "locb_iterations": int(st["iterations"]),
                 "sah": O.Bvh(b.nodes, b.indices).sah_cost(),
-                "reference_abi": {"create_bvh_ms_per_mtri_incl_h2d_d2h": abi["total_ms"] / mtri, "create_bvh_device_ms_per_mtri": abi["device_ms"] / mtri,
+                "reference_abi": {"first_call_create_bvh_ms_per_mtri_incl_h2d_d2h": abi_first["total_ms"] / mtri,
+                                  "first_call_create_mbvh_ms_incl_h2d_d2h": abi_c_first["total_ms"],
+                                  "create_bvh_ms_per_mtri_incl_h2d_d2h": abi["total_ms"] / mtri, "create_bvh_device_ms_per_mtri": abi["device_ms"] / mtri,
                                   "create_mbvh_ms_incl_h2d_d2h": abi_c["total_ms"], "create_mbvh_device_ms": abi_c["device_ms"]}}
         cpu, roof = None, None
         if not args.no_cpu:

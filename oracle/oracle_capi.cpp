@@ -163,7 +163,9 @@ int rto_bvh_build(int type, const void* aabbs, size_t aabb_count, const float* c
         if (kappa) *kappa = prim_count ? (double)lb.cluster_sum / (double)prim_count : 0.0;
     } else {
         BinnedSahBuilder sb{bbs, c.data(), prim_count, prims_per_leaf ? prims_per_leaf : 1, {}, {}, 1};
-        *b = sb.build();
+        // parallel: the reference's threaded scheduling (subtrees > 1024 primitives on other threads) with `parallel` threads
+        // (1 = all cores); node numbering then depends on the thread interleaving, like the reference's.  0: deterministic.
+        *b = parallel != 0 ? sb.build_parallel(parallel == 1 ? omp_get_max_threads() : parallel) : sb.build();
         if (kappa) *kappa = 0.0;
     }
     if (build_ms) *build_ms = now_ms() - t0;

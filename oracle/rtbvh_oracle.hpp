@@ -726,6 +726,7 @@ struct BinnedSahBuilder {
     std::vector<BvhNode> nodes;
     std::vector<uint32_t> prim_indices;
     size_t node_count = 1;  // AtomicNodeStack counter (builders/mod.rs:54)
+    bool threaded = false;  // build_parallel(): child pairs are handed out with an atomic fetch-add, like the reference's
 
     struct Task {
         size_t node, begin, end, depth;
@@ -789,8 +790,13 @@ struct BinnedSahBuilder {
                                  return compute_bin_index(centers[p], bin_offset, center_to_bin, best_axis) < split_index;
                              });
         if (begin_right > t.begin && begin_right < t.end) {
-            size_t left = node_count;  // AtomicNodeStack::allocate, builders/mod.rs:59-76
-            node_count += 2;
+            size_t left;  // AtomicNodeStack::allocate, builders/mod.rs:59-76
+            if (threaded) {
+                left = __atomic_fetch_add(&node_count, (size_t)2, __ATOMIC_RELAXED);
+            } else {
+                left = node_count;
+                node_count += 2;
+            }
             node.extra2 = (int32_t)left;
             node.extra1 = -1;
             Aabb lb = aabb_new(), rb = aabb_new();
@@ -828,6 +834,51 @@ struct BinnedSahBuilder {
                 stack.push_back(b);
                 stack.push_back(a);
             }
+        }
+        nodes.resize(node_count);
+        out.nodes = std::move(nodes);
+        out.prim_indices = std::move(prim_indices);
+        out.build_type = 2;
+        return out;
+    }
+
+    // The reference's threaded flavour (TaskSpawner, utils.rs:189-289): a child with more than 1024 primitives is handed to
+    // another thread while threads are available, the rest runs on the spawning thread's own stack.  Here: OpenMP tasks with
+    // the same 1024-primitive threshold.  Topology, boxes and leaf contents are those of build(); only the node NUMBERING
+    // depends on the interleaving of the threads' allocations — exactly as in the reference.  Used for the CPU build
+    // baseline of bench.py (every host core); the deterministic build() stays the checker.
+    void run_subtree(Task root) {
+        std::vector<Task> stack;
+        stack.push_back(root);
+        while (!stack.empty()) {
+            Task t = stack.back();
+            stack.pop_back();
+            Task a, b;
+            if (run(t, &a, &b)) {
+                if (a.work() < b.work()) std::swap(a, b);
+                if (b.work() > 1024) {  // utils.rs:253-262 (the smaller child is the one handed over)
+#pragma omp task firstprivate(b)
+                    run_subtree(b);
+                } else {
+                    stack.push_back(b);
+                }
+                stack.push_back(a);
+            }
+        }
+    }
+    Bvh build_parallel(int threads) {
+        Bvh out;
+        if (n == 0) return out;
+        threaded = true;
+        nodes.assign(n * 2 - 1, aabb_new());
+        prim_indices.resize(n);
+        for (size_t i = 0; i < n; i++) prim_indices[i] = (uint32_t)i;
+        node_count = 1;
+        nodes[0] = union_of_list(aabbs, n);
+#pragma omp parallel num_threads(threads > 0 ? threads : 1)
+        {
+#pragma omp single
+            run_subtree(Task{0, 0, n, 0});
         }
         nodes.resize(node_count);
         out.nodes = std::move(nodes);

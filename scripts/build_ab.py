@@ -13,8 +13,8 @@ from rtbvh_b200 import api, workloads as W  # noqa: E402
 name = os.environ.get("RTBVH_LIB", "default").split("librtbvh_rs")[-1].strip("_.so") or "default"
 scenes = {"teapot": W.teapot(), "soup64k": W.soup(1 << 16), "soup1m": W.soup(1 << 20), "soup4m": W.soup(1 << 22)}
 for sname, tris in scenes.items():
-    for kind, kname in ((api.BINNED_SAH, "sah"), (api.LOCB, "locb")):
-        if kind == api.LOCB and sname != "soup1m":
+    for kind, kname in ((api.BINNED_SAH, "sah"), (api.LOCALLY_ORDERED_CLUSTERED, "locb")):
+        if kind == api.LOCALLY_ORDERED_CLUSTERED and sname != "soup1m":
             continue
         ms = []
         for rep in range(5):

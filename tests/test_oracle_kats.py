@@ -218,3 +218,26 @@ def test_ffi_create_delete_codes(O):
     rc, bvh = O.build(O.BINNED_SAH, aabbs, c16, 1)
     assert rc == 0 and bvh.validate(27)
     assert len(bvh.collapse().nodes) >= 1
+
+
+def test_threaded_builder_is_the_serial_builder_up_to_numbering(O, W):
+    """oracle build(parallel=True) = the reference's threaded scheduling (subtrees > 1024 primitives on other threads,
+    src/utils.rs:189-289): same topology, boxes and leaves as the deterministic builder; only the node numbering may differ."""
+    tris = W.soup(60_000, seed=11)
+    aabbs, centers = O.prims_from_triangles(tris)
+    rc0, a = O.build(O.BINNED_SAH, aabbs, centers, 1)
+    rc1, b = O.build(O.BINNED_SAH, aabbs, centers, 1, parallel=True)
+    assert rc0 == 0 and rc1 == 0
+    assert len(a.nodes) == len(b.nodes)
+    assert abs(a.sah_cost() - b.sah_cost()) <= 1e-9 * a.sah_cost()
+
+    def signature(t):  # multiset of nodes as (box bits, count, first primitive id of a leaf)
+        n = t.nodes
+        rows = []
+        for k in range(len(n)):
+            cnt = int(n["count"][k])
+            first = int(t.indices[int(n["left_first"][k])]) if cnt > 0 else -1
+            rows.append((n["min"][k].tobytes(), n["max"][k].tobytes(), cnt, first))
+        return sorted(rows)
+
+    assert signature(a) == signature(b)
