@@ -174,7 +174,7 @@ ResultCode rtbvh_gpu_intersect_packets_device(RTGpuScene scene, RTTreeKind tree,
                                               size_t packet_count, float t_min, RTHitPacket4 *d_hits, void *stream);
 ResultCode rtbvh_gpu_occluded_packets_device(RTGpuScene scene, RTTreeKind tree, const RTRayPacket4 *d_packets,
                                              size_t packet_count, float t_min, uint8_t *d_occluded, void *stream);
-/* Nonzero if any ray of a previous *_device call on this scene needed more than the 64-entry
+/* Nonzero if any ray of a previous *_device call on this scene needed more than the 128-entry
  * traversal stack (the reference's stack has 32 entries and panics / is UB beyond, src/iter.rs:25).
  * Synchronises the device.  Host-buffer calls return Error in that case. */
 ResultCode rtbvh_gpu_scene_stack_overflowed(RTGpuScene scene, uint32_t *overflowed);

@@ -554,6 +554,29 @@ impl GpuScene {
         self.triangle_count
     }
 
+    /// Multi-GPU, one process per GPU: the scene is built once; `export` yields 512 bytes (cudaIpc handles + sizes) that any
+    /// channel carries to the other ranks, `import` turns them into a byte-identical replica on the caller's current GPU,
+    /// copied device to device over NVLink.  Keep the exporting scene alive until every importer has returned.
+    pub fn export(&self) -> Result<[u8; 512], GpuError> {
+        let mut x = sys::RTGpuSceneExport { bytes: [0u8; 512] };
+        check(unsafe { sys::rtbvh_gpu_scene_export(self.handle, &mut x) })?;
+        Ok(x.bytes)
+    }
+
+    pub fn import(exported: &[u8; 512], triangle_count: usize) -> Result<Self, GpuError> {
+        let x = sys::RTGpuSceneExport { bytes: *exported };
+        let mut handle: sys::RTGpuScene = 0;
+        check(unsafe { sys::rtbvh_gpu_scene_import(&x, &mut handle) })?;
+        Ok(GpuScene { handle, triangle_count, _not_copy: PhantomData })
+    }
+
+    /// The same inside one process that drives several GPUs (`cudaMemcpyPeer`).
+    pub fn clone_to_device(&self, device: i32) -> Result<Self, GpuError> {
+        let mut handle: sys::RTGpuScene = 0;
+        check(unsafe { sys::rtbvh_gpu_scene_clone(self.handle, device as c_int, &mut handle) })?;
+        Ok(GpuScene { handle, triangle_count: self.triangle_count, _not_copy: PhantomData })
+    }
+
     /// Dynamic scenes: new positions for the same triangles.  `Bvh::refit` (`src/bvh.rs:176-205`) on the device,
     /// followed by what the reference never does: the Mbvh's slot boxes are refreshed from the refitted binary tree
     /// (equal to `Mbvh::construct` of it).
