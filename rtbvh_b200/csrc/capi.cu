@@ -1028,8 +1028,10 @@ ResultCode rtbvh_gpu_scene_clone(RTGpuScene h, int device, RTGpuScene* clone) {
 }
 
 // Packet kernels (RTBVH_PACKET_MODE = static | persistent | lane).  Measured on config 2's frames as packets of four
-// x-adjacent pixels (scripts/trace_ab.py --packets, profiles/r5_trace_ab.md): Mbvh closest hit static quad 1 135, persistent
-// quad 1 288, one lane per packet see there; Bvh static 406, persistent 360.  Default: Mbvh = lane, Bvh = static.
+// x-adjacent pixels (scripts/trace_ab.py --packets, profiles/r5_trace_ab.md), closest / any hit Mrays/s:
+//   Mbvh: quad static 1 135 / 1 221, quad persistent 1 288 / 1 520, one lane per packet 2 008 / 2 183
+//   Bvh:  quad static   404 / 1 103, quad persistent   360,         one lane per packet   743 / 2 102
+// Default: one lane per packet for both trees.
 int packet_mode(RTTreeKind tree) {
     static const int forced = [] {
         const char* e = std::getenv("RTBVH_PACKET_MODE");
@@ -1041,7 +1043,8 @@ int packet_mode(RTTreeKind tree) {
         return -1;
     }();
     if (forced >= 0) return forced;
-    return tree == RT_TREE_MBVH ? (int)kTraceLane : (int)kTraceStatic;
+    (void)tree;
+    return (int)kTraceLane;
 }
 
 // ---- device-resident, asynchronous ---------------------------------------------------------------

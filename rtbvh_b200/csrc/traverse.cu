@@ -1309,6 +1309,12 @@ __global__ void __launch_bounds__(kBlock) trace_packet_persistent_kernel(const D
 #define RTB_LMINBLOCKS 5  // 96 registers: measured 4 blocks (128 regs) 1 781-1 806, 5 blocks 2 008, 6 blocks (80 regs, spills) 1 795, 7 blocks 1 454 Mrays/s
 #endif
 constexpr int kLBlock = RTB_LBLOCK;
+#ifndef RTB_LTRI_NUM
+#define RTB_LTRI_NUM RTB_TRI_NUM  // lane-per-packet kernels: triangle phase when lanes_T * RTB_LTRI_NUM >= lanes_N
+#endif
+#ifndef RTB_LREFILL
+#define RTB_LREFILL RTB_REFILL    // ... and refill once this many lanes are idle
+#endif
 #ifndef RTB_LKEEPDIR
 #define RTB_LKEEPDIR 0  // 1: keep the four directions in registers instead of re-reading them in the triangle phase
 #endif
@@ -1448,7 +1454,7 @@ __global__ void __launch_bounds__(kLBlock, RTB_LMINBLOCKS) trace_mbvh_packet_lan
     };
     for (;;) {
         unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
-        if (idle == 0xFFFFFFFFu || (!exhausted && __popc(idle) >= kRefillIdle)) {
+        if (idle == 0xFFFFFFFFu || (!exhausted && __popc(idle) >= RTB_LREFILL)) {
             while (idle != 0 && !exhausted) {
                 if (res_next >= res_end) {
                     unsigned long long base = 0;
@@ -1491,7 +1497,7 @@ __global__ void __launch_bounds__(kLBlock, RTB_LMINBLOCKS) trace_mbvh_packet_lan
         const int n_t = __popc(t_m), n_n = __popc(act_m & ~t_m);
         const bool in_n = active && !in_t;
         bool done = false;
-        if (n_t * RTB_TRI_NUM >= n_n * RTB_TRI_DEN && n_t > 0) {
+        if (n_t * RTB_LTRI_NUM >= n_n && n_t > 0) {
             if (in_t) {
                 const uint32_t acc = tri_candidate_packet(tree.tris, L.tri_pos, t_min, packets + my, k);
                 L.tri_pos++;
@@ -1535,6 +1541,185 @@ __global__ void __launch_bounds__(kLBlock, RTB_LMINBLOCKS) trace_mbvh_packet_lan
                 }
                 if (L.tri_pos >= L.tri_end) done = lane_advance(tree, nullptr, st, L);
             }
+        }
+        if (done) {
+            fin = true;
+            active = false;
+        }
+    }
+    if (fin) store();
+}
+
+// ================================================================================================
+// Bvh packets, one lane per packet: BvhPacketIndexIterator (iter_indices.rs:172-209) + Aabb::intersect4
+// (aabb.rs:218-244) + BvhNode::sort_nodes4 (bvh_node.rs:180-211) with the structure of the Mbvh kernel above.
+// A popped node is a leaf (its primitives go through the four-ray triangle test) or an inner node whose two
+// children are tested against the four rays: a child is entered when ANY ray passes
+// `t_max > 0 && t_max > t_min && t_min < packet.t[i]`; when both are entered the left child is pushed (visited
+// second) iff ANY ray has t_near_left < t_near_right — compared on all four rays, masks or not, like the SSE code.
+// The root is popped without a box test; a packet with a NaN lane is rejected as a whole (iter_indices.rs:129-144).
+// ================================================================================================
+template <bool EXACT>
+__device__ __forceinline__ void bvh_children_packet(const F8& lc, const F8& rc, const Packet& k, bool& hl, bool& hr, bool& left_nearer) {
+    hl = hr = left_nearer = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float key[2];
+        bool hit[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const float4 lo = c == 0 ? lc.lo : rc.lo, hi = c == 0 ? lc.hi : rc.hi;
+            const float t1x = fmul(fsub(lo.x, k.ox[i]), k.ix[i]), t1y = fmul(fsub(lo.y, k.oy[i]), k.iy[i]), t1z = fmul(fsub(lo.z, k.oz[i]), k.iz[i]);
+            const float t2x = fmul(fsub(hi.x, k.ox[i]), k.ix[i]), t2y = fmul(fsub(hi.y, k.oy[i]), k.iy[i]), t2z = fmul(fsub(hi.z, k.oz[i]), k.iz[i]);
+            const float tmin = vmax<EXACT>(vmin<EXACT>(t1x, t2x), vmax<EXACT>(vmin<EXACT>(t1y, t2y), vmin<EXACT>(t1z, t2z)));
+            const float tmax = vmin<EXACT>(vmax<EXACT>(t1x, t2x), vmin<EXACT>(vmax<EXACT>(t1y, t2y), vmax<EXACT>(t1z, t2z)));
+            key[c] = tmin;
+            hit[c] = tmax > 0.0f && tmax > tmin && tmin < k.t[i];
+        }
+        hl = hl || hit[0];
+        hr = hr || hit[1];
+        left_nearer = left_nearer || (key[0] < key[1]);
+    }
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(kLBlock, RTB_LMINBLOCKS) trace_bvh_packet_lane_kernel(
+    const DeviceTree tree, const RTRayPacket4* __restrict__ packets, size_t n_packets, float t_min,
+    RTHitPacket4* __restrict__ hits, uint8_t* __restrict__ occluded, unsigned long long* __restrict__ counter,
+    uint32_t* __restrict__ overflow) {
+    __shared__ int smem[kSmemStack * kLBlock];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int deep[kSpillStack];
+    Stack st{smem + threadIdx.x, deep, 0, overflow, kLBlock};
+    Packet k;
+    bool exact = false;
+    uint32_t retired = 0;
+    int cur = -1, tri_pos = 0, tri_end = 0;
+    size_t my = 0;
+    bool active = false, fin = false;
+    unsigned long long res_next = 0, res_end = 0;
+    bool exhausted = false;
+    constexpr unsigned kPacketChunk = 32;
+    auto store = [&]() {
+        if (ANY) {
+            const uint32_t v = (retired & 1u) | ((retired & 2u) << 7) | ((retired & 4u) << 14) | ((retired & 8u) << 21);
+            reinterpret_cast<uint32_t*>(occluded)[my] = v;
+        } else {
+            float4* o = reinterpret_cast<float4*>(hits + my);
+            o[0] = make_float4(k.t[0], k.t[1], k.t[2], k.t[3]);
+            o[1] = make_float4(__uint_as_float(k.prim[0]), __uint_as_float(k.prim[1]), __uint_as_float(k.prim[2]),
+                               __uint_as_float(k.prim[3]));
+        }
+    };
+    for (;;) {
+        unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (idle == 0xFFFFFFFFu || (!exhausted && __popc(idle) >= RTB_LREFILL)) {
+            while (idle != 0 && !exhausted) {
+                if (res_next >= res_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(counter, (unsigned long long)kPacketChunk);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (base >= n_packets) {
+                        exhausted = true;
+                        break;
+                    }
+                    res_next = base;
+                    res_end = base + kPacketChunk < n_packets ? base + kPacketChunk : n_packets;
+                }
+                const unsigned long long avail = res_end - res_next;
+                const unsigned want = __popc(idle);
+                const unsigned take = avail < want ? (unsigned)avail : want;
+                const unsigned rank = __popc(idle & lt_mask);
+                if (__any_sync(0xFFFFFFFFu, fin)) {
+                    if (fin) store();
+                    fin = false;
+                }
+                if (!active && rank < take) {
+                    my = (size_t)(res_next + rank);
+                    load_packet(packets, my, k, exact);
+                    st.reset();
+                    retired = 0;
+                    cur = 0;
+                    tri_pos = tri_end = 0;
+                    bool nan = false;  // BvhPacketIndexIterator::new rejects a packet with any NaN origin / direction lane
+                    {
+                        const float4* q = reinterpret_cast<const float4*>(packets + my);
+#pragma unroll
+                        for (int j = 0; j < 6; j++) {
+                            const float4 v = __ldg(q + j);
+                            nan = nan || isnan(v.x) || isnan(v.y) || isnan(v.z) || isnan(v.w);
+                        }
+                    }
+                    if (tree.node_count != 0 && !nan)
+                        active = true;
+                    else
+                        fin = true;
+                }
+                res_next += take;
+                idle = __ballot_sync(0xFFFFFFFFu, !active);
+            }
+            if (idle == 0xFFFFFFFFu) break;
+        }
+        const unsigned act_m = ~idle;
+        const bool in_t = active && tri_pos < tri_end;
+        const unsigned t_m = __ballot_sync(0xFFFFFFFFu, in_t);
+        const int n_t = __popc(t_m), n_n = __popc(act_m & ~t_m);
+        const bool in_n = active && !in_t;
+        bool done = false;
+        if (n_t * RTB_LTRI_NUM >= n_n && n_t > 0) {
+            if (in_t) {
+                const uint32_t acc = tri_candidate_packet(tree.tris, tri_pos, t_min, packets + my, k);
+                tri_pos++;
+                if (ANY && acc) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (acc & (1u << i)) k.t[i] = -1e34f;
+                    retired |= acc;
+                    if (retired == 0xFu) done = true;
+                }
+            }
+        } else {
+            const bool any_exact = __any_sync(0xFFFFFFFFu, in_n && exact) != 0;
+            if (in_n) {
+                const float4* __restrict__ nodes = tree.nodes;
+                const F8 nd = ld256(nodes + (size_t)cur * 2);
+                const int count = __float_as_int(nd.lo.w), left_first = __float_as_int(nd.hi.w);
+                int next = -1;
+                if (count > -1) {
+                    tri_pos = left_first;
+                    tri_end = left_first + count;
+                } else if (left_first > -1) {
+                    const float4* c = nodes + (size_t)left_first * 2;
+                    const F8 lc = ld256(c), rc = ld256(c + 2);
+                    bool hl, hr, ln;
+                    if (any_exact)
+                        bvh_children_packet<true>(lc, rc, k, hl, hr, ln);
+                    else
+                        bvh_children_packet<false>(lc, rc, k, hl, hr, ln);
+                    if (hl && hr) {
+                        if (ln) {
+                            st.push(left_first);
+                            next = left_first + 1;
+                        } else {
+                            st.push(left_first + 1);
+                            next = left_first;
+                        }
+                    } else if (hl) {
+                        next = left_first;
+                    } else if (hr) {
+                        next = left_first + 1;
+                    }
+                }
+                cur = next;
+            }
+        }
+        // a lane without triangles left needs a node: the register hand-over, else the stack; none left: the packet is done
+        if (active && !done && tri_pos >= tri_end && cur < 0) {
+            if (st.sp == 0)
+                done = true;
+            else
+                cur = st.pop();
         }
         if (done) {
             fin = true;
@@ -1808,14 +1993,21 @@ static cudaError_t launch_packets_t(const DeviceTree& tree, const RTRayPacket4* 
                                     RTHitPacket4* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
                                     uint32_t* d_overflow, int mode, cudaStream_t stream) {
     const size_t blocks_needed = ceil_div(n_packets * 4, kBlock);
-    if (mode == kTraceLane && TREE == RT_TREE_MBVH) {  // one lane per packet
-        static const unsigned machine = persistent_grid(trace_mbvh_packet_lane_kernel<ANY>, kLBlock);
+    if (mode == kTraceLane) {  // one lane per packet
         const size_t need = ceil_div(n_packets, kLBlock);
-        const unsigned grid = (unsigned)(need < machine ? need : machine);
         cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
-        trace_mbvh_packet_lane_kernel<ANY><<<grid, kLBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded,
-                                                                        d_counter, d_overflow);
+        if (TREE == RT_TREE_MBVH) {
+            static const unsigned machine = persistent_grid(trace_mbvh_packet_lane_kernel<ANY>, kLBlock);
+            const unsigned grid = (unsigned)(need < machine ? need : machine);
+            trace_mbvh_packet_lane_kernel<ANY><<<grid, kLBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded,
+                                                                            d_counter, d_overflow);
+        } else {
+            static const unsigned machine = persistent_grid(trace_bvh_packet_lane_kernel<ANY>, kLBlock);
+            const unsigned grid = (unsigned)(need < machine ? need : machine);
+            trace_bvh_packet_lane_kernel<ANY><<<grid, kLBlock, 0, stream>>>(tree, d_packets, n_packets, t_min, d_hits, d_occluded,
+                                                                           d_counter, d_overflow);
+        }
     } else if (mode != kTraceStatic) {
         static const unsigned machine = persistent_grid(trace_packet_persistent_kernel<TREE, ANY>);
         const unsigned grid = (unsigned)(blocks_needed < machine ? blocks_needed : machine);

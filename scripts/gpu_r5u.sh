@@ -1,0 +1,11 @@
+#!/bin/bash
+set -u
+TAG=${1:-r5u}
+OUT=gpurun_out
+mkdir -p $OUT
+{
+timeout 300 python scripts/trace_ab.py --packets --name lane_default 2>&1 | tail -1
+for LIB in rtbvh_b200/librtbvh_rs_l*.so; do
+  RTBVH_LIB=$PWD/$LIB timeout 300 python scripts/trace_ab.py --packets 2>&1 | tail -1
+done
+} | tee $OUT/${TAG}_ab.txt
