@@ -59,7 +59,10 @@ constexpr int kBinWords = 7;         // min xyz, max xyz (ordered keys), count
 constexpr int kTaskBinWords = 3 * kBins * kBinWords;  // 336 words = 1344 B per active node
 constexpr float kPad = 0.0001f;
 constexpr int kRadius = 14;          // locb.rs:27
-constexpr uint32_t kSmall = 32;      // subtrees with <= kSmall primitives are finished by one warp (sah_small_kernel)
+#ifndef RTB_SMALL
+#define RTB_SMALL 32
+#endif
+constexpr uint32_t kSmall = RTB_SMALL;  // subtrees with <= kSmall (<= 32) primitives are finished by one warp (sah_small_kernel)
 // Level tasks with <= kWarpTask primitives are binned, split AND partitioned by one warp each (sah_warp_task_kernel: bins
 // and the task's index range in shared memory, no global atomics, no global partition pass); larger ("span-class") tasks go
 // through the span-based bin kernel + sah_split_kernel + the segmented-scan partition.  pos_task holds, per index
@@ -177,8 +180,13 @@ __global__ void tri_boxes_kernel(const float* __restrict__ verts, uint32_t strid
     bb[(size_t)i * 2 + 1] = make_float4(mx[0], mx[1], mx[2], 0.f);
 }
 
-// Aabb::union_of_list without the pad (aabb.rs:125-129): block reduce + 6 key atomics
+// Aabb::union_of_list without the pad (aabb.rs:125-129): warp shuffle reduce, block reduce through shared-memory key atomics,
+// then 6 global key atomics per BLOCK (per warp they were 57 k atomics on six addresses: 44 us of a 1 Mi-triangle build)
 __global__ void world_reduce_kernel(const float4* __restrict__ bb, uint32_t n, uint32_t* __restrict__ keys) {
+    __shared__ uint32_t s_keys[6];
+    if (threadIdx.x < 3) s_keys[threadIdx.x] = fkey(1e34f);
+    else if (threadIdx.x < 6) s_keys[threadIdx.x] = fkey(-1e34f);
+    __syncthreads();
     Box b = box_empty();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         b = box_union(b, load_box(bb, i));
@@ -193,10 +201,13 @@ __global__ void world_reduce_kernel(const float4* __restrict__ bb, uint32_t n, u
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            atomicMin(&keys[k], fkey(b.mn[k]));
-            atomicMax(&keys[3 + k], fkey(b.mx[k]));
+            atomicMin(&s_keys[k], fkey(b.mn[k]));
+            atomicMax(&s_keys[3 + k], fkey(b.mx[k]));
         }
     }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicMin(&keys[threadIdx.x], s_keys[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicMax(&keys[threadIdx.x], s_keys[threadIdx.x]);
 }
 __global__ void world_init_kernel(uint32_t* keys) {
     if (threadIdx.x < 3) keys[threadIdx.x] = fkey(1e34f);

@@ -1993,6 +1993,10 @@ static cudaError_t launch_packets_t(const DeviceTree& tree, const RTRayPacket4* 
                                     RTHitPacket4* d_hits, uint8_t* d_occluded, unsigned long long* d_counter,
                                     uint32_t* d_overflow, int mode, cudaStream_t stream) {
     const size_t blocks_needed = ceil_div(n_packets * 4, kBlock);
+    // the lane kernels move packets and results with 16-byte accesses (any hit: one 32-bit word per packet); the C types only
+    // promise 4-byte alignment, so oddly placed caller buffers take the quad kernel (scalar accesses)
+    const bool aligned = ((uintptr_t)d_packets & 15u) == 0 && ((uintptr_t)d_hits & 15u) == 0 && ((uintptr_t)d_occluded & 3u) == 0;
+    if (mode == kTraceLane && !aligned) mode = kTraceStatic;
     if (mode == kTraceLane) {  // one lane per packet
         const size_t need = ceil_div(n_packets, kLBlock);
         cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);

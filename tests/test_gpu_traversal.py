@@ -478,3 +478,36 @@ def test_split_origin_direction_input(A, O, W, teapot, teapot_trees):
         assert len(sc.intersect_od(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))) == 0
     finally:
         sc.free()
+
+
+@pytest.mark.parametrize("tree_name", ["bvh", "mbvh"])
+def test_packet_calls_with_oddly_aligned_device_buffers(A, O, W, teapot, teapot_trees, tree_name):
+    """RTRayPacket4 / RTHitPacket4 only promise 4-byte alignment.  The one-lane-per-packet kernels use 16-byte accesses and
+    must hand oddly placed buffers to the scalar quad kernel: same results either way (closest and any hit)."""
+    import torch
+    tris = teapot["tris"]
+    bvh, m = teapot_trees["sah"]
+    sc = A.Scene(tris, bvh=A.Bvh.from_arrays(bvh.nodes, bvh.indices), mbvh=A.Mbvh.from_arrays(m.nodes, m.indices))
+    try:
+        rays = np.concatenate([W.camera_rays(W.benchmark_camera(96, 96)), W.random_rays(10_000, *W.bounds(tris), seed=77)])
+        packets = W.pack4(rays[: len(rays) // 4 * 4])
+        n = len(packets)
+        tree, otree = (A.TREE_BVH, bvh) if tree_name == "bvh" else (A.TREE_MBVH, m)
+        want = O.trace_packets(otree, tris, packets)[0]
+        want_any = O.trace_packets(otree, tris, packets, mode="any")[0]
+        flat = torch.from_numpy(packets.view(np.float32).reshape(-1).copy())
+        stream = torch.cuda.current_stream().cuda_stream
+        for shift in (0, 1):  # 0: 16-byte aligned (lane kernels); 1: shifted by one float (quad kernels)
+            d_in = torch.empty(flat.numel() + 4, dtype=torch.float32, device="cuda")
+            d_in[shift: shift + flat.numel()] = flat.cuda()
+            d_out = torch.zeros(n * 8 + 4, dtype=torch.float32, device="cuda")
+            d_occ = torch.zeros(n * 4 + 8, dtype=torch.uint8, device="cuda")
+            sc.intersect_packets_device(d_in[shift:], n, d_out[shift:], tree, stream=stream)
+            sc.occluded_packets_device(d_in[shift:], n, d_occ[shift:], tree, stream=stream)
+            torch.cuda.synchronize()
+            got = d_out[shift: shift + n * 8].cpu().numpy().view(A.HIT4_DTYPE).reshape(-1)
+            assert np.array_equal(got, want), f"shift {shift}"
+            assert np.array_equal(d_occ[shift: shift + n * 4].cpu().numpy().reshape(n, 4), want_any), f"shift {shift}"
+        assert not sc.stack_overflowed()
+    finally:
+        sc.free()
