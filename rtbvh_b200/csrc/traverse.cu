@@ -488,7 +488,7 @@ __device__ __forceinline__ bool packet_step(const DeviceTree& tree, RayRegs& r, 
 
 
 // ================================================================================================
-// Phase-split stepping (the default single-ray kernel).  ncu of the one-step-per-iteration kernel
+// Phase-split stepping (RTBVH_TRACE_MODE=phased; the structure of the packet kernels).  ncu of the one-step-per-iteration kernel
 // (profiles/r2g_*): 14.7 of 32 lanes active per issued instruction, because every iteration ran
 // "node visit, then the triangles of its hit leaf slots" and ~20 % of the lanes had triangles —
 // the other ~80 % idled through one or more ~80-instruction triangle tests per visit.
