@@ -334,7 +334,7 @@ __device__ __forceinline__ void bin_run(uint32_t* sb, uint32_t pos, uint32_t run
                                         const uint32_t* __restrict__ idx, const float4* __restrict__ bb,
                                         const float* __restrict__ cen, uint32_t cstride, uint32_t* __restrict__ g,
                                         uint16_t* __restrict__ binidx) {
-    const unsigned lane = COPIES == 32 ? (threadIdx.x & 31u) : 0u;
+    const unsigned lane = threadIdx.x & (unsigned)(COPIES - 1);  // COPIES is a power of two <= 32
     for (int w = threadIdx.x; w < kTaskBinWords * COPIES; w += kBinBlock) {
         const int f = (w / COPIES) % kBinWords;
         sb[w] = f < 3 ? fkey(1e34f) : (f < 6 ? fkey(-1e34f) : 0u);
@@ -379,6 +379,10 @@ __device__ __forceinline__ void bin_run(uint32_t* sb, uint32_t pos, uint32_t run
 // PRIV = false: the small-build variant without the lane-private path (1.3 KB instead of 42 KB of shared memory per block,
 // 8 instead of 5 blocks per SM): below a few M primitives a block sees too few primitives per run for the copies to pay
 // (measured at 1 Mi triangles: 0.55 ms per build for this variant, 0.71-0.77 ms with lane-private runs).
+#ifndef RTB_BIN_COPIES
+#define RTB_BIN_COPIES 1  // small-build variant: copies of the bins per block (lane & (COPIES - 1) picks one): fewer replays
+#endif
+constexpr int kBinCopies = RTB_BIN_COPIES;
 template <bool PRIV>
 __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __restrict__ idx, const int32_t* __restrict__ pos_task,
                                                             uint32_t n, uint32_t span, const Task* __restrict__ tasks,
@@ -388,7 +392,7 @@ __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __re
                                                             uint16_t* __restrict__ binidx /* 3 x 4-bit bin per position */,
                                                             const LevelState* __restrict__ state,
                                                             const uint32_t* __restrict__ span_tasks /* of this level */) {
-    __shared__ uint32_t sb[kTaskBinWords * (PRIV ? 32 : 1)];
+    __shared__ uint32_t sb[kTaskBinWords * (PRIV ? 32 : kBinCopies)];
     __shared__ uint32_t s_next;
     const uint64_t begin64 = (uint64_t)blockIdx.x * span;
     if (begin64 >= n || state->A == 0 || *span_tasks == 0) return;  // deep levels: only warp-class tasks are left
@@ -402,6 +406,8 @@ __global__ void __launch_bounds__(kBinBlock) sah_bin_kernel(const uint32_t* __re
             uint32_t* g = bins + (size_t)a.slot * kTaskBinWords;
             if (PRIV && run_end - pos >= kLanePrivateRun)
                 bin_run<PRIV ? 32 : 1>(sb, pos, run_end, a, idx, bb, cen, cstride, g, binidx);
+            else if (!PRIV && kBinCopies > 1 && run_end - pos >= 64u * kBinCopies)
+                bin_run<kBinCopies>(sb, pos, run_end, a, idx, bb, cen, cstride, g, binidx);
             else
                 bin_run<1>(sb, pos, run_end, a, idx, bb, cen, cstride, g, binidx);
             pos = run_end;
