@@ -328,6 +328,32 @@ def run_gpu(args):
         if not info["fused_gather_equals_all_gather"]:
             raise RuntimeError("fused gather buffer differs from the NCCL all_gather of the same records")
 
+    # ---- the same frames as RayPacket4 (four x-adjacent pixels, examples/benchmark.rs:135-141): reported next to the headline
+    try:
+        n_pk = min(3, ring)
+        d_pk = []
+        for b in range(n_pk):
+            r = d_rays[b].view(rays_per_step // 4, 4, 8)
+            d_pk.append(torch.stack([r[:, :, 0], r[:, :, 1], r[:, :, 2], r[:, :, 4], r[:, :, 5], r[:, :, 6], r[:, :, 7]],
+                                    dim=1).contiguous().view(-1))
+        d_pk_hits = torch.empty(rays_per_step * 2, dtype=torch.float32, device="cuda")
+        pk_steps = max(3, min(args.steps, 12))
+        for k in range(3):
+            scene.intersect_packets_device(d_pk[k % n_pk], rays_per_step // 4, d_pk_hits, api.TREE_MBVH, stream=stream)
+        barrier()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for k in range(pk_steps):
+            scene.intersect_packets_device(d_pk[k % n_pk], rays_per_step // 4, d_pk_hits, api.TREE_MBVH, stream=stream)
+        pe1.record()
+        torch.cuda.synchronize()
+        info["packet4"] = {"value": world * pk_steps * rays_per_step / pe0.elapsed_time(pe1) / 1e3, "unit": "Mrays/s",
+                           "steps": pk_steps, "kernel": "trace_mbvh_packet_lane_kernel<closest> (one lane per RayPacket4)",
+                           "note": "rank-local device time (not max over ranks); packets of 4 x-adjacent pixels of the same frames"}
+        del d_pk, d_pk_hits
+    except Exception as e:  # an extra: never costs the bench line
+        info["packet4"] = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- e2e: host buffers through rtbvh_gpu_intersect -------------------------------------------
     n_host = min(3, ring)
     h_rays = [torch.empty(rays_per_step * 8, dtype=torch.float32).pin_memory() for _ in range(n_host)]
@@ -421,20 +447,29 @@ def run_gpu(args):
         if not args.no_cpu:
             from oracle import oracle as O
             # bounded sample: the rays of up to 16 timed steps (128 M rays, ~10 s of CPU work on 16 cores)
-            n_batches = min(ring, 16)
+            n_batches = min(ring, 16) if world == 1 else 1
             host_rays = np.concatenate([d_rays[b].cpu().numpy().view(api.RAY_DTYPE).reshape(-1) for b in range(n_batches)])
             otree = O.Mbvh(mbvh.nodes.copy(), mbvh.indices.copy())
-            rate, n_s, per_ray, max_stack, threads = cpu_sample_rate(O, otree, tris, host_rays)
+            if world == 1:
+                rate, n_s, per_ray, max_stack, threads = cpu_sample_rate(O, otree, tris, host_rays)
+            else:
+                # N > 1: the CPU baseline is an N = 1 figure (the other ranks would idle in the barrier while rank 0 times it);
+                # only the oracle's work counters are taken here, on 1 M rays, for the roofline's algorithmic bytes
+                threads = host_threads()
+                nc = min(len(host_rays), 1_000_000)
+                _, _, cnt = O.trace(otree, tris, host_rays[:nc], threads=threads, counters=True)
+                rate, n_s, per_ray, max_stack = None, nc, {k: cnt[k] / nc for k in ("node_visits", "prim_tests")}, cnt["max_stack"]
             nm, npr = per_ray["node_visits"], per_ray["prim_tests"]
             bytes_per_ray = 32 + 8 + 128 * nm + 40 * npr
-            cpu = {"value": rate, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                   "sample": f"first {n_s} rays of the timed workload (the very rays the GPU steps trace), Mbvh single-ray "
-                             f"closest hit, OpenMP dynamic chunks of 1000",
-                   "single_thread_value": cpu_single_thread_rate(O, otree, tris, host_rays)}
-            tb = oracle_threaded_build_ms(O, tris)
-            cpu["binned_sah_build_ms_per_mtri"] = tb / (N_TRIS / 1e6) if tb else None
-            cpu["binned_sah_build_note"] = (f"the port's binned-SAH builder on this scene with the reference's threaded scheduling "
-                                            f"(subtrees > 1024 primitives on other threads, src/utils.rs:189-289), {threads} threads")
+            if rate is not None:
+                cpu = {"value": rate, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                       "sample": f"first {n_s} rays of the timed workload (the very rays the GPU steps trace), Mbvh single-ray "
+                                 f"closest hit, OpenMP dynamic chunks of 1000",
+                       "single_thread_value": cpu_single_thread_rate(O, otree, tris, host_rays)}
+                tb = oracle_threaded_build_ms(O, tris)
+                cpu["binned_sah_build_ms_per_mtri"] = tb / (N_TRIS / 1e6) if tb else None
+                cpu["binned_sah_build_note"] = (f"the port's binned-SAH builder on this scene with the reference's threaded scheduling "
+                                                f"(subtrees > 1024 primitives on other threads, src/utils.rs:189-289), {threads} threads")
             # parity spot check inside the bench: oracle vs GPU on the sample
             want, _, _ = O.trace(otree, tris, host_rays[:200_000], threads=threads)
             got = d_hits[0][: 200_000 * 2].cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
