@@ -2766,7 +2766,12 @@ struct DevCache {
         }();
         return v;
     }
-} g_dev_cache;
+};
+DevCache& dev_cache() {
+    static DevCache* c = new DevCache;  // leaked on purpose: scenes may be released during static destruction
+    return *c;
+}
+#define g_dev_cache dev_cache()
 }  // namespace
 
 cudaError_t dev_block_alloc(void** p, size_t bytes) {
