@@ -164,6 +164,9 @@ def run_gpu(args):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     api.set_device(local)
+    # everything below runs on ONE non-default stream: the fused gather's step barrier lives on a side stream, and a side stream
+    # only overlaps work that is not on the legacy default stream (which synchronises with every blocking stream)
+    torch.cuda.set_stream(torch.cuda.Stream())
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     all_cpus = set(os.sched_getaffinity(0))
@@ -300,6 +303,8 @@ def run_gpu(args):
             step_ev[k].record()
     for w in works[-2:]:
         w.wait()
+    if fused is not None:  # the last step's gather is complete when its barrier has passed: inside the timed region
+        fused.wait(args.warmup + args.steps - 1, stream)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)

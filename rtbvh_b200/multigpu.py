@@ -60,18 +60,25 @@ def all_gather_ragged(local, counts: list[int]):
 class FusedGather:
     """Gather of the hit records fused into the traversal kernel (rtbvh_gpu_*_device_scatter): every rank owns
     `buffers` gather buffers of `world * rays_per_rank` records that its peers map with cudaIpc; the kernel writes
-    each record, the moment its ray finishes, into slot [rank * rays_per_rank + i] of EVERY rank's buffer (P2P stores
-    over NVLink / NVSwitch), and a one-block device barrier (rtbvh_gpu_peer_barrier) closes the step — no NCCL call on
-    the data path.  Handles travel once, out of band, through torch.distributed (any backend).
+    each record into slot [rank * rays_per_rank + i] of EVERY rank's buffer (P2P stores over NVLink / NVSwitch), and a
+    one-block device barrier (rtbvh_gpu_peer_barrier) closes the step — no NCCL call on the data path.  Handles travel
+    once, out of band, through torch.distributed (any backend).
 
-    Buffer discipline: step k uses buffer k % buffers; after `barrier(k)` returns (stream-ordered) buffer k % buffers
-    holds the records of all ranks, and every rank has finished step k's kernel, hence its stream-ordered reads of
-    step k-1: with two buffers, step k+1 may overwrite the buffer of step k-1."""
+    The barrier is OFF the critical path: step k's barrier runs on a side stream behind an event recorded after step k's
+    kernel, and the kernel of step k only waits for the barrier of step k - 2 (long finished by then), so neither the
+    barrier's launch nor the wait for the slowest rank sits between two traversal kernels (8 GPUs: 4.41 -> see
+    profiles/r5n_gather_ab.txt for what the in-line barrier cost).
 
-    def __init__(self, rays_per_rank: int, record_bytes: int, buffers: int = 2):
+    Buffer discipline: step k uses buffer k % buffers (default 4).  `wait(k, stream)` makes `stream` wait until buffer
+    k % buffers holds the records of ALL ranks; a consumer of step k must be enqueued (behind `wait(k, ...)`) before the
+    call of step k + 2 on the same stream: the barrier of step k + 1 then certifies that every rank has consumed step k,
+    and step k + 4 — the next writer of that buffer — waits for the barrier of step k + 2."""
+
+    def __init__(self, rays_per_rank: int, record_bytes: int, buffers: int = 4):
+        import torch
         import torch.distributed as dist
         from . import api
-        self.api = api
+        self.api, self.torch = api, torch
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.rays_per_rank, self.record_bytes = rays_per_rank, record_bytes
         self.own = [api.PeerBuffer(self.world * rays_per_rank * record_bytes) for _ in range(buffers)]
@@ -93,21 +100,43 @@ class FusedGather:
             self.dests.append(row)
         self.flag_dests = self.dests.pop()
         self.step = 0
+        self.side = torch.cuda.Stream()
+        self.done = {}        # step -> event recorded on the side stream behind that step's barrier
         dist.barrier()
 
     def buffer_ptr(self, k: int) -> int:
         return self.own[k % len(self.own)].ptr.value
 
+    def _main(self, stream: int):
+        return self.torch.cuda.ExternalStream(stream) if stream else self.torch.cuda.default_stream()
+
+    def wait(self, k: int, stream: int = 0):
+        """Stream-orders `stream` behind the barrier of step k (its gather buffer is complete on this rank afterwards)."""
+        ev = self.done.get(k)
+        if ev is not None:
+            self._main(stream).wait_event(ev)
+
     def intersect(self, scene, d_rays, n: int, k: int, d_hits=None, tree=None, stream: int = 0, any_hit: bool = False):
-        """Traces this rank's shard for step k, scattering into every rank's buffer k % buffers, then the barrier."""
+        """Traces this rank's shard for step k, scattering into every rank's buffer k % buffers; the step barrier follows on
+        the side stream.  Steps must be issued with consecutive k."""
         tree = self.api.TREE_MBVH if tree is None else tree
+        main = self._main(stream)
+        self.wait(k - 2, stream)  # every rank is past step k - 2, hence has consumed what step k overwrites (see above)
         fn = scene.occluded_device_scatter if any_hit else scene.intersect_device_scatter
         fn(d_rays, n, self.dests[k % len(self.own)], self.rank * self.rays_per_rank, d_hits, tree, stream)
+        after = self.torch.cuda.Event()
+        after.record(main)
+        self.side.wait_event(after)
         self.step += 1
-        self.api.peer_barrier(self.flag_dests, self.rank, self.step, stream)
+        self.api.peer_barrier(self.flag_dests, self.rank, self.step, self.side.cuda_stream)
+        ev = self.torch.cuda.Event()
+        ev.record(self.side)
+        self.done[k] = ev
+        self.done.pop(k - 8, None)
 
     def close(self):
         import torch.distributed as dist
+        self.torch.cuda.synchronize()
         dist.barrier()
         for p in self.opened:
             self.api.PeerBuffer.close(p)

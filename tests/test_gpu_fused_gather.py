@@ -45,6 +45,7 @@ def _worker(rank, world, port, n_per_rank, steps, any_hit, out_dir, push=True, t
     scene.set_ray_tiling(tile_w)  # work-order hint: 8x8 tiles inside whole bands of 8 rows of tile_w rays (results unchanged)
     rec = 1 if any_hit else 8
     fg = MG.FusedGather(n_per_rank, rec)
+    torch.cuda.set_stream(torch.cuda.Stream())  # not the legacy default stream: the barrier's side stream overlaps it
     stream = torch.cuda.current_stream().cuda_stream
     n_total = world * n_per_rank
     snaps = []
@@ -54,7 +55,8 @@ def _worker(rank, world, port, n_per_rank, steps, any_hit, out_dir, push=True, t
         d_rays = torch.from_numpy(rays[lo: lo + n_per_rank].view(np.float32).reshape(-1).copy()).cuda()
         local = torch.zeros(n_per_rank * rec, dtype=torch.uint8, device="cuda")
         fg.intersect(scene, d_rays, n_per_rank, k, d_hits=local, stream=stream, any_hit=any_hit)
-        # stream-ordered consumer of step k: snapshot the gather buffer after the barrier
+        # stream-ordered consumer of step k: snapshot the gather buffer behind the step's barrier (side stream)
+        fg.wait(k, stream)
         snap = api.device_view(fg.buffer_ptr(k), n_total * rec).clone()
         snaps.append((snap, local))
     torch.cuda.synchronize()
