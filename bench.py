@@ -503,7 +503,9 @@ def run_gpu(args):
                                     f"P2P stores into every rank's gather buffer ({world * rays_per_step * 8} B per step per "
                                     "GPU) + one-block device barrier per step, no NCCL on the data path" if gather == "fused"
                                     else "single GPU" if world == 1 else "rays sharded, tree replicated, no gather"), **info},
-            "clocks": clocks, "gpu_launches": args.steps,
+            "clocks": clocks,
+            # own kernels per rank inside the timed region: one traversal launch per step (+ one step-barrier kernel with the fused gather)
+            "gpu_launches": args.steps * (2 if gather == "fused" else 1),
             "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": rays_per_step * 24,
                     "d2h_bytes_per_step": rays_per_step * 8, "steps": e2e_steps,
                     "host_equals_resident": same and same_async and same_od and same_cam,
