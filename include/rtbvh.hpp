@@ -467,6 +467,23 @@ class Scene {
     Scene(const Scene&) = delete;
     Scene& operator=(const Scene&) = delete;
     Scene(Scene&& o) noexcept : h_(o.h_) { o.h_ = 0; }
+    // Multi-GPU: build once, replicate device to device.  export_handle() / import_handle(): one process per GPU (ship the 512
+    // bytes over MPI / a pipe; keep this scene alive until every importer has returned); clone_to(): one process, several GPUs.
+    RTGpuSceneExport export_handle() const {
+        RTGpuSceneExport x;
+        if (rtbvh_gpu_scene_export(h_, &x) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
+        return x;
+    }
+    static Scene import_handle(const RTGpuSceneExport& x) {
+        Scene s;
+        if (rtbvh_gpu_scene_import(&x, &s.h_) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
+        return s;
+    }
+    Scene clone_to(int device) const {
+        Scene s;
+        if (rtbvh_gpu_scene_clone(h_, device, &s.h_) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
+        return s;
+    }
     // Bvh::refit for a resident scene: same triangles, new positions; also refreshes the Mbvh and the triangle records
     void refit(const float* vertices, size_t vertex_stride, size_t triangle_count) {
         if (rtbvh_gpu_scene_refit(h_, vertices, vertex_stride, triangle_count) != Ok) throw std::runtime_error(rtbvh_gpu_last_error());
