@@ -176,3 +176,176 @@ def test_python_builder_produces_the_oracles_bytes(O, W, teapot, scene, leaf):
     assert np.array_equal(cnt, want.nodes["count"]) and np.array_equal(lf, want.nodes["left_first"]), "topology / numbering differs"
     assert mn.view(np.uint32).tobytes() == np.ascontiguousarray(want.nodes["min"]).view(np.uint32).tobytes(), "min corners differ"
     assert mx.view(np.uint32).tobytes() == np.ascontiguousarray(want.nodes["max"]).view(np.uint32).tobytes(), "max corners differ"
+
+
+# ---- locally-ordered clustering ---------------------------------------------------------------------------------------
+# Followed sources: LocallyOrderedClusteringBuilder::build / cluster  src/builders/locb.rs:48-328 (search radius 14, first
+# strict minimum scanning j = i-14 .. i-1 then i+1 .. i+14, merge iff mutual, the lower index keeps the parent slot),
+# MortonEncoder::{new, encode, get_sorted_indices} + morton_split  src/morton.rs:10-102 (stable sort by code),
+# prefix_sum (inclusive)  src/utils.rs:42-58.
+def _morton_split(v):
+    v = v & 0x3FF
+    out = 0
+    for b in range(10):
+        out |= ((v >> b) & 1) << (3 * b)
+    return out
+
+
+def build_locb(aabb_min, aabb_max, centers):
+    n = len(centers)
+    delta = F(0.0001)
+    wmin, wmax = aabb_min.min(axis=0) - delta, aabb_max.max(axis=0) + delta
+    world_to_grid = F(1024.0) * (F(1.0) / (wmax - wmin))
+    grid_offset = (-wmin) * world_to_grid
+    grid = centers * world_to_grid + grid_offset
+    g = np.clip(np.nan_to_num(grid, nan=0.0).astype(np.float64).astype(np.int64), 0, 1023)  # `as i32` truncates; then min / max
+    codes = np.array([_morton_split(int(x)) | (_morton_split(int(y)) << 1) | (_morton_split(int(z)) << 2) for x, y, z in g],
+                     dtype=np.uint32)
+    prim_indices = np.argsort(codes, kind="stable").astype(np.uint32)
+    nc = 2 * n - 1
+    bmin, bmax = np.zeros((nc, 3), dtype=F), np.zeros((nc, 3), dtype=F)
+    count, left_first = np.full(nc, -1, dtype=np.int32), np.zeros(nc, dtype=np.int32)
+    begin, end, previous_end = nc - n, nc, nc
+    bmin[begin:end] = aabb_min[prim_indices] - delta
+    bmax[begin:end] = aabb_max[prim_indices] + delta
+    count[begin:end] = 1
+    left_first[begin:end] = np.arange(n, dtype=np.int32)
+    cur = [bmin, bmax, count, left_first]
+    nxt = [a.copy() for a in cur]
+    R = 14
+    fmax = np.finfo(F).max
+    iterations = 0
+    while end - begin > 1:
+        iterations += 1
+        imn, imx, icnt, ilf = cur
+        m = end - begin
+        lo, hi = imn[begin:end], imx[begin:end]
+        # candidate matrix in scan order: columns 0..13 = j = i-14 .. i-1, columns 14..27 = j = i+1 .. i+14
+        dist = np.full((m, 2 * R), fmax, dtype=F)
+        for d in range(1, R + 1):
+            if d >= m:
+                break
+            umn, umx = np.minimum(lo[:-d], lo[d:]), np.maximum(hi[:-d], hi[d:])
+            dd = umx - umn
+            ha = (dd[:, 0] + dd[:, 1]) * dd[:, 2] + dd[:, 0] * dd[:, 1]
+            dist[d:, R - d] = ha        # backward neighbour j = i - d of i
+            dist[:-d, R + d - 1] = ha   # forward neighbour j = i + d of i
+        col = np.argmin(dist, axis=1)   # first minimum in scan order == first strict minimum
+        off = np.where(col < R, col - R, col - R + 1)
+        nb = np.arange(m) + off
+        i_all = np.arange(m)
+        mutual = nb[nb] == i_all
+        merged = np.cumsum((mutual & (i_all < nb)).astype(np.int64))
+        merged_count = int(merged[-1])
+        unmerged_count = m - merged_count
+        children_count = 2 * merged_count
+        children_begin = end - children_count
+        unmerged_begin = end - (children_count + unmerged_count)
+        omn, omx, ocnt, olf = nxt
+        for i in range(m):
+            j = int(nb[i])
+            if mutual[i]:
+                if i < j:
+                    dst = unmerged_begin + j - int(merged[j])
+                    first_child = children_begin + (int(merged[i]) - 1) * 2
+                    omn[dst] = np.minimum(lo[j], lo[i])
+                    omx[dst] = np.maximum(hi[j], hi[i])
+                    ocnt[dst], olf[dst] = -1, first_child
+                    for a, b in zip(nxt, cur):
+                        a[first_child] = b[begin + i]
+                        a[first_child + 1] = b[begin + j]
+            else:
+                dst = unmerged_begin + i - int(merged[i])
+                for a, b in zip(nxt, cur):
+                    a[dst] = b[begin + i]
+        for a, b in zip(nxt, cur):
+            a[end:previous_end] = b[end:previous_end]
+        cur, nxt = nxt, cur
+        previous_end = end
+        begin, end = unmerged_begin, children_begin
+    return cur, prim_indices, iterations
+
+
+@pytest.mark.parametrize("scene", ["teapot", "soup900"])
+def test_python_locb_produces_the_oracles_bytes(O, W, teapot, scene):
+    tris = teapot["tris"] if scene == "teapot" else W.soup(900, seed=0xB11D)
+    aabbs, centers = O.prims_from_triangles(tris)
+    rc, want = O.build(O.LOCB, aabbs, centers, 1)
+    assert rc == 0
+    (mn, mx, cnt, lf), idx, iters = build_locb(np.ascontiguousarray(aabbs["min"], dtype=F), np.ascontiguousarray(aabbs["max"], dtype=F),
+                                               np.ascontiguousarray(centers, dtype=F).reshape(-1, 3))
+    assert np.array_equal(idx, want.indices), "Morton order differs"
+    assert np.array_equal(cnt, want.nodes["count"]) and np.array_equal(lf, want.nodes["left_first"]), "topology differs"
+    assert mn.view(np.uint32).tobytes() == np.ascontiguousarray(want.nodes["min"]).view(np.uint32).tobytes()
+    assert mx.view(np.uint32).tobytes() == np.ascontiguousarray(want.nodes["max"]).view(np.uint32).tobytes()
+    if scene == "teapot":
+        assert iters == 37  # the survey's own count
+
+
+# ---- collapse to the 4-wide layout --------------------------------------------------------------------------------------
+# Followed sources: Mbvh::construct  src/bvh.rs:381-404; MbvhNode::merge_nodes  src/mbvh_node.rs:297-411 (all four slots start
+# with the PARENT's box; a grandchild's box overwrites it, a direct leaf child keeps it; m-nodes numbered by pool_ptr in
+# recursion order); MbvhNode::new  src/mbvh_node.rs:55-78.
+def collapse(nodes):
+    import sys
+    n = len(nodes)
+    M = {k: np.full((n, 4), v, dtype=F) for k, v in (("min_x", 1e34), ("min_y", 1e34), ("min_z", 1e34), ("max_x", -1e34),
+                                                     ("max_y", -1e34), ("max_z", -1e34))}
+    children, counts = np.full((n, 4), -1, dtype=np.int32), np.full((n, 4), -1, dtype=np.int32)
+    pool = [1]
+    is_leaf = lambda k: int(nodes["count"][k]) >= 0
+    lf_of = lambda k: int(nodes["left_first"][k])
+
+    def set_bounds(m, slot, k):
+        for a, ax in enumerate("xyz"):
+            M["min_" + ax][m, slot] = nodes["min"][k][a]
+            M["max_" + ax][m, slot] = nodes["max"][k][a]
+
+    def merge(m, cur):
+        for i in range(4):
+            set_bounds(m, i, cur)
+        sel, leafs = [-1] * 4, [-1] * 4
+        if lf_of(cur) >= 0:
+            for side, base in ((lf_of(cur), 0), (lf_of(cur) + 1, 2)):
+                if side < n and lf_of(side) >= 0:
+                    if is_leaf(side):
+                        sel[base], leafs[base] = lf_of(side), int(nodes["count"][side])
+                    else:
+                        for off in (0, 1):
+                            g = lf_of(side) + off
+                            if is_leaf(g):
+                                sel[base + off], leafs[base + off] = lf_of(g), int(nodes["count"][g])
+                            else:
+                                sel[base + off] = g
+                            set_bounds(m, base + off, g)
+        for i in range(4):
+            node, cnt = sel[i], leafs[i]
+            if node >= 0 and cnt >= 0:
+                children[m, i], counts[m, i] = node, cnt
+                continue
+            if node == -1:
+                continue
+            if is_leaf(node):
+                children[m, i], counts[m, i] = lf_of(node), int(nodes["count"][node])
+                set_bounds(m, i, node)
+            else:
+                new_m = pool[0]
+                pool[0] += 1
+                children[m, i] = new_m
+                set_bounds(m, i, node)
+                merge(new_m, node)
+
+    sys.setrecursionlimit(10000)
+    merge(0, 0)
+    k = pool[0]
+    return {**{a: b[:k] for a, b in M.items()}, "children": children[:k], "counts": counts[:k]}
+
+
+@pytest.mark.parametrize("builder", ["sah", "locb"])
+def test_python_collapse_produces_the_oracles_bytes(O, teapot, teapot_trees, builder):
+    bvh, want = teapot_trees[builder]
+    got = collapse(bvh.nodes)
+    assert len(got["children"]) == len(want.nodes)
+    for key in ("min_x", "max_x", "min_y", "max_y", "min_z", "max_z"):
+        assert got[key].view(np.uint32).tobytes() == np.ascontiguousarray(want.nodes[key]).view(np.uint32).tobytes(), key
+    assert np.array_equal(got["children"], want.nodes["children"]) and np.array_equal(got["counts"], want.nodes["counts"])
