@@ -20,7 +20,9 @@
 // checks, five_triangle no-panic) are ported in tests/test_oracle_kats.py.  Hit ids,
 // packets, any-hit, SAH values and refit are NOT pinned by any reference test:
 // for those "parity unpinned" — this restatement is the definition, cross-checked
-// against brute force.
+// against brute force and against a second restatement written separately from the Rust
+// sources in plain Python (tests/test_oracle_second_opinion*.py: bit-identical t / ids for the
+// eight traversal flavours, byte-identical trees for binned SAH, LOCB and the collapse).
 #pragma once
 #include <algorithm>
 #include <cmath>
