@@ -68,6 +68,36 @@ __device__ __forceinline__ F8 ld256(const void* p) {
     return r;
 }
 
+// Experiment knobs (A/B only; defaults are the plain loads above): RTB_TRI_NOALLOC = 1 loads triangle records without
+// allocating in L1 (they are touched once or twice, the nodes many times), RTB_NODE_EVICT_LAST = 1 marks node lines evict-last in L1.
+#ifndef RTB_TRI_NOALLOC
+#define RTB_TRI_NOALLOC 0
+#endif
+#ifndef RTB_NODE_EVICT_LAST
+#define RTB_NODE_EVICT_LAST 0
+#endif
+__device__ __forceinline__ F8 ld256_tri(const void* p) {
+#if RTB_TRI_NOALLOC
+    F8 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
+    return r;
+#else
+    return ld256(p);
+#endif
+}
+__device__ __forceinline__ F8 ld256_node(const void* p) {
+#if RTB_NODE_EVICT_LAST
+    F8 r;
+    asm("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+        : "l"(p));
+    return r;
+#else
+    return ld256(p);
+#endif
+}
+
 struct DeviceTree {
     const float4* nodes;      // Bvh: 2 float4 per node; Mbvh: 8 float4 per node
     uint32_t node_count;

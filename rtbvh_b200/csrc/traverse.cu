@@ -87,7 +87,7 @@ __device__ __forceinline__ void finish_ray_setup(RayRegs& r) {
 // an earlier accepted hit) only lower the reported id (north-star rule).
 template <bool PACKET>
 __device__ __forceinline__ bool tri_candidate(const TriRec* __restrict__ tris, int pos, RayRegs& r) {
-    const F8 ab = ld256(&tris[pos].a);
+    const F8 ab = ld256_tri(&tris[pos].a);
     const float4 A = ab.lo, E1 = ab.hi;
     const float4 E2 = __ldg(&tris[pos].c);
     // h = direction x edge2
@@ -259,7 +259,7 @@ __device__ __forceinline__ int4 as_int4(const float4 f) {
 }
 __device__ __forceinline__ MNode mnode_load_global(const float4* __restrict__ nodes, int cur) {
     const float4* n = nodes + (size_t)cur * 8;
-    const F8 q0 = ld256(n), q1 = ld256(n + 2), q2 = ld256(n + 4), q3 = ld256(n + 6);
+    const F8 q0 = ld256_node(n), q1 = ld256_node(n + 2), q2 = ld256_node(n + 4), q3 = ld256_node(n + 6);
     return MNode{q0.lo, q0.hi, q1.lo, q1.hi, q2.lo, q2.hi, as_int4(q3.lo), as_int4(q3.hi)};
 }
 
@@ -552,7 +552,7 @@ __device__ __forceinline__ bool lane_advance(const DeviceTree& tree, const float
 // step nearly all lanes hold a triangle, so some lane needs every instruction anyway and branches only add
 // divergence bookkeeping.  Returns true when the candidate was accepted with t < ray.t.
 __device__ __forceinline__ bool tri_candidate_flat(const TriRec* __restrict__ tris, int pos, RayRegs& r) {
-    const F8 ab = ld256(&tris[pos].a);
+    const F8 ab = ld256_tri(&tris[pos].a);
     const float4 A = ab.lo, E1 = ab.hi;
     const float4 E2 = __ldg(&tris[pos].c);
     const float hx = fsub(fmul(r.dy, E2.z), fmul(E2.y, r.dz));
@@ -1383,7 +1383,7 @@ __device__ __forceinline__ uint32_t mbvh_slabs_packet(const MNode& nd, const Pac
 // Returns the 4-bit mask of rays that accepted the candidate with t < packet.t[i].
 __device__ __forceinline__ uint32_t tri_candidate_packet(const TriRec* __restrict__ tris, int pos, float t_min,
                                                          const RTRayPacket4* __restrict__ rec, Packet& k) {
-    const F8 ab = ld256(&tris[pos].a);
+    const F8 ab = ld256_tri(&tris[pos].a);
     const float4 A = ab.lo, E1 = ab.hi;
     const float4 E2 = __ldg(&tris[pos].c);
     const uint32_t id = __float_as_uint(A.w);
