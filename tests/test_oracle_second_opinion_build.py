@@ -349,3 +349,40 @@ def test_python_collapse_produces_the_oracles_bytes(O, teapot, teapot_trees, bui
     for key in ("min_x", "max_x", "min_y", "max_y", "min_z", "max_z"):
         assert got[key].view(np.uint32).tobytes() == np.ascontiguousarray(want.nodes[key]).view(np.uint32).tobytes(), key
     assert np.array_equal(got["children"], want.nodes["children"]) and np.array_equal(got["counts"], want.nodes["counts"])
+
+
+# ---- refit ------------------------------------------------------------------------------------------------------------
+# Followed source: Bvh::refit  src/bvh.rs:176-205 — reverse sweep (children sit behind their parent), leaf = union of its
+# primitives' new boxes, inner = union of its two children, each padded by 1e-4.  The reference then assigns the fresh Aabb to
+# node.bounds, which also zeroes count / left_first (Aabb::new has extras = 0) and leaves a destroyed tree; like the oracle and
+# the GPU this restatement keeps the topology fields (the one deliberate deviation).
+def refit(nodes, indices, new_min, new_max):
+    mn, mx = np.array(nodes["min"], dtype=F), np.array(nodes["max"], dtype=F)
+    delta = F(0.0001)
+    for i in range(len(nodes) - 1, -1, -1):
+        bmn, bmx = _empty()
+        lf, cnt = int(nodes["left_first"][i]), int(nodes["count"][i])
+        if lf >= 0:
+            if cnt >= 0:
+                for k in range(cnt):
+                    p = int(indices[lf + k])
+                    bmn, bmx = np.minimum(bmn, new_min[p]), np.maximum(bmx, new_max[p])
+            else:
+                bmn, bmx = np.minimum(bmn, mn[lf]), np.maximum(bmx, mx[lf])
+                bmn, bmx = np.minimum(bmn, mn[lf + 1]), np.maximum(bmx, mx[lf + 1])
+            bmn, bmx = bmn - delta, bmx + delta
+        mn[i], mx[i] = bmn, bmx
+    return mn, mx
+
+
+@pytest.mark.parametrize("builder", ["sah", "locb"])
+def test_python_refit_produces_the_oracles_bytes(O, W, teapot, teapot_trees, builder):
+    bvh, _ = teapot_trees[builder]
+    moved = teapot["tris"].copy()
+    moved[:, :, 1] += (0.05 * np.sin(7.0 * moved[:, :, 0])).astype(np.float32)  # the same triangles, wobbling
+    new_aabbs, _ = O.prims_from_triangles(moved)
+    want = bvh.refit(new_aabbs)
+    mn, mx = refit(bvh.nodes, bvh.indices, np.ascontiguousarray(new_aabbs["min"], dtype=F), np.ascontiguousarray(new_aabbs["max"], dtype=F))
+    assert mn.view(np.uint32).tobytes() == np.ascontiguousarray(want.nodes["min"]).view(np.uint32).tobytes()
+    assert mx.view(np.uint32).tobytes() == np.ascontiguousarray(want.nodes["max"]).view(np.uint32).tobytes()
+    assert np.array_equal(want.nodes["count"], bvh.nodes["count"]) and np.array_equal(want.nodes["left_first"], bvh.nodes["left_first"])
