@@ -361,3 +361,40 @@ def test_python_restatement_agrees_on_any_hit_and_packets(O, W, teapot, teapot_t
         same = (got["t"].view(np.uint32) == want["t"].view(np.uint32)).all(axis=1) & (got["prim"] == want["prim"]).all(axis=1)
         bad = np.nonzero(~same)[0]
         assert len(bad) == 0, f"{builder}/{kind} packets: {len(bad)} of {len(packets)} differ, first {bad[:5]}: {got[bad[:2]]} vs {want[bad[:2]]}"
+
+
+@pytest.mark.parametrize("leaf,kind", [(1, "sah"), (3, "sah"), (8, "sah"), (1, "locb")])
+def test_second_opinion_on_duplicated_triangles_and_wide_leaves(O, W, leaf, kind):
+    """Exactly equal t from duplicated triangles (the lowest id must be reported, whatever order the leaves come in) and
+    leaves with several primitives: the two restatements must still agree bit for bit."""
+    tris = W.soup(240, seed=0x71E5).astype(np.float32)
+    tris[160:240] = tris[0:80]  # 80 exact duplicates with higher ids
+    aabbs, centers = O.prims_from_triangles(tris)
+    rc, bvh = O.build(O.BINNED_SAH if kind == "sah" else O.LOCB, aabbs, centers, leaf)
+    assert rc == 0
+    m = bvh.collapse()
+    rays = np.concatenate([W.camera_rays(W.soup_camera(24, 24)), W.random_rays(400, *W.bounds(tris), seed=5)])
+    T = [[[F(c) for c in v] for v in t] for t in tris]
+    brute = O.brute_force(tris, rays)
+    for name, nodes, idx, tree in (("bvh", bvh.nodes, bvh.indices, bvh), ("mbvh", m.nodes, m.indices, m)):
+        want = O.trace(tree, tris, rays, threads=1)[0]
+        got = np.zeros(len(rays), dtype=want.dtype)
+        for k, r in enumerate(rays):
+            ray = _ray_new([F(x) for x in r["origin"]], [F(x) for x in r["direction"]], F(r["t_min"]), F(r["t"]))
+            with np.errstate(all="ignore"):
+                (_trace_bvh if name == "bvh" else _trace_mbvh)(nodes, idx, T, ray)
+            got["t"][k], got["prim"][k] = ray["t"], ray["prim"]
+        assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)) and np.array_equal(got["prim"], want["prim"]), name
+        hit = want["prim"] != NO_HIT
+        assert hit.any() and (want["prim"][hit] < 160).all(), "a duplicate's higher id was reported"
+        if kind == "locb":  # conservative boxes: the walk finds what brute force finds
+            assert np.array_equal(want, brute), name
+    packets = W.pack4(rays[: len(rays) // 4 * 4])
+    for name, nodes, idx, tree in (("bvh", bvh.nodes, bvh.indices, bvh), ("mbvh", m.nodes, m.indices, m)):
+        want = O.trace_packets(tree, tris, packets, threads=1)[0]
+        for k, pk in enumerate(packets):
+            P = _packet_new(pk)
+            with np.errstate(all="ignore"):
+                (_trace_bvh_packet if name == "bvh" else _trace_mbvh_packet)(nodes, idx, T, P)
+            assert np.array_equal(np.array(P["t"], dtype=F).view(np.uint32), want["t"][k].view(np.uint32)), (name, k)
+            assert np.array_equal(np.array(P["prim"], dtype=np.uint32), want["prim"][k]), (name, k)
