@@ -511,3 +511,20 @@ def test_packet_calls_with_oddly_aligned_device_buffers(A, O, W, teapot, teapot_
         assert not sc.stack_overflowed()
     finally:
         sc.free()
+
+
+@pytest.mark.parametrize("leaf,kind", [(1, "sah"), (4, "sah"), (1, "locb")])
+def test_duplicated_triangles_report_the_lowest_id(A, O, W, leaf, kind):
+    """Exactly equal t from duplicated triangles: every flavour (single / packet, closest / any, both trees, sorted launches)
+    reports the lowest id like the oracle, whatever order the leaves are reached in; multi-primitive leaves included."""
+    tris = W.soup(6_000, seed=0x71E5).astype(np.float32)
+    tris[4_000:6_000] = tris[0:2_000]  # 2 000 exact duplicates with higher ids
+    aabbs, centers = O.prims_from_triangles(tris)
+    rc, bvh = O.build(O.BINNED_SAH if kind == "sah" else O.LOCB, aabbs, centers, leaf)
+    assert rc == 0
+    m = bvh.collapse()
+    rays = np.concatenate([W.camera_rays(W.soup_camera(160, 160)), W.random_rays(30_000, *W.bounds(tris), seed=9)])
+    want = O.trace(m, tris, rays)[0]
+    hit = want["prim"] != A.NO_HIT
+    assert hit.mean() > 0.2 and (want["prim"][hit] < 4_000).all()
+    _check_all_paths(A, O, W, tris, bvh, m, rays, f"duplicates leaf={leaf} {kind}")
